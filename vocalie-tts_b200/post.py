@@ -1,0 +1,315 @@
+"""Host-side mirror of the reference's post-processing interface, running on the GPU.
+
+Same names, argument meaning and error behaviour as the reference functions it replaces
+(backend/shared/tts_pipeline.py:114-274, backend/shared/audio_edit.py:16-79); the arithmetic
+runs in ``csrc/vt_post.cu`` through the C ABI.  There is no CPU fallback: without the CUDA
+extension or a CUDA device every call raises ``BackendUnavailableError``.
+
+Two layers:
+  * device layer  - ``post_process_device`` & friends: torch CUDA tensors in/out, no host sync
+    except the optional read-back of the per-segment results.  Used by the pipeline/bench.
+  * reference-facing layer - ``_find_active_range``, ``_snap_zero_crossing``, ``_fade_in``,
+    ``_fade_out``, ``_apply_inter_chunk_gap``, ``minimal_post_process``, ``apply_minimal_edit``:
+    numpy arrays / WAV paths in and out, exactly like the reference.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from pathlib import Path
+from typing import Any, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import PostParams, check
+from .errors import BackendUnavailableError
+from . import wav as _wav
+
+SILENCE_THRESHOLD = 0.002   # reference backend/shared/audio_defaults.py:3
+SILENCE_MIN_MS = 20         # reference backend/shared/audio_defaults.py:4
+TARGET_SR = 24000           # reference backend/shared/tts_pipeline.py:26
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise BackendUnavailableError("no CUDA device: the B200 path has no CPU fallback")
+    return torch
+
+
+def _ms_to_frames(sr: int, ms) -> int:
+    return max(0, int(sr * (int(ms) / 1000.0)))   # tts_pipeline.py:173-174,232,238,246
+
+
+def _ptr(t) -> int:
+    return 0 if t is None else int(t.data_ptr())
+
+
+def _stream(torch) -> int:
+    return int(torch.cuda.current_stream().cuda_stream)
+
+
+@dataclass
+class PostResult:
+    out: Any                 # torch CUDA tensor (float32 or int16), capacity >= total
+    total: Optional[int]     # total output samples (None when not read back)
+    results: Optional[np.ndarray]  # [n_seg, 8] float64: start,end,peak,scale,dst,len,peak_used,-
+
+
+class _Workspace:
+    """Grow-only device scratch shared by the post calls of one process (guarded by the GIL;
+    kernels are stream-ordered)."""
+    buf = None
+
+    @classmethod
+    def get(cls, torch, nbytes: int):
+        if cls.buf is None or cls.buf.numel() < nbytes:
+            cls.buf = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, device="cuda")
+        return cls.buf
+
+
+def make_params(*, sr=TARGET_SR, trim=0, silence_threshold=SILENCE_THRESHOLD, min_silence_frames=0,
+                snap_radius=-1, fade_in_frames=0, fade_out_frames=0, stitch=0, gap_frames=0,
+                normalize=0, clip=0, target_peak=1.0, concat=1, out_pcm16=0) -> PostParams:
+    return PostParams(int(sr), int(trim), float(silence_threshold), int(min_silence_frames),
+                      int(snap_radius), int(fade_in_frames), int(fade_out_frames), int(stitch),
+                      int(gap_frames), int(normalize), int(clip), float(target_peak), int(concat),
+                      int(out_pcm16))
+
+
+def _seg_arrays(torch, seg_off):
+    seg_np = np.ascontiguousarray(seg_off, dtype=np.int64)
+    if seg_np.ndim != 1 or seg_np.size < 1 or np.any(np.diff(seg_np) < 0) or seg_np[0] != 0:
+        raise ValueError("seg_off must be a non-decreasing int64 array starting at 0")
+    n_seg = seg_np.size - 1
+    n_samples = int(seg_np[-1])
+    max_len = int(np.max(np.diff(seg_np))) if n_seg else 0
+    seg_dev = torch.from_numpy(seg_np).cuda()
+    return seg_np, seg_dev, n_seg, n_samples, max_len
+
+
+def post_process_device(audio, seg_off, params: PostParams, *, out=None, range_override=None,
+                        peak_override=None, read_back=True) -> PostResult:
+    """Run analyse + write on device tensors.  ``audio``: 1-D float32 CUDA tensor holding all
+    segments; ``seg_off``: int64[n_seg+1] (host).  Output capacity is the worst case
+    ``n_samples + (n_seg-1)*gap``."""
+    torch = _torch()
+    lib = _lib.load_library()
+    if audio.dtype != torch.float32 or audio.dim() != 1 or not audio.is_cuda:
+        raise ValueError("audio must be a 1-D float32 CUDA tensor")
+    audio = audio.contiguous()
+    if audio.data_ptr() % 16:
+        audio = audio.clone()
+    seg_np, seg_dev, n_seg, n_samples, max_len = _seg_arrays(torch, seg_off)
+    if n_samples > audio.numel():
+        raise ValueError("seg_off exceeds the audio buffer")
+    cap = n_samples + max(n_seg - 1, 0) * max(int(params.gap_frames), 0) if params.concat else n_samples
+    odt = torch.int16 if params.out_pcm16 else torch.float32
+    if out is None:
+        out = torch.empty(max(cap, 4), dtype=odt, device="cuda") if params.concat else \
+            torch.zeros(max(cap, 4), dtype=odt, device="cuda")
+    elif out.dtype != odt or out.numel() < cap or not out.is_cuda:
+        raise ValueError("out tensor has the wrong dtype/size")
+    ws_bytes = int(lib.vt_post_workspace_bytes(n_seg, n_samples))
+    ws = _Workspace.get(torch, ws_bytes)
+    res = torch.empty((max(n_seg, 1), _lib.POST_RESULT_STRIDE), dtype=torch.float64, device="cuda")
+    tot = torch.zeros(1, dtype=torch.int64, device="cuda")
+    st = _stream(torch)
+    check(lib.vt_post_analyze(_ptr(audio), _ptr(seg_dev), n_seg, n_samples, max_len, C.byref(params),
+                              _ptr(range_override), _ptr(ws), ws.numel(), st), "vt_post_analyze")
+    check(lib.vt_post_write(_ptr(audio), _ptr(seg_dev), n_seg, n_samples, max_len, C.byref(params),
+                            _ptr(peak_override), _ptr(out), out.numel(), _ptr(res), _ptr(tot),
+                            _ptr(ws), ws.numel(), st), "vt_post_write")
+    if not read_back:
+        return PostResult(out, None, None)
+    res_h = res.cpu().numpy()[:n_seg]
+    return PostResult(out, int(tot.item()), res_h)
+
+
+# ------------------------------------------------------------------------- reference-facing layer
+def _as_f32(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float32).reshape(-1))
+
+
+def _find_active_range(mono: np.ndarray, *, threshold: float, min_silence_frames: int) -> tuple[int, int]:
+    """GPU ``_find_active_range`` (reference tts_pipeline.py:192-209)."""
+    torch = _torch()
+    lib = _lib.load_library()
+    x = _as_f32(mono)
+    if x.size == 0:
+        return 0, 0
+    xd = torch.from_numpy(x).cuda()
+    seg_np, seg_dev, n_seg, n_samples, max_len = _seg_arrays(torch, [0, x.size])
+    ws = _Workspace.get(torch, int(lib.vt_post_workspace_bytes(1, n_samples)))
+    rng = torch.empty(2, dtype=torch.int64, device="cuda")
+    check(lib.vt_find_active_range(_ptr(xd), _ptr(seg_dev), 1, n_samples, max_len, float(threshold),
+                                   int(min_silence_frames), _ptr(rng), _ptr(ws), ws.numel(), _stream(torch)),
+          "vt_find_active_range")
+    s, e = rng.cpu().tolist()
+    return int(s), int(e)
+
+
+def _snap_zero_crossing(audio: np.ndarray, idx: int, *, radius_samples: int) -> int:
+    """GPU ``_snap_zero_crossing`` (reference tts_pipeline.py:114-137)."""
+    torch = _torch()
+    lib = _lib.load_library()
+    x = _as_f32(audio)
+    if x.size == 0:
+        return idx
+    xd = torch.from_numpy(x).cuda()
+    seg_np, seg_dev, *_ = _seg_arrays(torch, [0, x.size])
+    i_in = torch.tensor([int(idx)], dtype=torch.int64, device="cuda")
+    i_out = torch.empty(1, dtype=torch.int64, device="cuda")
+    check(lib.vt_snap_zero_crossing(_ptr(xd), _ptr(seg_dev), 1, _ptr(i_in), int(radius_samples),
+                                    _ptr(i_out), _stream(torch)), "vt_snap_zero_crossing")
+    return int(i_out.item())
+
+
+def _fade(audio: np.ndarray, fade_frames: int, which: str) -> np.ndarray:
+    if audio.size == 0:
+        return audio
+    f = max(0, min(int(fade_frames), len(audio)))
+    if f == 0:
+        return audio
+    torch = _torch()
+    x = _as_f32(audio)
+    prm = make_params(fade_in_frames=f if which == "in" else 0, fade_out_frames=f if which == "out" else 0)
+    r = post_process_device(torch.from_numpy(x).cuda(), [0, x.size], prm, read_back=False)
+    audio[...] = r.out[:x.size].cpu().numpy().reshape(audio.shape)   # in place, like the reference
+    return audio
+
+
+def _fade_in(audio: np.ndarray, fade_frames: int) -> np.ndarray:
+    """GPU ``_fade_in`` (reference tts_pipeline.py:140-148); mutates and returns ``audio``."""
+    return _fade(audio, fade_frames, "in")
+
+
+def _fade_out(audio: np.ndarray, fade_frames: int) -> np.ndarray:
+    """GPU ``_fade_out`` (reference tts_pipeline.py:151-159); mutates and returns ``audio``."""
+    return _fade(audio, fade_frames, "out")
+
+
+def stitch_params(n_chunks: int, *, sr: int, gap_ms: int, fade_ms: int = 10, **kw) -> PostParams:
+    """Parameter block with ``_apply_inter_chunk_gap`` semantics (tts_pipeline.py:162-189):
+    ``gap_ms <= 0`` or a single chunk is a plain concatenate without fades."""
+    if gap_ms <= 0 or n_chunks <= 1:
+        return make_params(sr=sr, stitch=1, gap_frames=0, concat=1, **kw)
+    fade = _ms_to_frames(sr, fade_ms)
+    return make_params(sr=sr, stitch=1, gap_frames=_ms_to_frames(sr, gap_ms), fade_in_frames=fade,
+                       fade_out_frames=fade, concat=1, **kw)
+
+
+def _apply_inter_chunk_gap(audio_chunks: Sequence[np.ndarray], *, sr: int, gap_ms: int, fade_ms: int = 10) -> np.ndarray:
+    """GPU ``_apply_inter_chunk_gap`` (reference tts_pipeline.py:162-189)."""
+    if not audio_chunks:
+        return np.zeros(0, dtype=np.float32)
+    torch = _torch()
+    chunks = [_as_f32(c) for c in audio_chunks]
+    lens = [c.size for c in chunks]
+    seg_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    flat = np.concatenate(chunks) if chunks else np.zeros(0, np.float32)
+    if flat.size == 0:
+        prm0 = stitch_params(len(chunks), sr=sr, gap_ms=gap_ms, fade_ms=fade_ms)
+        return np.zeros(max(len(chunks) - 1, 0) * int(prm0.gap_frames), dtype=np.float32)
+    prm = stitch_params(len(chunks), sr=sr, gap_ms=gap_ms, fade_ms=fade_ms)
+    r = post_process_device(torch.from_numpy(flat).cuda(), seg_off, prm)
+    return r.out[:r.total].cpu().numpy()
+
+
+def minimal_post_process(raw_path, processed_path, *, zero_cross_radius_ms: int = 10, fade_ms: int = 10,
+                         silence_threshold: float = SILENCE_THRESHOLD, silence_min_ms: int = SILENCE_MIN_MS,
+                         normalize_peak_db: float = -1.0) -> dict[str, Any]:
+    """GPU ``minimal_post_process`` (reference tts_pipeline.py:212-274): trim + zero-cross snap +
+    fades + peak normalise, PCM_16 WAV in / PCM_16 WAV out, same meta dict."""
+    raw_path = Path(raw_path)
+    processed_path = Path(processed_path)
+    if raw_path.resolve() == processed_path.resolve():
+        raise ValueError("Le traitement doit écrire dans un fichier différent du raw.")
+    torch = _torch()
+    lib = _lib.load_library()
+    q, sr = _wav.read_pcm16(raw_path)
+    n = q.size
+    fade = int(sr * (int(fade_ms) / 1000.0))
+    prm = make_params(sr=sr, trim=1, silence_threshold=float(silence_threshold),
+                      min_silence_frames=int(sr * (int(silence_min_ms) / 1000.0)),
+                      snap_radius=int(sr * (int(zero_cross_radius_ms) / 1000.0)),
+                      fade_in_frames=fade, fade_out_frames=fade, normalize=1,
+                      target_peak=float(10 ** (float(normalize_peak_db) / 20.0)), out_pcm16=1)
+    start = end = 0
+    scale, peak = 1.0, 0.0
+    out_q = np.zeros(0, np.int16)
+    if n:
+        qd = torch.from_numpy(q).cuda()
+        x = torch.empty(n + 4, dtype=torch.float32, device="cuda")
+        check(lib.vt_pcm16_decode(_ptr(qd), _ptr(x), n, _stream(torch)), "vt_pcm16_decode")
+        r = post_process_device(x, [0, n], prm)
+        start, end, peak, scale = int(r.results[0, 0]), int(r.results[0, 1]), float(r.results[0, 2]), float(r.results[0, 3])
+        out_q = r.out[:r.total].cpu().numpy()
+    _wav.write_pcm16(processed_path, out_q, sr)
+    return {
+        "trim": {"start_sample": int(start), "end_sample": int(end)},
+        "fade_ms": int(fade_ms),
+        "zero_cross_radius_ms": int(zero_cross_radius_ms),
+        "silence_threshold": float(silence_threshold),
+        "silence_min_ms": int(silence_min_ms),
+        "normalize_peak_db": float(normalize_peak_db),
+        "normalize_scale": float(scale),
+        "peak_before": float(peak),
+    }
+
+
+def apply_minimal_edit(raw_path: Path, output_path: Path, *, trim_enabled: bool, normalize_enabled: bool,
+                       target_dbfs: float, silence_threshold: float = SILENCE_THRESHOLD,
+                       silence_min_ms: int = SILENCE_MIN_MS, zero_cross_radius_ms: int = 10,
+                       fade_ms: int = 10) -> dict[str, Any]:
+    """GPU ``apply_minimal_edit`` (reference audio_edit.py:16-79): optional trim (no snap, no
+    fades) + optional peak normalise + clip, written as PCM_16."""
+    raw_path = Path(raw_path)
+    output_path = Path(output_path)
+    if raw_path.resolve() == output_path.resolve():
+        raise ValueError("Output must be different from input.")
+    torch = _torch()
+    lib = _lib.load_library()
+    q, sr = _wav.read_pcm16(raw_path)
+    n = q.size
+    target_peak = 10 ** (float(target_dbfs) / 20.0)
+    prm = make_params(sr=sr, trim=1 if trim_enabled else 0, silence_threshold=float(silence_threshold),
+                      min_silence_frames=int(sr * (int(silence_min_ms) / 1000.0)), snap_radius=-1,
+                      normalize=1, clip=1, target_peak=float(target_peak), out_pcm16=1)
+    # the peak is always measured (peak_before is reported even when normalisation is off);
+    # the gain is only applied when requested
+    trimmed = False
+    normalized = False
+    peak_before, gain = 0.0, 1.0
+    out_q = np.zeros(0, np.int16)
+    if n:
+        qd = torch.from_numpy(q).cuda()
+        x = torch.empty(n + 4, dtype=torch.float32, device="cuda")
+        check(lib.vt_pcm16_decode(_ptr(qd), _ptr(x), n, _stream(torch)), "vt_pcm16_decode")
+        if not normalize_enabled:
+            # analyse with normalize=1 to obtain the peak, write with unit gain
+            one = torch.zeros(1, dtype=torch.float32, device="cuda")  # peak_override 0 -> no gain applied
+            r = post_process_device(x, [0, n], prm, peak_override=one)
+        else:
+            r = post_process_device(x, [0, n], prm)
+        start, end = int(r.results[0, 0]), int(r.results[0, 1])
+        trimmed = bool(trim_enabled and 0 <= start < end <= n)
+        peak_before = float(r.results[0, 2])
+        if normalize_enabled and peak_before > 0.0 and target_peak > 0.0:
+            gain = float(r.results[0, 3])
+            normalized = True
+        out_q = r.out[:r.total].cpu().numpy()
+    if normalized:
+        peak_after = float(min(np.float32(peak_before) * np.float32(gain), np.float32(1.0)))
+    else:
+        peak_after = float(min(np.float32(peak_before), np.float32(1.0)))
+    _wav.write_pcm16(output_path, out_q, sr)
+    return {
+        "trimmed": trimmed,
+        "normalized": normalized,
+        "target_dbfs": float(target_dbfs),
+        "peak_before": peak_before,
+        "peak_after": peak_after,
+        "gain": gain,
+    }
