@@ -130,8 +130,9 @@ int vt_pcm16_decode(const int16_t* in, float* out, int64_t n, void* stream);
 typedef struct vt_hift vt_hift;   /* opaque handle: packed weights + layer plan */
 
 /* Operand precision of the tensor-core convolutions (accumulation is always fp32). */
-#define VT_OPERAND_FP16 0
-#define VT_OPERAND_BF16 1
+#define VT_OPERAND_FP16 0   /* fp16 operands on tcgen05 (default: meets the 60 dB parity bar) */
+#define VT_OPERAND_BF16 1   /* bf16 operands on tcgen05 */
+#define VT_OPERAND_FP32 2   /* exact path: every layer in fp32 on CUDA cores */
 
 /* One entry of the flat weight table handed to vt_hift_create: upstream state-dict name,
  * HOST float32 data with weight-norm already folded (w = g*v/||v||), and shape

@@ -19,6 +19,7 @@ _lib = None
 VT_OK = 0
 VT_OPERAND_FP16 = 0
 VT_OPERAND_BF16 = 1
+VT_OPERAND_FP32 = 2
 POST_RESULT_STRIDE = 8
 
 

@@ -1,10 +1,617 @@
-// HiFT vocoder entry points (placeholder while the kernels land; replaced by the real path).
-#include "vt_common.cuh"
-extern "C" {
-int vt_hift_create(const vt_tensor*, int, int, vt_hift**) { vt::set_error("vt_hift: not built yet"); return VT_ERR_UNSUPPORTED; }
-void vt_hift_destroy(vt_hift*) {}
-int64_t vt_hift_workspace_bytes(const vt_hift*, int, int64_t, int64_t) { return VT_ERR_UNSUPPORTED; }
-int vt_hift_forward(vt_hift*, const float*, const int32_t*, int, const float*, const float*, const float*, uint64_t,
-                    float*, void*, int64_t, void*) { vt::set_error("vt_hift: not built yet"); return VT_ERR_UNSUPPORTED; }
-int64_t vt_hift_read_tap(vt_hift*, const char*, int, float*, int64_t, void*, void*) { return VT_ERR_UNSUPPORTED; }
+// HiFT vocoder: handle (weight packing), per-batch plan (ragged packing, tile tables), forward
+// orchestration and inspection taps.  Upstream chatterbox-tts==0.1.6 hifigan.py
+// HiFTGenerator.inference / decode + s3gen.py trim_fade, reached in the reference through
+// tts_backends/chatterbox_impl.py:189.
+#include "vt_hift.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+
+namespace vt {
+
+int launch_conv_tc(const ConvArgs& a, const ConvLayer& L, int act_elem, const void* tc_tiles, int n_tc_tiles,
+                   int tile_rows, cudaStream_t st);
+int pack_conv_tc(ConvLayer& L, const std::vector<float>& w_kcico, int act_elem, std::vector<void*>& allocs);
+bool conv_tc_supported(const ConvLayer& L);
+int conv_tc_tile_rows(const ConvLayer& L);
+
+namespace {
+
+const int kUpRates[3] = {8, 5, 3};
+const int kUpKernels[3] = {16, 11, 7};
+const int kRbKernels[3] = {3, 7, 11};
+const int kRbDil[3] = {1, 3, 5};
+const int kSrcRbKernels[3] = {7, 7, 11};
+const int kSdK[3] = {30, 6, 1}, kSdS[3] = {15, 3, 1}, kSdP[3] = {7, 1, 0};
+const int kLevelMul[3] = {8, 40, 120};
+
+struct HostTensor {
+  const float* data;
+  std::vector<int64_t> shape;
+  int64_t numel() const {
+    int64_t n = 1;
+    for (auto s : shape) n *= s;
+    return n;
+  }
+};
+
+}  // namespace
+
+struct Plan {
+  int B = 0;
+  std::vector<int> T;
+  long long total_T = 0;
+  int T_max = 0;
+  long long rows[3] = {0, 0, 0};            // packed rows per level (incl. gaps, excl. slack)
+  // device tables
+  int* d_T = nullptr;
+  int* d_mel_off = nullptr;
+  long long* d_off[3] = {nullptr, nullptr, nullptr};
+  ConvTile* d_tiles = nullptr;
+  // tile-table segments (offset, count) inside d_tiles
+  struct Seg { int off = 0, n = 0; };
+  Seg mel, up[3], sd[3], lvl[3];
+  Seg tc[3][2];                             // tensor-core tiles per level, [0]: 128 rows, [1]: 256 rows
+  std::vector<long long> h_off[3];
+  std::vector<int> h_mel_off;
+  void* d_block = nullptr;
+  size_t d_block_bytes = 0;
+};
+
+struct Workspace {
+  float *f0a, *f0b, *f0, *s, *spec, *xpre, *post;
+  double* phase_base;
+  float *U[3], *S[3], *X[3], *XR[3], *Y[3];
+  void *A[3][4];                            // activation copies A0, A1, A2, Q per level
+  long long cap_rows[3];
+  size_t bytes;
+};
+
+}  // namespace vt
+
+using namespace vt;
+
+struct vt_hift {
+  int act_elem = ELEM_F32;
+  bool use_tc = false;
+  std::vector<void*> allocs;
+  ConvLayer conv_pre, ups[3], sdown[3], src_c1[3][3], src_c2[3][3], rb_c1[9][3], rb_c2[9][3], conv_post, f0c[5];
+  float *src_a1[3][3], *src_a2[3][3], *rb_a1[9][3], *rb_a2[9][3];
+  float *f0_w = nullptr, *f0_b = nullptr, *lin_w = nullptr, *lin_b = nullptr, *trim_fade = nullptr;
+  Plan plan;
+  Workspace ws{};
+  bool have_forward = false;
+};
+
+namespace vt {
+namespace {
+
+size_t elem_size(int e) { return e == ELEM_F32 ? 4 : 2; }
+
+int dev_upload(vt_hift* h, const void* src, size_t bytes, void** out) {
+  void* p = nullptr;
+  VT_CUDA_OK(cudaMalloc(&p, bytes ? bytes : 4));
+  h->allocs.push_back(p);
+  if (bytes) VT_CUDA_OK(cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice));
+  *out = p;
+  return VT_OK;
 }
+
+// conv weight [cout][cin][k] -> [k][cin_pad][cout_pad]
+int pack_conv(vt_hift* h, ConvLayer& L, const std::map<std::string, HostTensor>& tab, const std::string& name,
+              int cin, int cout, int k, int dil, int stride, int pad, int cin_pad, int cout_pad) {
+  auto wi = tab.find(name + ".weight"), bi = tab.find(name + ".bias");
+  VT_REQUIRE(wi != tab.end() && bi != tab.end(), "missing tensor %s.weight/.bias", name.c_str());
+  const HostTensor& W = wi->second;
+  VT_REQUIRE(W.shape.size() == 3 && W.shape[0] == cout && W.shape[1] == cin && W.shape[2] == k,
+             "%s.weight has the wrong shape (want [%d,%d,%d])", name.c_str(), cout, cin, k);
+  VT_REQUIRE(bi->second.numel() == cout, "%s.bias has the wrong size", name.c_str());
+  std::vector<float> w((size_t)k * cin_pad * cout_pad, 0.0f), b(cout_pad, 0.0f);
+  for (int co = 0; co < cout; ++co)
+    for (int ci = 0; ci < cin; ++ci)
+      for (int j = 0; j < k; ++j)
+        w[((size_t)j * cin_pad + ci) * cout_pad + co] = W.data[((size_t)co * cin + ci) * k + j];
+  for (int co = 0; co < cout; ++co) b[co] = bi->second.data[co];
+  L.name = name;
+  L.cin = cin_pad; L.cout = cout_pad; L.k = k; L.dil = dil; L.stride = stride; L.pad = pad;
+  L.out_mul = 1; L.phase_c = cout_pad;
+  L.flops_per_step = 2.0 * cin * cout * k;
+  int rc = dev_upload(h, w.data(), w.size() * 4, (void**)&L.w);
+  if (rc) return rc;
+  rc = dev_upload(h, b.data(), b.size() * 4, (void**)&L.bias);
+  if (rc) return rc;
+  if (h->use_tc && conv_tc_supported(L)) return pack_conv_tc(L, w, h->act_elem, h->allocs);
+  return VT_OK;
+}
+
+// ConvTranspose1d weight [cin][cout][k], stride s, padding p -> 3-tap conv with cout' = s*cout:
+//   out[s*q + r] = sum_{d in -1..1} x[q + d] . W[:, :, r + p - s*d]
+int pack_convT(vt_hift* h, ConvLayer& L, const std::map<std::string, HostTensor>& tab, const std::string& name,
+               int cin, int cout, int k, int s, int p) {
+  auto wi = tab.find(name + ".weight"), bi = tab.find(name + ".bias");
+  VT_REQUIRE(wi != tab.end() && bi != tab.end(), "missing tensor %s.weight/.bias", name.c_str());
+  const HostTensor& W = wi->second;
+  VT_REQUIRE(W.shape.size() == 3 && W.shape[0] == cin && W.shape[1] == cout && W.shape[2] == k,
+             "%s.weight has the wrong shape (want [%d,%d,%d])", name.c_str(), cin, cout, k);
+  const int cN = s * cout;
+  std::vector<float> w((size_t)3 * cin * cN, 0.0f), b(cN, 0.0f);
+  for (int d = -1; d <= 1; ++d)
+    for (int r = 0; r < s; ++r) {
+      const int j = r + p - s * d;
+      if (j < 0 || j >= k) continue;
+      for (int ci = 0; ci < cin; ++ci)
+        for (int co = 0; co < cout; ++co)
+          w[((size_t)(d + 1) * cin + ci) * cN + r * cout + co] = W.data[((size_t)ci * cout + co) * k + j];
+    }
+  // every tap j in [0, k) must be reachable with d in {-1, 0, 1}
+  for (int r = 0; r < s; ++r)
+    for (int d = -3; d <= 3; ++d) {
+      const int j = r + p - s * d;
+      VT_REQUIRE(!(j >= 0 && j < k) || (d >= -1 && d <= 1), "%s: transposed conv does not fit 3 taps", name.c_str());
+    }
+  for (int r = 0; r < s; ++r)
+    for (int co = 0; co < cout; ++co) b[r * cout + co] = bi->second.data[co];
+  L.name = name;
+  L.cin = cin; L.cout = cN; L.k = 3; L.dil = 1; L.stride = 1; L.pad = 1;
+  L.out_mul = s; L.phase_c = cout;
+  L.flops_per_step = 2.0 * cin * cout * k;   // per INPUT step (= per s output steps)
+  int rc = dev_upload(h, w.data(), w.size() * 4, (void**)&L.w);
+  if (rc) return rc;
+  return dev_upload(h, b.data(), b.size() * 4, (void**)&L.bias);
+}
+
+int upload_vec(vt_hift* h, const std::map<std::string, HostTensor>& tab, const std::string& name, int64_t n, float** out) {
+  auto it = tab.find(name);
+  VT_REQUIRE(it != tab.end(), "missing tensor %s", name.c_str());
+  VT_REQUIRE(it->second.numel() == n, "%s has %lld elements, want %lld", name.c_str(), (long long)it->second.numel(), (long long)n);
+  return dev_upload(h, it->second.data, (size_t)n * 4, (void**)out);
+}
+
+void add_tiles(std::vector<ConvTile>& v, Plan::Seg& seg, int B, const long long* in_row0, const int* in_len,
+               const long long* out_row0, const int* out_len, int tile) {
+  seg.off = (int)v.size();
+  for (int b = 0; b < B; ++b)
+    for (int q0 = 0; q0 < out_len[b]; q0 += tile) {
+      ConvTile t;
+      t.in_row0 = in_row0[b]; t.out_row0 = out_row0[b];
+      t.in_len = in_len[b]; t.out_len = out_len[b];
+      t.q0 = q0; t.n = std::min(tile, out_len[b] - q0);
+      v.push_back(t);
+    }
+  seg.n = (int)v.size() - seg.off;
+}
+
+int build_plan(vt_hift* h, const int32_t* T, int B, cudaStream_t st) {
+  Plan& P = h->plan;
+  if (P.B == B && (int)P.T.size() == B && std::equal(P.T.begin(), P.T.end(), T)) return VT_OK;
+  P.B = B;
+  P.T.assign(T, T + B);
+  P.total_T = 0;
+  P.T_max = 0;
+  P.h_mel_off.resize(B);
+  std::vector<long long> melrow(B);
+  std::vector<int> lenM(B), len[3];
+  for (int l = 0; l < 3; ++l) { len[l].resize(B); P.h_off[l].resize(B); }
+  for (int b = 0; b < B; ++b) {
+    P.h_mel_off[b] = (int)P.total_T;
+    melrow[b] = P.total_T;
+    lenM[b] = T[b];
+    P.total_T += T[b];
+    P.T_max = std::max(P.T_max, (int)T[b]);
+  }
+  for (int l = 0; l < 3; ++l) {
+    long long o = kGap;
+    for (int b = 0; b < B; ++b) {
+      len[l][b] = kLevelMul[l] * T[b] + (l == 2 ? 1 : 0);
+      P.h_off[l][b] = o;
+      o += len[l][b] + kGap;
+    }
+    P.rows[l] = o;
+  }
+  std::vector<ConvTile> tiles;
+  add_tiles(tiles, P.mel, B, melrow.data(), lenM.data(), melrow.data(), lenM.data(), kTileQ);
+  // ups[i]: conv space = input steps; input is mel-level (i=0) or level i-1
+  add_tiles(tiles, P.up[0], B, melrow.data(), lenM.data(), P.h_off[0].data(), lenM.data(), kTileQ);
+  add_tiles(tiles, P.up[1], B, P.h_off[0].data(), len[0].data(), P.h_off[1].data(), len[0].data(), kTileQ);
+  add_tiles(tiles, P.up[2], B, P.h_off[1].data(), len[1].data(), P.h_off[2].data(), len[1].data(), kTileQ);
+  for (int l = 0; l < 3; ++l) {
+    add_tiles(tiles, P.sd[l], B, P.h_off[2].data(), len[2].data(), P.h_off[l].data(), len[l].data(), kTileQ);
+    add_tiles(tiles, P.lvl[l], B, P.h_off[l].data(), len[l].data(), P.h_off[l].data(), len[l].data(), kTileQ);
+    add_tiles(tiles, P.tc[l][0], B, P.h_off[l].data(), len[l].data(), P.h_off[l].data(), len[l].data(), 128);
+    add_tiles(tiles, P.tc[l][1], B, P.h_off[l].data(), len[l].data(), P.h_off[l].data(), len[l].data(), 256);
+  }
+  // one device block: T | mel_off | off[3] | tiles
+  const size_t nI = align_up((size_t)B * 4, 256), nL = align_up((size_t)B * 8, 256);
+  const size_t bytes = 2 * nI + 3 * nL + align_up(tiles.size() * sizeof(ConvTile), 256);
+  if (bytes > P.d_block_bytes) {
+    if (P.d_block) cudaFree(P.d_block);
+    P.d_block = nullptr;
+    P.d_block_bytes = 0;
+    VT_CUDA_OK(cudaMalloc(&P.d_block, bytes));
+    P.d_block_bytes = bytes;
+  }
+  std::vector<char> host(bytes, 0);
+  char* hp = host.data();
+  char* dp = (char*)P.d_block;
+  std::memcpy(hp, T, (size_t)B * 4); P.d_T = (int*)dp;
+  std::memcpy(hp + nI, P.h_mel_off.data(), (size_t)B * 4); P.d_mel_off = (int*)(dp + nI);
+  for (int l = 0; l < 3; ++l) {
+    std::memcpy(hp + 2 * nI + l * nL, P.h_off[l].data(), (size_t)B * 8);
+    P.d_off[l] = (long long*)(dp + 2 * nI + l * nL);
+  }
+  std::memcpy(hp + 2 * nI + 3 * nL, tiles.data(), tiles.size() * sizeof(ConvTile));
+  P.d_tiles = (ConvTile*)(dp + 2 * nI + 3 * nL);
+  // synchronous copy: `host` dies at scope exit; plans are cached per shape so this is off the steady state
+  VT_CUDA_OK(cudaStreamSynchronize(st));
+  VT_CUDA_OK(cudaMemcpy(P.d_block, host.data(), bytes, cudaMemcpyHostToDevice));
+  return VT_OK;
+}
+
+Workspace carve_ws(const vt_hift* h, int B, long long total_T, void* base) {
+  Workspace w{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    void* p = base ? (void*)((char*)base + off) : nullptr;
+    off += align_up((int64_t)bytes, 1024);
+    return p;
+  };
+  const size_t es = elem_size(h->act_elem);
+  const long long rowsM = total_T + 64;
+  w.f0a = (float*)take((size_t)rowsM * kF0Ch * 4);
+  w.f0b = (float*)take((size_t)rowsM * kF0Ch * 4);
+  w.f0 = (float*)take((size_t)rowsM * 4);
+  w.phase_base = (double*)take((size_t)kHarm * rowsM * 8);
+  w.s = (float*)take((size_t)total_T * kSPF * 4 + 64);
+  w.xpre = (float*)take((size_t)rowsM * kBase * 4);
+  for (int l = 0; l < 3; ++l) {
+    const long long cap = (long long)kLevelMul[l] * total_T + (long long)B * (kGap + 1) + kGap + 512;
+    w.cap_rows[l] = cap;
+    const int C = kBase >> (l + 1);
+    w.U[l] = (float*)take((size_t)cap * C * 4);
+    w.S[l] = (float*)take((size_t)cap * C * 4);
+    w.X[l] = (float*)take((size_t)cap * C * 4);
+    w.XR[l] = (float*)take((size_t)cap * C * 4);
+    w.Y[l] = (float*)take((size_t)cap * C * 4);
+    for (int i = 0; i < 4; ++i) w.A[l][i] = take((size_t)cap * C * es);
+  }
+  w.spec = (float*)take((size_t)w.cap_rows[2] * kSpecCh * 4);
+  w.post = (float*)take((size_t)w.cap_rows[2] * kSpecCh * 4);
+  w.bytes = off;
+  return w;
+}
+
+// Zero the gap rows of the activation copies (read through TMA by the tensor-core kernels).
+__global__ void k_zero_gaps(void* buf, int row_bytes, const long long* off, const int* T, int B, int mul, int plus,
+                            long long rows_total) {
+  // gap g (0..B): rows [start_g, start_g + kGap)
+  const int g = blockIdx.x;
+  long long start = 0;
+  if (g > 0) start = off[g - 1] + (long long)mul * T[g - 1] + plus;
+  const long long bytes = (long long)kGap * row_bytes;
+  uint4* p = reinterpret_cast<uint4*>((char*)buf + start * row_bytes);
+  for (long long i = threadIdx.x; i < bytes / 16; i += blockDim.x) p[i] = make_uint4(0, 0, 0, 0);
+  (void)rows_total;
+}
+
+}  // namespace
+
+static ConvArgs base_args(const ConvLayer& L, const Plan& P, const Plan::Seg& seg) {
+  ConvArgs a{};
+  a.w = L.w; a.bias = L.bias;
+  a.cin = L.cin; a.cout = L.cout; a.k = L.k; a.dil = L.dil; a.stride = L.stride; a.pad = L.pad;
+  a.in_ld = L.cin;
+  a.pro_act = ACT_NONE; a.pro_slope = 0.f;
+  a.out_scale = 1.0f;
+  a.out_mul = L.out_mul; a.out_shift = 0; a.phase_c = L.phase_c; a.dup_row2 = 0;
+  a.tiles = P.d_tiles + seg.off;
+  a.n_tiles = seg.n;
+  return a;
+}
+
+static int run_conv(vt_hift* h, const ConvArgs& a, const ConvLayer& L, int level, cudaStream_t st) {
+  if (h->use_tc && L.w_tc && level >= 0) {
+    const int rows = conv_tc_tile_rows(L);
+    const Plan::Seg& seg = h->plan.tc[level][rows == 256 ? 1 : 0];
+    return launch_conv_tc(a, L, h->act_elem, h->plan.d_tiles + seg.off, seg.n, rows, st);
+  }
+  return launch_conv_ref(a, h->act_elem, st);
+}
+
+}  // namespace vt
+
+namespace vt {
+template <typename T> __device__ float to_f(T v);
+template <> __device__ float to_f<float>(float v) { return v; }
+template <> __device__ float to_f<__half>(__half v) { return __half2float(v); }
+template <> __device__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T>
+__global__ void k_tap(const T* src, long long row0, int ld, int ch, long long rows, float* dst) {
+  const long long n = rows * ch;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / ch;
+    const int c = (int)(i - r * ch);
+    dst[i] = to_f<T>(src[(row0 + r) * ld + c]);
+  }
+}
+}  // namespace
+
+extern "C" {
+
+int vt_hift_create(const vt_tensor* tensors, int n_tensors, int operand_dtype, vt_hift** out_handle) {
+  VT_REQUIRE(tensors && n_tensors > 0 && out_handle, "vt_hift_create: NULL argument");
+  VT_REQUIRE(operand_dtype == VT_OPERAND_FP16 || operand_dtype == VT_OPERAND_BF16 || operand_dtype == VT_OPERAND_FP32,
+             "vt_hift_create: unknown operand dtype %d", operand_dtype);
+  std::map<std::string, HostTensor> tab;
+  for (int i = 0; i < n_tensors; ++i) {
+    VT_REQUIRE(tensors[i].name && tensors[i].data && tensors[i].ndim >= 1 && tensors[i].ndim <= 4,
+               "vt_hift_create: bad tensor entry %d", i);
+    HostTensor t;
+    t.data = tensors[i].data;
+    t.shape.assign(tensors[i].shape, tensors[i].shape + tensors[i].ndim);
+    tab[tensors[i].name] = t;
+  }
+  vt_hift* h = new vt_hift();
+  h->act_elem = operand_dtype == VT_OPERAND_FP32 ? ELEM_F32 : (operand_dtype == VT_OPERAND_FP16 ? ELEM_F16 : ELEM_BF16);
+  h->use_tc = operand_dtype != VT_OPERAND_FP32;
+  int rc = VT_OK;
+  auto fail = [&](int code) { vt_hift_destroy(h); return code; };
+#define TRY(expr) do { rc = (expr); if (rc) return fail(rc); } while (0)
+  TRY(pack_conv(h, h->conv_pre, tab, "conv_pre", kMel, kBase, 7, 1, 1, 3, kMel, kBase));
+  for (int i = 0; i < 3; ++i) {
+    const int cin = kBase >> i, cout = kBase >> (i + 1);
+    TRY(pack_convT(h, h->ups[i], tab, "ups." + std::to_string(i), cin, cout, kUpKernels[i], kUpRates[i],
+                   (kUpKernels[i] - kUpRates[i]) / 2));
+    TRY(pack_conv(h, h->sdown[i], tab, "source_downs." + std::to_string(i), kNfft + 2, cout, kSdK[i], 1, kSdS[i],
+                  kSdP[i], kSpecCh, cout));
+    for (int j = 0; j < 3; ++j) {
+      const std::string p = "source_resblocks." + std::to_string(i);
+      const int k = kSrcRbKernels[i];
+      TRY(pack_conv(h, h->src_c1[i][j], tab, p + ".convs1." + std::to_string(j), cout, cout, k, kRbDil[j], 1,
+                    (k * kRbDil[j] - kRbDil[j]) / 2, cout, cout));
+      TRY(pack_conv(h, h->src_c2[i][j], tab, p + ".convs2." + std::to_string(j), cout, cout, k, 1, 1, (k - 1) / 2, cout, cout));
+      TRY(upload_vec(h, tab, p + ".activations1." + std::to_string(j) + ".alpha", cout, &h->src_a1[i][j]));
+      TRY(upload_vec(h, tab, p + ".activations2." + std::to_string(j) + ".alpha", cout, &h->src_a2[i][j]));
+    }
+    for (int kk = 0; kk < 3; ++kk) {
+      const int r = i * 3 + kk, k = kRbKernels[kk];
+      const std::string p = "resblocks." + std::to_string(r);
+      for (int j = 0; j < 3; ++j) {
+        TRY(pack_conv(h, h->rb_c1[r][j], tab, p + ".convs1." + std::to_string(j), cout, cout, k, kRbDil[j], 1,
+                      (k * kRbDil[j] - kRbDil[j]) / 2, cout, cout));
+        TRY(pack_conv(h, h->rb_c2[r][j], tab, p + ".convs2." + std::to_string(j), cout, cout, k, 1, 1, (k - 1) / 2, cout, cout));
+        TRY(upload_vec(h, tab, p + ".activations1." + std::to_string(j) + ".alpha", cout, &h->rb_a1[r][j]));
+        TRY(upload_vec(h, tab, p + ".activations2." + std::to_string(j) + ".alpha", cout, &h->rb_a2[r][j]));
+      }
+    }
+  }
+  TRY(pack_conv(h, h->conv_post, tab, "conv_post", kBase >> 3, kNfft + 2, 7, 1, 1, 3, kBase >> 3, kSpecCh));
+  for (int i = 0; i < 5; ++i)
+    TRY(pack_conv(h, h->f0c[i], tab, "f0_predictor.condnet." + std::to_string(2 * i), i == 0 ? kMel : kF0Ch, kF0Ch, 3, 1, 1, 1,
+                  i == 0 ? kMel : kF0Ch, kF0Ch));
+  TRY(upload_vec(h, tab, "f0_predictor.classifier.weight", kF0Ch, &h->f0_w));
+  TRY(upload_vec(h, tab, "f0_predictor.classifier.bias", 1, &h->f0_b));
+  TRY(upload_vec(h, tab, "m_source.l_linear.weight", kHarm, &h->lin_w));
+  TRY(upload_vec(h, tab, "m_source.l_linear.bias", 1, &h->lin_b));
+  {
+    // s3gen.py: trim_fade = zeros(2n); trim_fade[n:] = (cos(linspace(pi, 0, n)) + 1) / 2, n = 480 (fp32)
+    std::vector<float> tf(2 * kSPF, 0.0f);
+    const float step = (0.0f - 3.14159265358979323846f) / (float)(kSPF - 1);
+    for (int i = 0; i < kSPF; ++i) {
+      // torch.linspace (fp32): first half from the start, second half from the end
+      const float x = i < kSPF / 2 ? 3.14159265358979323846f + step * (float)i : 0.0f - step * (float)(kSPF - 1 - i);
+      tf[kSPF + i] = (cosf(x) + 1.0f) / 2.0f;
+    }
+    TRY(dev_upload(h, tf.data(), tf.size() * 4, (void**)&h->trim_fade));
+  }
+#undef TRY
+  *out_handle = h;
+  return VT_OK;
+}
+
+void vt_hift_destroy(vt_hift* h) {
+  if (!h) return;
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->plan.d_block) cudaFree(h->plan.d_block);
+  delete h;
+}
+
+int64_t vt_hift_workspace_bytes(const vt_hift* h, int B, int64_t total_T, int64_t T_max) {
+  if (!h || B < 0 || total_T < 0 || T_max < 0) return VT_ERR_INVALID;
+  return (int64_t)carve_ws(h, B, total_T, nullptr).bytes;
+}
+
+int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const float* f0_in, const float* phase_vec,
+                    const float* noise, uint64_t seed, float* wav, void* workspace, int64_t workspace_bytes,
+                    void* stream_v) {
+  VT_REQUIRE(h != nullptr, "vt_hift_forward: NULL handle");
+  VT_REQUIRE(B >= 0 && B <= 65535, "vt_hift_forward: B must be in [0, 65535]");
+  launch_counter() = 0;
+  if (B == 0) return VT_OK;
+  VT_REQUIRE(mel && T && wav && workspace, "vt_hift_forward: NULL argument");
+  VT_REQUIRE((reinterpret_cast<uintptr_t>(mel) & 15) == 0 && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
+             "vt_hift_forward: mel must be 16-byte and workspace 256-byte aligned");
+  long long total_T = 0;
+  for (int b = 0; b < B; ++b) {
+    VT_REQUIRE(T[b] >= 1, "vt_hift_forward: every sequence needs at least one mel frame (T[%d]=%d)", b, T[b]);
+    total_T += T[b];
+  }
+  VT_REQUIRE(total_T * 121LL + B * 40LL < 2000000000LL, "vt_hift_forward: batch too large for 32-bit tile tables");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
+  int rc = build_plan(h, T, B, st);
+  if (rc) return rc;
+  const Plan& P = h->plan;
+  Workspace w = carve_ws(h, B, total_T, workspace);
+  VT_REQUIRE((int64_t)w.bytes <= workspace_bytes, "vt_hift_forward: workspace too small (%lld < %lld)",
+             (long long)workspace_bytes, (long long)w.bytes);
+  h->ws = w;
+  h->have_forward = true;
+  const int ae = h->act_elem;
+
+  if (h->use_tc) {
+    for (int l = 0; l < 3; ++l)
+      for (int i = 0; i < 4; ++i) {
+        k_zero_gaps<<<B + 1, 256, 0, st>>>(w.A[l][i], (kBase >> (l + 1)) * (int)elem_size(ae), P.d_off[l], P.d_T, B,
+                                           kLevelMul[l], l == 2 ? 1 : 0, P.rows[l]);
+        VT_LAUNCHED();
+      }
+  }
+
+  // ---- F0 (ConvRNNF0Predictor) unless injected
+  const float* f0 = f0_in;
+  if (!f0) {
+    float* bufs[2] = {w.f0a, w.f0b};
+    for (int i = 0; i < 5; ++i) {
+      ConvArgs a = base_args(h->f0c[i], P, P.mel);
+      a.in = i == 0 ? mel : bufs[(i - 1) & 1];
+      // the F0 trunk is fp32 end to end: its ELU output is the next conv's fp32 input
+      a.out = nullptr;
+      a.act[0] = {bufs[i & 1], nullptr, ACT_ELU, 0.f};
+      rc = launch_conv_ref(a, ELEM_F32, st);
+      if (rc) return rc;
+    }
+    rc = launch_f0_head(bufs[0], h->f0_w, h->f0_b, w.f0, total_T, st);
+    if (rc) return rc;
+    f0 = w.f0;
+  } else {
+    VT_CUDA_OK(cudaMemcpyAsync(w.f0, f0_in, (size_t)total_T * 4, cudaMemcpyDeviceToDevice, st));  // keeps the "f0" tap valid
+  }
+  // ---- source: SineGen -> tanh(Linear) -> STFT
+  rc = launch_sine_source(f0, P.d_mel_off, P.d_T, B, total_T, phase_vec, noise, seed, h->lin_w, h->lin_b,
+                          w.phase_base, w.s, st);
+  if (rc) return rc;
+  rc = launch_stft(w.s, P.d_mel_off, P.d_T, P.d_off[2], B, total_T, w.spec, st);
+  if (rc) return rc;
+  // ---- conv_pre
+  {
+    ConvArgs a = base_args(h->conv_pre, P, P.mel);
+    a.in = mel;
+    a.out = w.xpre;
+    rc = launch_conv_ref(a, ae, st);
+    if (rc) return rc;
+  }
+  for (int i = 0; i < 3; ++i) {
+    // ups[i]( leaky_relu(x, 0.1) ), reflection pad (1, 0) on the last stage
+    {
+      ConvArgs a = base_args(h->ups[i], P, P.up[i]);
+      a.in = i == 0 ? w.xpre : w.Y[i - 1];
+      a.pro_act = ACT_LRELU; a.pro_slope = 0.1f;
+      a.out = w.U[i];
+      if (i == 2) { a.out_shift = 1; a.dup_row2 = 1; }
+      rc = launch_conv_ref(a, ae, st);
+      if (rc) return rc;
+    }
+    // source_downs[i](s_stft) -> S stream + Snake copy for the first source-resblock conv
+    {
+      ConvArgs a = base_args(h->sdown[i], P, P.sd[i]);
+      a.in = w.spec;
+      a.out = w.S[i];
+      a.act[0] = {w.A[i][1], h->src_a1[i][0], ACT_SNAKE, 0.f};
+      rc = launch_conv_ref(a, ae, st);
+      if (rc) return rc;
+    }
+    // source_resblocks[i]; its last conv also adds the upsampled stream: x = ups + si
+    for (int j = 0; j < 3; ++j) {
+      ConvArgs a = base_args(h->src_c1[i][j], P, P.lvl[i]);
+      a.in_act = w.A[i][1];
+      a.act[0] = {w.A[i][3], h->src_a2[i][j], ACT_SNAKE, 0.f};
+      rc = run_conv(h, a, h->src_c1[i][j], i, st);
+      if (rc) return rc;
+      ConvArgs c = base_args(h->src_c2[i][j], P, P.lvl[i]);
+      c.in_act = w.A[i][3];
+      c.res1 = w.S[i];
+      if (j < 2) {
+        c.out = w.S[i];
+        c.act[0] = {w.A[i][1], h->src_a1[i][j + 1], ACT_SNAKE, 0.f};
+      } else {
+        c.res2 = w.U[i];
+        c.out = w.X[i];
+        for (int r = 0; r < 3; ++r) c.act[r] = {w.A[i][r], h->rb_a1[i * 3 + r][0], ACT_SNAKE, 0.f};
+      }
+      rc = run_conv(h, c, h->src_c2[i][j], i, st);
+      if (rc) return rc;
+    }
+    // three multi-receptive-field resblocks, averaged
+    for (int r = 0; r < 3; ++r) {
+      const int R = i * 3 + r;
+      for (int j = 0; j < 3; ++j) {
+        ConvArgs a = base_args(h->rb_c1[R][j], P, P.lvl[i]);
+        a.in_act = w.A[i][r];
+        a.act[0] = {w.A[i][3], h->rb_a2[R][j], ACT_SNAKE, 0.f};
+        rc = run_conv(h, a, h->rb_c1[R][j], i, st);
+        if (rc) return rc;
+        ConvArgs c = base_args(h->rb_c2[R][j], P, P.lvl[i]);
+        c.in_act = w.A[i][3];
+        c.res1 = j == 0 ? w.X[i] : w.XR[i];
+        if (j < 2) {
+          c.out = w.XR[i];
+          c.act[0] = {w.A[i][r], h->rb_a1[R][j + 1], ACT_SNAKE, 0.f};
+        } else {
+          c.out = w.Y[i];
+          c.out_accum = r > 0;
+          c.out_scale = 1.0f / 3.0f;
+        }
+        rc = run_conv(h, c, h->rb_c2[R][j], i, st);
+        if (rc) return rc;
+      }
+    }
+  }
+  // ---- conv_post( leaky_relu(x) ) with the default slope 0.01, then the spectral head
+  {
+    ConvArgs a = base_args(h->conv_post, P, P.lvl[2]);
+    a.in = w.Y[2];
+    a.pro_act = ACT_LRELU; a.pro_slope = 0.01f;
+    a.out = w.post;
+    rc = launch_conv_ref(a, ae, st);
+    if (rc) return rc;
+  }
+  return launch_istft_head(w.post, P.d_mel_off, P.d_T, P.d_off[2], B, P.T_max, h->trim_fade, wav, st);
+}
+
+
+int64_t vt_hift_read_tap(vt_hift* h, const char* tap, int seq, float* out, int64_t capacity, void* workspace,
+                         void* stream_v) {
+  if (!h || !tap || !h->have_forward) { set_error("vt_hift_read_tap: no forward has run on this handle"); return VT_ERR_INVALID; }
+  (void)workspace;
+  const Plan& P = h->plan;
+  if (seq < 0 || seq >= P.B) { set_error("vt_hift_read_tap: bad sequence index %d", seq); return VT_ERR_INVALID; }
+  const Workspace& w = h->ws;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
+  const std::string name(tap);
+  const int T = P.T[seq];
+  const void* src = nullptr;
+  long long row0 = 0, rows = 0;
+  int ld = 0, ch = 0, elem = ELEM_F32;
+  auto level = [&](int l, const void* p, int e) {
+    src = p; row0 = P.h_off[l][seq]; rows = (long long)kLevelMul[l] * T + (l == 2 ? 1 : 0);
+    ld = ch = kBase >> (l + 1); elem = e;
+  };
+  if (name == "f0") { src = w.f0; row0 = P.h_mel_off[seq]; rows = T; ld = ch = 1; }
+  else if (name == "s") { src = w.s; row0 = (long long)P.h_mel_off[seq] * kSPF; rows = (long long)T * kSPF; ld = ch = 1; }
+  else if (name == "s_stft") { src = w.spec; row0 = P.h_off[2][seq]; rows = 120LL * T + 1; ld = kSpecCh; ch = kNfft + 2; }
+  else if (name == "conv_post") { src = w.post; row0 = P.h_off[2][seq]; rows = 120LL * T + 1; ld = kSpecCh; ch = kNfft + 2; }
+  else if (name == "conv_pre") { src = w.xpre; row0 = P.h_mel_off[seq]; rows = T; ld = ch = kBase; }
+  else if (name.size() == 4 && name.compare(0, 3, "ups") == 0) level(name[3] - '0', w.U[name[3] - '0'], ELEM_F32);
+  else if (name.size() == 2 && name[0] == 'x') level(name[1] - '0', w.X[name[1] - '0'], ELEM_F32);
+  else if (name.size() == 6 && name.compare(0, 5, "stage") == 0) level(name[5] - '0', w.Y[name[5] - '0'], ELEM_F32);
+  else if (name.size() == 5 && name.compare(0, 4, "act0") == 0) level(name[4] - '0', w.A[name[4] - '0'][0], h->act_elem);
+  else { set_error("vt_hift_read_tap: unknown tap '%s'", tap); return VT_ERR_INVALID; }
+  if (name.size() >= 2 && (name[name.size() - 1] < '0' || name[name.size() - 1] > '2') &&
+      (name.compare(0, 3, "ups") == 0 || name[0] == 'x' || name.compare(0, 5, "stage") == 0)) {
+    set_error("vt_hift_read_tap: bad level in '%s'", tap);
+    return VT_ERR_INVALID;
+  }
+  const int64_t n = rows * ch;
+  if (!out) return n;
+  if (capacity < n) { set_error("vt_hift_read_tap: capacity %lld < %lld", (long long)capacity, (long long)n); return VT_ERR_INVALID; }
+  if (n == 0) return 0;
+  const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+  if (elem == ELEM_F32) k_tap<float><<<blocks, 256, 0, st>>>((const float*)src, row0, ld, ch, rows, out);
+  else if (elem == ELEM_F16) k_tap<__half><<<blocks, 256, 0, st>>>((const __half*)src, row0, ld, ch, rows, out);
+  else k_tap<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)src, row0, ld, ch, rows, out);
+  if (cudaGetLastError() != cudaSuccess) { set_error("vt_hift_read_tap: launch failed"); return VT_ERR_CUDA; }
+  return n;
+}
+
+}  // extern "C"

@@ -1,0 +1,102 @@
+// Internal structures of the HiFT vocoder path (upstream chatterbox-tts==0.1.6
+// chatterbox/models/s3gen/hifigan.py as instantiated by S3Token2Wav).
+//
+// Data layout in HBM
+//   Activations are channel-last: one row per time step, channels contiguous.  The ragged batch
+//   is packed along the row axis; at the three generator levels (8T, 40T, 120T+1 rows per
+//   sequence) every sequence is preceded and followed by kGap zero rows, so a conv's zero padding
+//   is "read the gap" for the TMA-fed tensor-core kernels (the CUDA-core kernels bounds-check
+//   explicitly and never rely on it).  Row of step r of sequence b at level l:
+//       off_l(b) + r,   off_l(b) = kGap + sum_{b'<b} (len_l(b') + kGap)
+//   mel-rate tensors (mel, F0 predictor, conv_pre) are packed without gaps: row mel_off[b] + t.
+//   1-D sample-rate signals (source s, wav) are packed without gaps at 480 * mel_off[b].
+#pragma once
+#include "vt_common.cuh"
+
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+
+#include <string>
+#include <vector>
+
+namespace vt {
+
+constexpr int kGap = 32;           // >= largest one-sided conv halo (k=11, dilation 5 -> 25)
+constexpr int kMel = 80;
+constexpr int kBase = 512;
+constexpr int kF0Ch = 512;
+constexpr int kHarm = 9;           // nb_harmonics + 1
+constexpr int kSPF = 480;          // samples per mel frame
+constexpr int kNfft = 16;
+constexpr int kHop = 4;
+constexpr int kSpecCh = 32;        // 18 STFT / conv_post channels padded to 32 (zeros)
+constexpr int kTileQ = 64;         // output steps per tile of the CUDA-core conv kernel
+
+enum ActKind : int { ACT_NONE = 0, ACT_SNAKE = 1, ACT_LRELU = 2, ACT_ELU = 3 };
+enum ElemKind : int { ELEM_F32 = 0, ELEM_F16 = 1, ELEM_BF16 = 2 };
+
+// One tile of output steps of one sequence (all conv kernels iterate over a table of these).
+struct __align__(16) ConvTile {
+  long long in_row0;    // packed row of the sequence's input step 0
+  long long out_row0;   // packed row of the sequence's output step 0
+  int in_len;           // input steps of the sequence
+  int out_len;          // output steps of the sequence ("conv space", before the phase expansion)
+  int q0;               // first output step of this tile
+  int n;                // output steps in this tile
+};
+
+struct ActOut {
+  void* dst;            // [rows][C] in the activation element type; nullptr = unused
+  const float* alpha;   // per-channel Snake alpha
+  int kind;
+  float slope;
+};
+
+// Arguments of one convolution launch (shared by the CUDA-core and the tensor-core kernels).
+struct ConvArgs {
+  const float* in;      // fp32 input [rows][in_ld]  (CUDA-core path)
+  const void* in_act;   // activation-typed input [rows][in_ld] (resblock convs)
+  int in_ld;
+  const float* w;       // [k][cin][cout] fp32
+  const float* bias;    // [cout]
+  int cin, cout, k, dil, stride, pad;
+  int pro_act;          // prologue activation applied to the input on load
+  float pro_slope;
+  // epilogue: v = acc + bias (+res1) (+res2); out = (accum ? out : 0) + v*scale; act_i = f_i(v)
+  const float* res1;
+  const float* res2;
+  float* out;
+  int out_accum;
+  float out_scale;
+  ActOut act[3];
+  // output row mapping: column c' -> phase r = c'/phase_c, channel c'%phase_c, packed row
+  //   out_row0 + q*out_mul + r + out_shift ; dup_row2: value landing on row 2 is also written to row 0
+  int out_mul, out_shift, phase_c, dup_row2;
+  const ConvTile* tiles;
+  int n_tiles;
+};
+
+struct ConvLayer {
+  std::string name;
+  int cin = 0, cout = 0, k = 1, dil = 1, stride = 1, pad = 0;
+  int out_mul = 1, phase_c = 0;     // transposed convs run as a k'=3 conv with cout = s*C_out
+  float* w = nullptr;               // device [k][cin][cout] fp32
+  float* bias = nullptr;            // device [cout]
+  void* w_tc = nullptr;             // device, tensor-core operand packing (vt_conv_tc.cu)
+  double flops_per_step = 0;        // algorithmic 2*MAC per output step of the ORIGINAL layer
+};
+
+int launch_conv_ref(const ConvArgs& a, int act_elem, cudaStream_t st);
+
+// Source path (vt_source.cu)
+int launch_f0_head(const float* h, const float* w, const float* b, float* f0, long long rows, cudaStream_t st);
+int launch_sine_source(const float* f0, const int* mel_off, const int* T, int B, long long total_T,
+                       const float* phase_vec, const float* noise, unsigned long long seed,
+                       const float* lin_w, const float* lin_b, double* phase_base, float* s, cudaStream_t st);
+int launch_stft(const float* s, const int* mel_off, const int* T, const long long* off2, int B, long long total_T,
+                float* spec, cudaStream_t st);
+// Spectral head (vt_head.cu): conv_post output -> exp/sin -> iSTFT -> clamp -> trim_fade
+int launch_istft_head(const float* post, const int* mel_off, const int* T, const long long* off2, int B,
+                      int T_max, const float* trim_fade, float* wav, cudaStream_t st);
+
+}  // namespace vt

@@ -1,0 +1,216 @@
+// Source path of the HiFT vocoder: F0 head, SineGen + SourceModuleHnNSF, STFT of the source.
+// Bandwidth-bound elementwise work over sample-rate signals (upstream hifigan.py SineGen.forward,
+// SourceModuleHnNSF.forward, HiFTGenerator._stft).
+#include "vt_hift.cuh"
+#include "vt_tables.cuh"
+
+namespace vt {
+
+// ---- F0 head: classifier Linear(512 -> 1) + abs (upstream f0_predictor.py) -----------------------
+__global__ void __launch_bounds__(256)
+k_f0_head(const float* __restrict__ h, const float* __restrict__ w, const float* __restrict__ b,
+          float* __restrict__ f0, long long rows) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* hp = reinterpret_cast<const float4*>(h + row * kF0Ch);
+  const float4* wp = reinterpret_cast<const float4*>(w);
+  float acc = 0.0f;
+#pragma unroll
+  for (int i = 0; i < kF0Ch / 128; ++i) {
+    const float4 x = hp[i * 32 + lane], y = wp[i * 32 + lane];
+    acc = fmaf(x.x, y.x, acc);
+    acc = fmaf(x.y, y.y, acc);
+    acc = fmaf(x.z, y.z, acc);
+    acc = fmaf(x.w, y.w, acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) f0[row] = fabsf(acc + b[0]);
+}
+
+int launch_f0_head(const float* h, const float* w, const float* b, float* f0, long long rows, cudaStream_t st) {
+  if (rows == 0) return VT_OK;
+  k_f0_head<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(h, w, b, f0, rows);
+  VT_LAUNCHED();
+  return VT_OK;
+}
+
+// ---- SineGen -------------------------------------------------------------------------------
+// Phase: torch CPU cumsum over fp32 accumulates in fp64 and rounds every prefix to fp32
+// (SURVEY A.4 [probe]).  F is constant inside a mel frame, so the fp64 prefix at sample j of
+// frame t is base[t] + (j+1)*F with base[t] = sum_{t'<t} 480*F(t') (exact products in fp64);
+// it is rounded to fp32 *before* the mod-1 exactly like the reference.
+__device__ __forceinline__ float harmonic_inc(float f0, int h) {
+  // upstream: F_mat = f0 * (i + 1) / sampling_rate   (fp32 mul, then fp32 div)
+  return __fdiv_rn(__fmul_rn(f0, (float)(h + 1)), 24000.0f);
+}
+
+__global__ void k_phase_base(const float* __restrict__ f0, const int* __restrict__ mel_off,
+                             const int* __restrict__ T, int B, long long total_T, double* __restrict__ base) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * kHarm) return;
+  const int b = i / kHarm, h = i % kHarm;
+  const long long o = mel_off[b];
+  double acc = 0.0;
+  double* dst = base + (long long)h * total_T + o;
+  for (int t = 0; t < T[b]; ++t) {
+    dst[t] = acc;
+    acc += (double)kSPF * (double)harmonic_inc(f0[o + t], h);
+  }
+}
+
+// Philox4x32-10 counter-based generator for the performance mode (no explicit noise given).
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const unsigned hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const unsigned hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+__device__ __forceinline__ float2 box_muller(unsigned a, unsigned b) {
+  const float u1 = ((float)a + 1.0f) * 2.3283064365386963e-10f;  // (0, 1]
+  const float u2 = (float)b * 2.3283064365386963e-10f;
+  const float r = sqrtf(-2.0f * __logf(u1));
+  float s, c;
+  __sincosf(6.283185307179586f * u2, &s, &c);
+  return make_float2(r * c, r * s);
+}
+
+// One thread per output sample: 9 harmonics, noise mix, Linear(9->1), tanh.
+__global__ void __launch_bounds__(256)
+k_sine_source(const float* __restrict__ f0, const int* __restrict__ mel_off, const int* __restrict__ T, int B,
+              long long total_T, const float* __restrict__ phase_vec, const float* __restrict__ noise,
+              unsigned long long seed, const float* __restrict__ lin_w, const float* __restrict__ lin_b,
+              const double* __restrict__ base, float* __restrict__ s) {
+  const int b = blockIdx.y;
+  const long long o = mel_off[b];
+  const long long L = (long long)T[b] * kSPF;
+  const float lb = lin_b[0];
+  float lw[kHarm], pv[kHarm];
+#pragma unroll
+  for (int h = 0; h < kHarm; ++h) {
+    lw[h] = lin_w[h];
+    pv[h] = phase_vec ? phase_vec[b * kHarm + h] : 0.0f;
+  }
+  if (!phase_vec) {
+    // U(-pi, pi) per (sequence, harmonic), harmonic 0 -> 0 (upstream SineGen)
+    const uint4 r0 = philox4x32(make_uint4((unsigned)b, 0u, 0u, 0x51u), make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+    const uint4 r1 = philox4x32(make_uint4((unsigned)b, 1u, 0u, 0x51u), make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+    const unsigned rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+    for (int h = 1; h < kHarm; ++h) pv[h] = ((float)rr[h - 1] * 2.3283064365386963e-10f * 2.0f - 1.0f) * 3.14159265358979f;
+  }
+  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < L; n += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(n / kSPF), j = (int)(n - (long long)t * kSPF);
+    const float f = f0[o + t];
+    const bool voiced = f > 10.0f;
+    const float uv = voiced ? 1.0f : 0.0f;
+    // upstream: noise_amp = uv * noise_std + (1 - uv) * sine_amp / 3
+    const float namp = __fadd_rn(__fmul_rn(uv, 0.003f), __fdiv_rn(__fmul_rn(1.0f - uv, 0.1f), 3.0f));
+    float z[kHarm];
+    if (noise) {
+#pragma unroll
+      for (int h = 0; h < kHarm; ++h) z[h] = noise[(o * kSPF) * kHarm + (long long)h * L + n];
+    } else {
+      const uint2 key = make_uint2((unsigned)seed, (unsigned)(seed >> 32));
+      const unsigned long long gi = (unsigned long long)(o * kSPF + n);
+#pragma unroll
+      for (int g = 0; g < 3; ++g) {
+        const uint4 r = philox4x32(make_uint4((unsigned)gi, (unsigned)(gi >> 32), (unsigned)g, 0xA5u), key);
+        const float2 n0 = box_muller(r.x, r.y), n1 = box_muller(r.z, r.w);
+        if (4 * g + 0 < kHarm) z[4 * g + 0] = n0.x;
+        if (4 * g + 1 < kHarm) z[4 * g + 1] = n0.y;
+        if (4 * g + 2 < kHarm) z[4 * g + 2] = n1.x;
+        if (4 * g + 3 < kHarm) z[4 * g + 3] = n1.y;
+      }
+    }
+    float acc = lb;
+#pragma unroll
+    for (int h = 0; h < kHarm; ++h) {
+      const float inc = harmonic_inc(f, h);
+      const double c64 = base[(long long)h * total_T + o + t] + (double)(j + 1) * (double)inc;
+      const float c = __double2float_rn(c64);
+      const float frac = c - truncf(c);                       // torch `% 1` on a non-negative value
+      const float theta = __fmul_rn(frac, 6.283185307179586f);  // 2*pi as an fp32 scalar
+      const float sine = __fmul_rn(0.1f, sinf(theta + pv[h]));
+      const float v = __fadd_rn(__fmul_rn(sine, uv), __fmul_rn(namp, z[h]));
+      acc = fmaf(v, lw[h], acc);
+    }
+    s[o * kSPF + n] = tanhf(acc);
+  }
+}
+
+int launch_sine_source(const float* f0, const int* mel_off, const int* T, int B, long long total_T,
+                       const float* phase_vec, const float* noise, unsigned long long seed,
+                       const float* lin_w, const float* lin_b, double* phase_base, float* s, cudaStream_t st) {
+  if (B == 0 || total_T == 0) return VT_OK;
+  k_phase_base<<<(B * kHarm + 63) / 64, 64, 0, st>>>(f0, mel_off, T, B, total_T, phase_base);
+  VT_LAUNCHED();
+  // grid.x sized for the longest sequence (grid-stride inside): aim at ~148*8 blocks in total
+  int gx = (148 * 8 + B - 1) / B;
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, B);
+  k_sine_source<<<grid, 256, 0, st>>>(f0, mel_off, T, B, total_T, phase_vec, noise, seed, lin_w, lin_b,
+                                      phase_base, s);
+  VT_LAUNCHED();
+  return VT_OK;
+}
+
+// ---- STFT of the source: n_fft 16, hop 4, periodic Hann, center=True (reflect) ---------------
+// One thread per frame: 16 windowed samples -> 9 real + 9 imaginary bins, written channel-last
+// into the level-2 packed layout (row off2[b] + frame, 32 channels, 18..31 zero).
+
+__global__ void __launch_bounds__(256)
+k_stft(const float* __restrict__ s, const int* __restrict__ mel_off, const int* __restrict__ T,
+       const long long* __restrict__ off2, int B, float* __restrict__ spec) {
+  const int b = blockIdx.y;
+  const long long L = (long long)T[b] * kSPF;
+  const long long frames = L / kHop + 1;
+  const float* sb = s + (long long)mel_off[b] * kSPF;
+  for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < frames; f += (long long)gridDim.x * blockDim.x) {
+    float x[kNfft];
+#pragma unroll
+    for (int n = 0; n < kNfft; ++n) {
+      long long i = f * kHop + n - kNfft / 2;
+      if (i < 0) i = -i;
+      if (i >= L) i = 2 * (L - 1) - i;
+      x[n] = sb[i] * c_hann16[n];
+    }
+    float* dst = spec + (off2[b] + f) * kSpecCh;
+    float outv[kSpecCh];
+#pragma unroll
+    for (int m = 0; m <= kNfft / 2; ++m) {
+      float re = 0.0f, im = 0.0f;
+#pragma unroll
+      for (int n = 0; n < kNfft; ++n) {
+        const int ph = (m * n) & 15;
+        re = fmaf(x[n], c_cos16[ph], re);
+        im = fmaf(x[n], -c_sin16[ph], im);
+      }
+      outv[m] = re;
+      outv[kNfft / 2 + 1 + m] = im;
+    }
+#pragma unroll
+    for (int c = kNfft + 2; c < kSpecCh; ++c) outv[c] = 0.0f;
+#pragma unroll
+    for (int c = 0; c < kSpecCh; c += 4)
+      *reinterpret_cast<float4*>(dst + c) = make_float4(outv[c], outv[c + 1], outv[c + 2], outv[c + 3]);
+  }
+}
+
+int launch_stft(const float* s, const int* mel_off, const int* T, const long long* off2, int B, long long total_T,
+                float* spec, cudaStream_t st) {
+  if (B == 0 || total_T == 0) return VT_OK;
+  int gx = (148 * 8 + B - 1) / B;
+  dim3 grid(gx < 1 ? 1 : gx, B);
+  k_stft<<<grid, 256, 0, st>>>(s, mel_off, T, off2, B, spec);
+  VT_LAUNCHED();
+  return VT_OK;
+}
+
+}  // namespace vt

@@ -1,0 +1,212 @@
+"""Host side of the B200 HiFT vocoder: weight folding/packing, ragged batching, the ctypes call.
+
+Mirrors the upstream call the reference reaches through ``tts.generate`` (reference
+tts_backends/chatterbox_impl.py:189): ``HiFTGenerator.inference(speech_feat=mel)`` followed by
+the ``S3Token2Wav`` ``trim_fade`` tail - mel ``[80, T]`` in, waveform ``[480*T]`` at 24 kHz out -
+batched over independent chunks.  All arithmetic runs in ``csrc/`` through the C ABI
+(``include/vocalie_b200.h``); there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+from .errors import BackendUnavailableError
+
+S3GEN_SR = 24000            # upstream const.py
+N_MEL = 80
+SAMPLES_PER_FRAME = 480     # 8 * 5 * 3 upsampling x hop 4
+N_HARMONICS = 9
+
+OPERANDS = {"fp16": _lib.VT_OPERAND_FP16, "bf16": _lib.VT_OPERAND_BF16, "fp32": _lib.VT_OPERAND_FP32}
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise BackendUnavailableError("no CUDA device: the B200 HiFT path has no CPU fallback")
+    return torch
+
+
+def fold_weight_norm(state_dict: Dict[str, "object"]) -> Dict[str, np.ndarray]:
+    """Fold ``torch.nn.utils.parametrizations.weight_norm`` (``w = g * v / ||v||`` over all dims
+    but 0) and return float32 numpy arrays keyed by plain upstream names.  Entries
+    that are already plain ``.weight`` pass through; legacy ``weight_g``/``weight_v`` keys are
+    folded too."""
+    def to_np(v):
+        if hasattr(v, "detach"):
+            v = v.detach().cpu().numpy()
+        return np.asarray(v)
+
+    out: Dict[str, np.ndarray] = {}
+    pairs = ((".parametrizations.weight.original0", ".parametrizations.weight.original1"), (".weight_g", ".weight_v"))
+    for k, v in state_dict.items():
+        done = False
+        for gs, vs in pairs:
+            if k.endswith(vs):
+                base = k[: -len(vs)]
+                g = to_np(state_dict[base + gs]).astype(np.float64)
+                vv = to_np(v).astype(np.float64)
+                norm = np.sqrt((vv.reshape(vv.shape[0], -1) ** 2).sum(axis=1)).reshape((-1,) + (1,) * (vv.ndim - 1))
+                out[base + ".weight"] = np.ascontiguousarray((g.reshape(norm.shape) * vv / norm).astype(np.float32))
+                done = True
+            elif k.endswith(gs):
+                done = True
+        if not done:
+            out[k] = np.ascontiguousarray(to_np(v).astype(np.float32))
+    return out
+
+
+def algorithmic_flops_per_frame(include_f0: bool = True) -> float:
+    """2*MAC of every conv of the path per mel frame (612.45 MFLOP with the F0 predictor)."""
+    f = 0.0
+    if include_f0:
+        f += 2 * (80 * 512 * 3 + 4 * 512 * 512 * 3 + 512)
+    f += 2 * 80 * 512 * 7
+    ups = [(512, 256, 16, 1), (256, 128, 11, 8), (128, 64, 7, 40)]      # (cin, cout, k, input steps per frame)
+    for cin, cout, k, steps in ups:
+        f += 2 * cin * cout * k * steps
+    for (k, cout, steps) in ((30, 256, 8), (6, 128, 40), (1, 64, 120)):
+        f += 2 * 18 * cout * k * steps
+    for stage, (c, steps) in enumerate(((256, 8), (128, 40), (64, 120))):
+        f += 6 * 2 * c * c * (7, 7, 11)[stage] * steps
+        for k in (3, 7, 11):
+            f += 6 * 2 * c * c * k * steps
+    f += 2 * 64 * 18 * 7 * 120
+    return f
+
+
+class HiFTVocoder:
+    """A HiFT generator resident on the current CUDA device.
+
+    ``state_dict``: upstream ``HiFTGenerator`` state dict (weight-norm parametrised or folded).
+    ``operand``: "fp16" (default; tensor-core operands, fp32 accumulate - meets the 1e-3 / 60 dB
+    parity bar), "bf16", or "fp32" (exact CUDA-core path).
+    """
+
+    def __init__(self, state_dict, operand: str = "fp16"):
+        torch = _torch()
+        if operand not in OPERANDS:
+            raise ValueError(f"operand must be one of {sorted(OPERANDS)}")
+        self.operand = operand
+        self._lib = _lib.load_library()
+        sm, major, minor = C.c_int(), C.c_int(), C.c_int()
+        check(self._lib.vt_device_check(C.byref(sm), C.byref(major), C.byref(minor)), "vt_device_check")
+        self.sm_count = sm.value
+        folded = fold_weight_norm(state_dict)
+        names = [k for k in folded if not k.endswith("num_batches_tracked")]
+        arr = (_lib.Tensor * len(names))()
+        keep = []
+        for i, k in enumerate(names):
+            a = folded[k]
+            if a.ndim == 0:
+                a = a.reshape(1)
+            if a.ndim > 4:
+                raise ValueError(f"{k}: rank {a.ndim} tensors are not part of HiFT")
+            keep.append((k.encode(), a))
+            arr[i].name = keep[-1][0]
+            arr[i].data = a.ctypes.data_as(C.c_void_p)
+            arr[i].ndim = a.ndim
+            for d in range(a.ndim):
+                arr[i].shape[d] = a.shape[d]
+        h = C.c_void_p()
+        check(self._lib.vt_hift_create(arr, len(names), OPERANDS[operand], C.byref(h)), "vt_hift_create")
+        self._h = h
+        self._ws = None
+        self._lock = threading.Lock()   # reference jobs run on up to 2 threads (backend/config.py:11)
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.last_launches = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.vt_hift_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ batching helpers
+    @staticmethod
+    def pack_mels(mels: Sequence, device=None):
+        """List of upstream-layout mels ``[80, T_b]`` -> (frame-major float32 ``[sum_T, 80]``, int32 T)."""
+        torch = _torch()
+        T = np.array([int(m.shape[-1]) for m in mels], dtype=np.int32)
+        rows = [m.reshape(N_MEL, -1).to(device or "cuda", torch.float32).t() for m in mels]
+        packed = torch.cat(rows, dim=0).contiguous() if rows else torch.zeros((0, N_MEL), device="cuda")
+        return packed, T
+
+    def workspace_bytes(self, B: int, total_T: int, T_max: int) -> int:
+        n = int(self._lib.vt_hift_workspace_bytes(self._h, B, total_T, T_max))
+        if n < 0:
+            raise BackendUnavailableError("vt_hift_workspace_bytes failed")
+        return n
+
+    def _workspace(self, torch, nbytes):
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    # ------------------------------------------------------------------ forward
+    def forward_packed(self, mel, T, *, f0=None, phase_vec=None, noise=None, seed: int = 0, out=None):
+        """``mel``: float32 CUDA ``[sum_T, 80]`` frame-major; ``T``: int32 host array of frames per
+        sequence.  Optional ``f0`` ``[sum_T]`` (Hz), ``phase_vec`` ``[B, 9]``, ``noise`` packed
+        ``[9, 480*T_b]`` blocks (see the header).  Returns the packed waveform ``[480*sum_T]``
+        (sequence b at ``480 * sum(T[:b])``)."""
+        torch = _torch()
+        T = np.ascontiguousarray(T, dtype=np.int32)
+        B = int(T.size)
+        total_T = int(T.sum())
+        if mel.dtype != torch.float32 or not mel.is_cuda or mel.numel() != total_T * N_MEL:
+            raise ValueError("mel must be a float32 CUDA tensor of shape [sum(T), 80]")
+        mel = mel.contiguous()
+        for name, t, n in (("f0", f0, total_T), ("phase_vec", phase_vec, B * N_HARMONICS),
+                           ("noise", noise, total_T * SAMPLES_PER_FRAME * N_HARMONICS)):
+            if t is not None and (t.dtype != torch.float32 or not t.is_cuda or t.numel() != n or not t.is_contiguous()):
+                raise ValueError(f"{name} must be a contiguous float32 CUDA tensor with {n} elements")
+        if out is None:
+            out = torch.empty(total_T * SAMPLES_PER_FRAME, dtype=torch.float32, device=self.device)
+        elif out.numel() < total_T * SAMPLES_PER_FRAME or out.dtype != torch.float32 or not out.is_cuda:
+            raise ValueError("out must be a float32 CUDA tensor with 480*sum(T) elements")
+        with self._lock:
+            ws = self._workspace(torch, self.workspace_bytes(B, total_T, int(T.max()) if B else 0))
+            ptr = lambda t: 0 if t is None else int(t.data_ptr())
+            rc = self._lib.vt_hift_forward(self._h, ptr(mel), T.ctypes.data_as(C.POINTER(C.c_int32)), B, ptr(f0),
+                                           ptr(phase_vec), ptr(noise), int(seed) & (2 ** 64 - 1), ptr(out), ptr(ws),
+                                           ws.numel(), int(torch.cuda.current_stream().cuda_stream))
+            check(rc, "vt_hift_forward")
+            self.last_launches = int(self._lib.vt_last_launch_count())
+        return out
+
+    def inference(self, mels: Sequence, *, f0: Optional[Sequence] = None, phase_vec=None, noise: Optional[Sequence] = None,
+                  seed: int = 0) -> List:
+        """Batched ``HiFTGenerator.inference``: list of mels ``[80, T_b]`` -> list of waveforms ``[480*T_b]``."""
+        torch = _torch()
+        mel, T = self.pack_mels(mels, self.device)
+        f0p = None if f0 is None else torch.cat([x.reshape(-1).to(self.device, torch.float32) for x in f0]).contiguous()
+        pv = None if phase_vec is None else torch.stack([p.reshape(-1) for p in phase_vec]).to(self.device, torch.float32).contiguous()
+        nz = None if noise is None else torch.cat([n.reshape(-1).to(self.device, torch.float32) for n in noise]).contiguous()
+        wav = self.forward_packed(mel, T, f0=f0p, phase_vec=pv, noise=nz, seed=seed)
+        off = np.concatenate([[0], np.cumsum(T.astype(np.int64) * SAMPLES_PER_FRAME)])
+        return [wav[off[i]:off[i + 1]] for i in range(len(T))]
+
+    def read_tap(self, name: str, seq: int, channels: int = 1):
+        """Intermediate of the last forward as float32 ``[rows, channels]`` (parity tests)."""
+        torch = _torch()
+        st = int(torch.cuda.current_stream().cuda_stream)
+        n = int(self._lib.vt_hift_read_tap(self._h, name.encode(), int(seq), 0, 0, 0, st))
+        if n < 0:
+            check(n, f"vt_hift_read_tap({name})")
+        out = torch.empty(max(n, 1), dtype=torch.float32, device=self.device)
+        n2 = int(self._lib.vt_hift_read_tap(self._h, name.encode(), int(seq), int(out.data_ptr()), out.numel(), 0, st))
+        if n2 < 0:
+            check(n2, f"vt_hift_read_tap({name})")
+        return out[:n].view(-1, channels)
