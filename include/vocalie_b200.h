@@ -169,6 +169,16 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T /* HOST */, i
 int64_t vt_hift_read_tap(vt_hift* h, const char* tap, int seq, float* out, int64_t capacity,
                          void* workspace, void* stream);
 
+/* Device-side timing of the last forward (CUDA events recorded on the launch stream).  With
+ * profiling enabled every vt_hift_forward records the whole call and each stage's run of
+ * ResBlock convolutions (the dominant, tensor-bound kernel class: 72 launches per forward).
+ * vt_hift_read_profile waits for the forward to finish and returns the device milliseconds of
+ * both, the algorithmic FLOPs (2*C_in*C_out*k per output step) of the ResBlock launches and
+ * their count - the numerator/denominator of bench.py's roofline object. */
+int vt_hift_set_profiling(vt_hift* h, int enable);
+int vt_hift_read_profile(vt_hift* h, double* total_ms, double* resblock_ms, double* resblock_flops,
+                         int* resblock_launches);
+
 /* Number of kernels launched by the last vt_hift_forward / vt_post_process on this thread. */
 int vt_last_launch_count(void);
 

@@ -1,12 +1,426 @@
-// Tensor-core (tcgen05/TMEM/TMA) convolution - placeholder until the kernel lands: reports that no
-// layer is supported so every conv runs on the CUDA-core path.
+// Tensor-core convolution for the ResBlock layers (95 % of the path's FLOPs): implicit GEMM on
+// tcgen05 with TMEM accumulators, sm_100a only.
+//
+//   out[q][co] = sum_j sum_ci act[q + j*dil - pad][ci] * W[co][ci][j]        C_in = C_out = C in {64,128,256}
+//
+// GEMM view per CTA tile: M = 128*MB time steps, N = C output channels, K = C*k.
+//   A (activations, fp16/bf16, channel-last rows) : the tile *with its halo* (128*MB + (k-1)*dil rows) is
+//      brought into shared memory ONCE as K-major no-swizzle panels [C/8][RA rows][8 ch]; every tap is the
+//      same panels read through a shared-memory descriptor whose start address is shifted by j*dil rows
+//      (16 B per row), so a k-tap conv costs one activation load, not k.  RA is odd => the 16-byte cp.async
+//      scatter that builds the panels is bank-conflict free.
+//   B (weights) : pre-packed on the host per (tap, 64-channel block) as the exact shared-memory image
+//      [8][C][8 ch]; streamed with 1-D bulk TMA copies (cp.async.bulk + mbarrier complete_tx) through a ring.
+//   D (fp32) : TMEM, double buffered (2 x MB x C columns) so the epilogue of tile i overlaps the MMAs of i+1.
+//
+// Warp roles (256 threads, persistent over a static round-robin tile schedule):
+//   warps 0-3 epilogue (tcgen05.ld -> bias/residual/Snake -> global), warp 4 MMA issuer + TMEM owner,
+//   warp 5 weight producer (bulk TMA), warps 6-7 activation producers (cp.async).
 #include "vt_hift.cuh"
+
+#include <cstring>
+
 namespace vt {
-bool conv_tc_supported(const ConvLayer&) { return false; }
-int conv_tc_tile_rows(const ConvLayer&) { return 128; }
-int pack_conv_tc(ConvLayer&, const std::vector<float>&, int, std::vector<void*>&) { return VT_OK; }
-int launch_conv_tc(const ConvArgs&, const ConvLayer&, int, const void*, int, int, cudaStream_t) {
-  set_error("tensor-core conv not built");
-  return VT_ERR_UNSUPPORTED;
+
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Bounded wait: a protocol bug must fault the launch, not hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Shared-memory matrix descriptor, K-major, SWIZZLE_NONE (canonical layout ((8,n),2):((16B,SBO),LBO)):
+// 8 rows x 16 B core matrices; SBO = byte distance between 8-row groups, LBO = between the two
+// 8-element K halves of one UMMA_K = 16 step.  Bits: [0,14) addr>>4, [16,30) LBO>>4, [32,46) SBO>>4,
+// [46,48) version = 1 (sm_100), [61,64) layout = 0.
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+template <typename T> struct Pack8;
+template <> struct Pack8<__half> {
+  static __device__ __forceinline__ uint4 pack(const float* y) {
+    __half2 a = __floats2half2_rn(y[0], y[1]), b = __floats2half2_rn(y[2], y[3]);
+    __half2 c = __floats2half2_rn(y[4], y[5]), d = __floats2half2_rn(y[6], y[7]);
+    return make_uint4(*reinterpret_cast<unsigned*>(&a), *reinterpret_cast<unsigned*>(&b),
+                      *reinterpret_cast<unsigned*>(&c), *reinterpret_cast<unsigned*>(&d));
+  }
+};
+template <> struct Pack8<__nv_bfloat16> {
+  static __device__ __forceinline__ uint4 pack(const float* y) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(y[0], y[1]), b = __floats2bfloat162_rn(y[2], y[3]);
+    __nv_bfloat162 c = __floats2bfloat162_rn(y[4], y[5]), d = __floats2bfloat162_rn(y[6], y[7]);
+    return make_uint4(*reinterpret_cast<unsigned*>(&a), *reinterpret_cast<unsigned*>(&b),
+                      *reinterpret_cast<unsigned*>(&c), *reinterpret_cast<unsigned*>(&d));
+  }
+};
+
+__device__ __forceinline__ float snake_f(float v, float alpha) {
+  const float s = sinf(v * alpha);
+  return v + (1.0f / (alpha + 1e-9f)) * (s * s);
+}
+
+template <int C, int MB>
+struct Cfg {
+  static constexpr int RA = 128 * MB + 51;          // rows of the activation panels (odd; halo <= 50)
+  static constexpr int KC = C / 8;                  // 16-byte K chunks per row
+  static constexpr int A_BYTES = KC * RA * 16;
+  static constexpr int W_BYTES = C * 128;           // one (tap, 64-channel block) weight chunk
+  static constexpr int ACC_COLS = MB * C;
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;    // 256 or 512: a power of two
+};
+
+template <int C, int MB, int A_ST, int W_ST, typename ActT>
+__global__ void __launch_bounds__(256, 1)
+k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t idesc) {
+  using K = Cfg<C, MB>;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* sA = smem;
+  uint8_t* sW = sA + A_ST * K::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + W_ST * K::W_BYTES);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + A_ST;
+  uint64_t* w_full = a_empty + A_ST;
+  uint64_t* w_empty = w_full + W_ST;
+  uint64_t* acc_full = w_empty + W_ST;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < A_ST; ++i) { mbar_init(&a_full[i], 64); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < W_ST; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)K::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int nchunks = a.k * (C / 64);
+  const int n_tiles = a.n_tiles;
+
+  if (warp >= 6) {
+    // ---------------- activation producers: halo tile -> K-major panels
+    const int pt = threadIdx.x - 192;
+    const ActT* in = reinterpret_cast<const ActT*>(a.in_act);
+    const int r_need = 128 * MB + (a.k - 1) * a.dil;
+    const int pieces = r_need * K::KC;
+    int it = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      const int ab = it % A_ST;
+      const uint32_t ph = (uint32_t)(it / A_ST) & 1u;
+      mbar_wait(&a_empty[ab], ph ^ 1u);
+      const ConvTile tile = a.tiles[t];
+      const ActT* src = in + (tile.in_row0 + tile.q0 - a.pad) * (long long)C;
+      const uint32_t dst = smem_u32(sA + ab * K::A_BYTES);
+      for (int p = pt; p < pieces; p += 64) {
+        const int r = p / K::KC, c = p - r * K::KC;
+        cp_async16(dst + (uint32_t)(c * K::RA + r) * 16u, src + (long long)r * C + c * 8);
+      }
+      cp_async_wait_all();
+      fence_proxy_async();
+      mbar_arrive(&a_full[ab]);
+    }
+  } else if (warp == 5) {
+    // ---------------- weight producer: one bulk copy per (tap, 64-channel block)
+    if (lane == 0) {
+      uint32_t g = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        for (int c = 0; c < nchunks; ++c, ++g) {
+          const uint32_t ws = g % W_ST, ph = (g / W_ST) & 1u;
+          mbar_wait(&w_empty[ws], ph ^ 1u);
+          mbar_arrive_expect_tx(&w_full[ws], K::W_BYTES);
+          bulk_g2s(sW + ws * K::W_BYTES, wtc + (size_t)c * K::W_BYTES, K::W_BYTES, &w_full[ws]);
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // ---------------- MMA issuer (one thread)
+    if (lane == 0) {
+      uint32_t g = 0;
+      int it = 0;
+      const uint32_t sA_addr = smem_u32(sA), sW_addr = smem_u32(sW);
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        const int ab = it % A_ST;
+        const uint32_t aph = (uint32_t)(it / A_ST) & 1u;
+        const int as = it & 1;
+        const uint32_t asph = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(&acc_empty[as], asph ^ 1u);
+        mbar_wait(&a_full[ab], aph);
+        tc_fence_after();
+        for (int c = 0; c < nchunks; ++c, ++g) {
+          const int j = c / (C / 64), cb = c - j * (C / 64);
+          const uint32_t ws = g % W_ST, wph = (g / W_ST) & 1u;
+          mbar_wait(&w_full[ws], wph);
+          tc_fence_after();
+#pragma unroll
+          for (int mb = 0; mb < MB; ++mb) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint32_t a_addr = sA_addr + ab * K::A_BYTES +
+                                      (uint32_t)((cb * 8 + ks * 2) * K::RA + mb * 128 + j * a.dil) * 16u;
+              const uint32_t b_addr = sW_addr + ws * K::W_BYTES + (uint32_t)(ks * 2 * C) * 16u;
+              umma_f16(tmem_base + (uint32_t)(as * K::ACC_COLS + mb * C), make_desc(a_addr, K::RA * 16, 128),
+                       make_desc(b_addr, C * 16, 128), idesc, (c > 0 || ks > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(&w_empty[ws]);
+        }
+        umma_commit(&a_empty[ab]);
+        umma_commit(&acc_full[as]);
+      }
+    }
+  } else {
+    // ---------------- epilogue warps 0-3: TMEM lanes 32*warp .. +31, one output row per thread
+    int it = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t asph = (uint32_t)(it >> 1) & 1u;
+      const ConvTile tile = a.tiles[t];
+      mbar_wait(&acc_full[as], asph);
+      tc_fence_after();
+#pragma unroll
+      for (int mb = 0; mb < MB; ++mb) {
+        const int rl = mb * 128 + warp * 32 + lane;
+        const bool valid = rl < tile.n;
+        const long long rowbase = (tile.out_row0 + tile.q0 + rl) * (long long)C;
+        for (int c0 = 0; c0 < C; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * K::ACC_COLS + mb * C + c0), v);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int g8 = 0; g8 < 4; ++g8) {
+              const int cc = c0 + g8 * 8;
+              const long long idx = rowbase + cc;
+              float x[8];
+              const float4 b0 = *reinterpret_cast<const float4*>(a.bias + cc);
+              const float4 b1 = *reinterpret_cast<const float4*>(a.bias + cc + 4);
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[g8 * 8 + e]) + bb[e];
+              if (a.res1) {
+                const float4 r0 = *reinterpret_cast<const float4*>(a.res1 + idx);
+                const float4 r1 = *reinterpret_cast<const float4*>(a.res1 + idx + 4);
+                x[0] += r0.x; x[1] += r0.y; x[2] += r0.z; x[3] += r0.w;
+                x[4] += r1.x; x[5] += r1.y; x[6] += r1.z; x[7] += r1.w;
+              }
+              if (a.res2) {
+                const float4 r0 = *reinterpret_cast<const float4*>(a.res2 + idx);
+                const float4 r1 = *reinterpret_cast<const float4*>(a.res2 + idx + 4);
+                x[0] += r0.x; x[1] += r0.y; x[2] += r0.z; x[3] += r0.w;
+                x[4] += r1.x; x[5] += r1.y; x[6] += r1.z; x[7] += r1.w;
+              }
+              if (a.out) {
+                float o[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = x[e] * a.out_scale;
+                if (a.out_accum) {
+                  const float4 p0 = *reinterpret_cast<const float4*>(a.out + idx);
+                  const float4 p1 = *reinterpret_cast<const float4*>(a.out + idx + 4);
+                  o[0] += p0.x; o[1] += p0.y; o[2] += p0.z; o[3] += p0.w;
+                  o[4] += p1.x; o[5] += p1.y; o[6] += p1.z; o[7] += p1.w;
+                }
+                *reinterpret_cast<float4*>(a.out + idx) = make_float4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<float4*>(a.out + idx + 4) = make_float4(o[4], o[5], o[6], o[7]);
+              }
+#pragma unroll
+              for (int s = 0; s < 3; ++s) {
+                if (!a.act[s].dst) continue;
+                float y[8];
+                if (a.act[s].kind == ACT_SNAKE) {
+                  const float4 a0 = *reinterpret_cast<const float4*>(a.act[s].alpha + cc);
+                  const float4 a1 = *reinterpret_cast<const float4*>(a.act[s].alpha + cc + 4);
+                  const float al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) y[e] = snake_f(x[e], al[e]);
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) y[e] = x[e];
+                }
+                *reinterpret_cast<uint4*>(reinterpret_cast<ActT*>(a.act[s].dst) + idx) = Pack8<ActT>::pack(y);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)K::TMEM_COLS) : "memory");
+  }
+}
+
+template <int C, int MB, int A_ST, int W_ST>
+constexpr int smem_bytes() {
+  return A_ST * Cfg<C, MB>::A_BYTES + W_ST * Cfg<C, MB>::W_BYTES + (2 * A_ST + 2 * W_ST + 4) * 8 + 16;
+}
+
+template <int C, int MB, int A_ST, int W_ST, typename ActT>
+int launch(const ConvArgs& a, const void* wtc, uint32_t idesc, int grid, cudaStream_t st) {
+  constexpr int smem = smem_bytes<C, MB, A_ST, W_ST>();
+  static bool configured = false;
+  if (!configured) {
+    VT_CUDA_OK(cudaFuncSetAttribute(k_conv_tc<C, MB, A_ST, W_ST, ActT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  k_conv_tc<C, MB, A_ST, W_ST, ActT><<<grid, 256, smem, st>>>(a, reinterpret_cast<const uint8_t*>(wtc), idesc);
+  VT_LAUNCHED();
+  return VT_OK;
+}
+
+}  // namespace tc
+
+bool conv_tc_supported(const ConvLayer& L) {
+  return L.cin == L.cout && (L.cin == 64 || L.cin == 128 || L.cin == 256) && L.stride == 1 && L.out_mul == 1 &&
+         L.k >= 1 && (L.k - 1) * L.dil <= 50 && L.pad <= kGap;
+}
+
+int conv_tc_tile_rows(const ConvLayer& L) { return L.cin == 256 ? 128 : 256; }
+
+// [k][cin][cout] fp32 -> per (tap j, 64-channel block cb) the shared-memory image [8][C][8] in the operand type
+int pack_conv_tc(ConvLayer& L, const std::vector<float>& w, int act_elem, std::vector<void*>& allocs) {
+  const int C = L.cin, k = L.k;
+  const size_t n = (size_t)k * C * C;
+  std::vector<uint16_t> img(n);
+  size_t o = 0;
+  for (int j = 0; j < k; ++j)
+    for (int cb = 0; cb < C / 64; ++cb)
+      for (int k8 = 0; k8 < 8; ++k8)
+        for (int co = 0; co < C; ++co)
+          for (int e = 0; e < 8; ++e) {
+            const float v = w[((size_t)j * C + cb * 64 + k8 * 8 + e) * C + co];
+            uint16_t bits;
+            if (act_elem == ELEM_F16) {
+              const __half hv = __float2half_rn(v);
+              std::memcpy(&bits, &hv, 2);
+            } else {
+              const __nv_bfloat16 bv = __float2bfloat16_rn(v);
+              std::memcpy(&bits, &bv, 2);
+            }
+            img[o++] = bits;
+          }
+  void* p = nullptr;
+  VT_CUDA_OK(cudaMalloc(&p, n * 2));
+  allocs.push_back(p);
+  VT_CUDA_OK(cudaMemcpy(p, img.data(), n * 2, cudaMemcpyHostToDevice));
+  L.w_tc = p;
+  return VT_OK;
+}
+
+int launch_conv_tc(const ConvArgs& a_in, const ConvLayer& L, int act_elem, const void* tc_tiles, int n_tc_tiles,
+                   int tile_rows, cudaStream_t st) {
+  VT_REQUIRE(L.w_tc && a_in.in_act && (act_elem == ELEM_F16 || act_elem == ELEM_BF16), "conv_tc: layer %s not packed", L.name.c_str());
+  if (n_tc_tiles == 0) return VT_OK;
+  ConvArgs a = a_in;
+  a.tiles = reinterpret_cast<const ConvTile*>(tc_tiles);
+  a.n_tiles = n_tc_tiles;
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    VT_CUDA_OK(cudaGetDevice(&dev));
+    VT_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int grid = n_tc_tiles < sm_count ? n_tc_tiles : sm_count;
+  const uint32_t fmt = act_elem == ELEM_F16 ? 0u : 1u;
+  // instruction descriptor: D = f32 (bits 4-5 = 1), A/B format (bits 7-9, 10-12), K-major A and B,
+  // N>>3 at bits 17-22, M>>4 at bits 24-28
+  const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(L.cout >> 3) << 17) | ((128u >> 4) << 24);
+  const bool h = act_elem == ELEM_F16;
+  (void)tile_rows;
+  switch (L.cin) {
+    case 64:
+      return h ? tc::launch<64, 2, 2, 4, __half>(a, L.w_tc, idesc, grid, st)
+               : tc::launch<64, 2, 2, 4, __nv_bfloat16>(a, L.w_tc, idesc, grid, st);
+    case 128:
+      return h ? tc::launch<128, 2, 2, 3, __half>(a, L.w_tc, idesc, grid, st)
+               : tc::launch<128, 2, 2, 3, __nv_bfloat16>(a, L.w_tc, idesc, grid, st);
+    case 256:
+      return h ? tc::launch<256, 1, 1, 4, __half>(a, L.w_tc, idesc, grid, st)
+               : tc::launch<256, 1, 1, 4, __nv_bfloat16>(a, L.w_tc, idesc, grid, st);
+    default:
+      VT_REQUIRE(false, "conv_tc: unsupported channel count %d", L.cin);
+  }
+  return VT_OK;
+}
+
 }  // namespace vt

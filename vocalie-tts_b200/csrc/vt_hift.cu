@@ -83,6 +83,13 @@ struct vt_hift {
   Plan plan;
   Workspace ws{};
   bool have_forward = false;
+  // profiling (vt_hift_set_profiling): events around the whole forward and around each stage's
+  // run of resblock convolutions (the dominant kernel class)
+  bool profiling = false;
+  cudaEvent_t ev_fwd[2] = {nullptr, nullptr};
+  cudaEvent_t ev_rb[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+  double rb_flops = 0;
+  int rb_launches = 0;
 };
 
 namespace vt {
@@ -414,6 +421,9 @@ void vt_hift_destroy(vt_hift* h) {
   if (!h) return;
   for (void* p : h->allocs) cudaFree(p);
   if (h->plan.d_block) cudaFree(h->plan.d_block);
+  for (int i = 0; i < 2; ++i) if (h->ev_fwd[i]) cudaEventDestroy(h->ev_fwd[i]);
+  for (int l = 0; l < 3; ++l)
+    for (int i = 0; i < 2; ++i) if (h->ev_rb[l][i]) cudaEventDestroy(h->ev_rb[l][i]);
   delete h;
 }
 
@@ -448,6 +458,12 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
   h->ws = w;
   h->have_forward = true;
   const int ae = h->act_elem;
+  const bool prof = h->profiling;
+  if (prof) {
+    VT_CUDA_OK(cudaEventRecord(h->ev_fwd[0], st));
+    h->rb_flops = 0;
+    h->rb_launches = 0;
+  }
 
   if (h->use_tc) {
     for (int l = 0; l < 3; ++l)
@@ -512,6 +528,13 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
       if (rc) return rc;
     }
     // source_resblocks[i]; its last conv also adds the upsampled stream: x = ups + si
+    if (prof) {
+      VT_CUDA_OK(cudaEventRecord(h->ev_rb[i][0], st));
+      const double steps = (double)kLevelMul[i] * (double)total_T + (i == 2 ? B : 0);
+      const double c = (double)(kBase >> (i + 1));
+      h->rb_flops += steps * 2.0 * c * c * 6.0 * (kSrcRbKernels[i] + kRbKernels[0] + kRbKernels[1] + kRbKernels[2]);
+      h->rb_launches += 24;
+    }
     for (int j = 0; j < 3; ++j) {
       ConvArgs a = base_args(h->src_c1[i][j], P, P.lvl[i]);
       a.in_act = w.A[i][1];
@@ -556,6 +579,7 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
         if (rc) return rc;
       }
     }
+    if (prof) VT_CUDA_OK(cudaEventRecord(h->ev_rb[i][1], st));
   }
   // ---- conv_post( leaky_relu(x) ) with the default slope 0.01, then the spectral head
   {
@@ -566,7 +590,39 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
     rc = launch_conv_ref(a, ae, st);
     if (rc) return rc;
   }
-  return launch_istft_head(w.post, P.d_mel_off, P.d_T, P.d_off[2], B, P.T_max, h->trim_fade, wav, st);
+  rc = launch_istft_head(w.post, P.d_mel_off, P.d_T, P.d_off[2], B, P.T_max, h->trim_fade, wav, st);
+  if (rc) return rc;
+  if (prof) VT_CUDA_OK(cudaEventRecord(h->ev_fwd[1], st));
+  return VT_OK;
+}
+
+int vt_hift_set_profiling(vt_hift* h, int enable) {
+  VT_REQUIRE(h != nullptr, "vt_hift_set_profiling: NULL handle");
+  if (enable && !h->ev_fwd[0]) {
+    for (int i = 0; i < 2; ++i) VT_CUDA_OK(cudaEventCreate(&h->ev_fwd[i]));
+    for (int l = 0; l < 3; ++l)
+      for (int i = 0; i < 2; ++i) VT_CUDA_OK(cudaEventCreate(&h->ev_rb[l][i]));
+  }
+  h->profiling = enable != 0;
+  return VT_OK;
+}
+
+int vt_hift_read_profile(vt_hift* h, double* total_ms, double* resblock_ms, double* resblock_flops,
+                         int* resblock_launches) {
+  VT_REQUIRE(h != nullptr && h->profiling && h->have_forward, "vt_hift_read_profile: profiling is off or no forward ran");
+  VT_CUDA_OK(cudaEventSynchronize(h->ev_fwd[1]));
+  float ms = 0.f;
+  VT_CUDA_OK(cudaEventElapsedTime(&ms, h->ev_fwd[0], h->ev_fwd[1]));
+  if (total_ms) *total_ms = ms;
+  double rb = 0;
+  for (int l = 0; l < 3; ++l) {
+    VT_CUDA_OK(cudaEventElapsedTime(&ms, h->ev_rb[l][0], h->ev_rb[l][1]));
+    rb += ms;
+  }
+  if (resblock_ms) *resblock_ms = rb;
+  if (resblock_flops) *resblock_flops = h->rb_flops;
+  if (resblock_launches) *resblock_launches = h->rb_launches;
+  return VT_OK;
 }
 
 

@@ -198,6 +198,15 @@ class HiFTVocoder:
         off = np.concatenate([[0], np.cumsum(T.astype(np.int64) * SAMPLES_PER_FRAME)])
         return [wav[off[i]:off[i + 1]] for i in range(len(T))]
 
+    def set_profiling(self, enable: bool = True):
+        check(self._lib.vt_hift_set_profiling(self._h, 1 if enable else 0), "vt_hift_set_profiling")
+
+    def read_profile(self) -> dict:
+        """Device timing of the last forward: {'total_ms', 'resblock_ms', 'resblock_flops', 'resblock_launches'}."""
+        t, r, f, n = C.c_double(), C.c_double(), C.c_double(), C.c_int()
+        check(self._lib.vt_hift_read_profile(self._h, C.byref(t), C.byref(r), C.byref(f), C.byref(n)), "vt_hift_read_profile")
+        return {"total_ms": t.value, "resblock_ms": r.value, "resblock_flops": f.value, "resblock_launches": n.value}
+
     def read_tap(self, name: str, seq: int, channels: int = 1):
         """Intermediate of the last forward as float32 ``[rows, channels]`` (parity tests)."""
         torch = _torch()
@@ -210,3 +219,52 @@ class HiFTVocoder:
         if n2 < 0:
             check(n2, f"vt_hift_read_tap({name})")
         return out[:n].view(-1, channels)
+
+
+def random_state_dict(seed: int = 0) -> Dict[str, np.ndarray]:
+    """Random-init HiFT weights in upstream state-dict naming (benchmarks and smoke tests - there
+    is no network to fetch ``ResembleAI/chatterbox``'s ``s3gen`` checkpoint).  Follows upstream
+    initialisation (SURVEY 8(d) W_init): ``normal(0, 0.01)`` on the weight-normed convs of ups /
+    resblocks / source_resblocks / conv_post, ``U(+-1/sqrt(fan_in))`` elsewhere, Snake alpha = 1,
+    weight-norm gain ``g = ||v||``."""
+    rng = np.random.default_rng(seed)
+    sd: Dict[str, np.ndarray] = {}
+
+    def conv(name, cout, cin, k, normal, wn=True, transposed=False):
+        shape = (cin, cout, k) if transposed else (cout, cin, k)
+        fan_in = (cout if transposed else cin) * k
+        if normal:
+            v = rng.standard_normal(shape).astype(np.float32) * np.float32(0.01)
+        else:
+            v = rng.uniform(-1, 1, shape).astype(np.float32) / np.float32(np.sqrt(fan_in))
+        if wn:
+            sd[name + ".parametrizations.weight.original1"] = v
+            sd[name + ".parametrizations.weight.original0"] = np.sqrt((v.reshape(v.shape[0], -1) ** 2).sum(1)).reshape(-1, 1, 1).astype(np.float32)
+        else:
+            sd[name + ".weight"] = v
+        sd[name + ".bias"] = (rng.uniform(-1, 1, cout).astype(np.float32) / np.float32(np.sqrt(fan_in)))
+
+    conv("conv_pre", 512, 80, 7, False)
+    for i, (k, (sk, cout)) in enumerate(zip((16, 11, 7), ((30, 256), (6, 128), (1, 64)))):
+        conv(f"ups.{i}", cout, 512 >> i, k, True, transposed=True)
+        conv(f"source_downs.{i}", cout, 18, sk, False, wn=False)
+        for j in range(3):
+            for c12 in ("convs1", "convs2"):
+                conv(f"source_resblocks.{i}.{c12}.{j}", cout, cout, (7, 7, 11)[i], True)
+            for a in ("activations1", "activations2"):
+                sd[f"source_resblocks.{i}.{a}.{j}.alpha"] = np.ones(cout, np.float32)
+        for kk, rk in enumerate((3, 7, 11)):
+            r = i * 3 + kk
+            for j in range(3):
+                for c12 in ("convs1", "convs2"):
+                    conv(f"resblocks.{r}.{c12}.{j}", cout, cout, rk, True)
+                for a in ("activations1", "activations2"):
+                    sd[f"resblocks.{r}.{a}.{j}.alpha"] = np.ones(cout, np.float32)
+    conv("conv_post", 18, 64, 7, True)
+    for i in range(5):
+        conv(f"f0_predictor.condnet.{2 * i}", 512, 80 if i == 0 else 512, 3, False)
+    sd["f0_predictor.classifier.weight"] = rng.uniform(-1, 1, (1, 512)).astype(np.float32) / np.float32(np.sqrt(512))
+    sd["f0_predictor.classifier.bias"] = rng.uniform(-1, 1, 1).astype(np.float32) / np.float32(np.sqrt(512))
+    sd["m_source.l_linear.weight"] = rng.uniform(-1, 1, (1, 9)).astype(np.float32) / np.float32(3.0)
+    sd["m_source.l_linear.bias"] = rng.uniform(-1, 1, 1).astype(np.float32) / np.float32(3.0)
+    return sd

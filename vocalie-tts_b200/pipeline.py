@@ -1,0 +1,111 @@
+"""Mel -> finished audio on the GPU: the B200 replacement of the reference's serial chunk loop
+tail (backend/shared/tts_pipeline.py:353-409 after synthesis, plus the post-processing of
+tts_pipeline.py:162-274 / audio_edit.py:16-79), batched over the independent chunks of a job.
+
+``VocoderPipeline.run`` is the call a user of this package makes: host mel buffers in, host audio
+out.  ``run_device`` is the same with device-resident tensors (no copies) for callers that
+already hold mels on the GPU.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import post as _post
+from .hift import HiFTVocoder, SAMPLES_PER_FRAME, S3GEN_SR, N_MEL, _torch
+
+
+@dataclass
+class JobResult:
+    audio: "object"              # float32 (or int16) tensor/array holding the stitched job audio
+    total_samples: int
+    segments: Optional[np.ndarray]   # [n_chunks, 8] per-chunk start,end,peak,scale,dst,len,peak_used,-
+    sr: int = S3GEN_SR
+
+
+class VocoderPipeline:
+    """HiFT vocoder + per-chunk post-processing + gap stitching on one GPU."""
+
+    def __init__(self, vocoder: HiFTVocoder, *, chunk_gap_ms: int = 250, trim_silence: bool = True,
+                 normalize: bool = True, target_dbfs: float = -1.0, fade_ms: int = 10,
+                 zero_cross_radius_ms: int = 10, silence_threshold: float = _post.SILENCE_THRESHOLD,
+                 silence_min_ms: int = _post.SILENCE_MIN_MS, out_pcm16: bool = False):
+        self.voc = vocoder
+        self.sr = S3GEN_SR
+        self.opts = dict(chunk_gap_ms=int(chunk_gap_ms), trim_silence=bool(trim_silence), normalize=bool(normalize),
+                         target_dbfs=float(target_dbfs), fade_ms=int(fade_ms), zero_cross_radius_ms=int(zero_cross_radius_ms),
+                         silence_threshold=float(silence_threshold), silence_min_ms=int(silence_min_ms),
+                         out_pcm16=bool(out_pcm16))
+        self._host_in = None
+        self._host_out = None
+        self._dev_in = None
+        self._wav = None
+        self._out = None
+        self.last_launches = 0
+
+    def post_params(self, n_chunks: int):
+        o = self.opts
+        sr = self.sr
+        gap_on = o["chunk_gap_ms"] > 0 and n_chunks > 1
+        fade = _post._ms_to_frames(sr, o["fade_ms"])
+        return _post.make_params(
+            sr=sr, trim=1 if o["trim_silence"] else 0, silence_threshold=o["silence_threshold"],
+            min_silence_frames=_post._ms_to_frames(sr, o["silence_min_ms"]),
+            snap_radius=_post._ms_to_frames(sr, o["zero_cross_radius_ms"]) if o["trim_silence"] else -1,
+            fade_in_frames=fade if gap_on else 0, fade_out_frames=fade if gap_on else 0, stitch=1,
+            gap_frames=_post._ms_to_frames(sr, o["chunk_gap_ms"]) if gap_on else 0,
+            normalize=1 if o["normalize"] else 0, target_peak=float(10 ** (o["target_dbfs"] / 20.0)), concat=1,
+            out_pcm16=1 if o["out_pcm16"] else 0)
+
+    def run_device(self, mel, T, *, f0=None, phase_vec=None, noise=None, seed: int = 0, read_back: bool = False) -> JobResult:
+        """``mel``: float32 CUDA [sum_T, 80]; ``T``: int32 frames per chunk (host)."""
+        torch = _torch()
+        T = np.ascontiguousarray(T, dtype=np.int32)
+        n = int(T.astype(np.int64).sum()) * SAMPLES_PER_FRAME
+        if self._wav is None or self._wav.numel() < n + 4:
+            self._wav = torch.empty(n + 4, dtype=torch.float32, device=self.voc.device)
+        wav = self.voc.forward_packed(mel, T, f0=f0, phase_vec=phase_vec, noise=noise, seed=seed, out=self._wav)
+        seg_off = np.concatenate([[0], np.cumsum(T.astype(np.int64) * SAMPLES_PER_FRAME)])
+        prm = self.post_params(len(T))
+        cap = n + max(len(T) - 1, 0) * int(prm.gap_frames)
+        odt = torch.int16 if prm.out_pcm16 else torch.float32
+        if self._out is None or self._out.numel() < max(cap, 4) or self._out.dtype != odt:
+            self._out = torch.empty(max(cap, 4), dtype=odt, device=self.voc.device)
+        r = _post.post_process_device(wav, seg_off, prm, out=self._out, read_back=read_back)
+        # the library's per-thread launch counter is reset by vt_hift_forward and keeps counting through the post calls
+        self.last_launches = _post.last_launch_count()
+        return JobResult(r.out, r.total if r.total is not None else cap, r.results)
+
+    def run(self, mel_host, T, *, seed: int = 0) -> JobResult:
+        """Host in / host out: ``mel_host`` float32 [sum_T, 80] (numpy or CPU tensor; pinned staging is
+        managed here), returns the stitched job audio as a numpy array of exactly the right length."""
+        torch = _torch()
+        T = np.ascontiguousarray(T, dtype=np.int32)
+        total_T = int(T.astype(np.int64).sum())
+        src = torch.as_tensor(mel_host, dtype=torch.float32).reshape(total_T, N_MEL)
+        if self._host_in is None or self._host_in.numel() < src.numel():
+            self._host_in = torch.empty(src.numel(), dtype=torch.float32).pin_memory()
+            self._dev_in = torch.empty(src.numel(), dtype=torch.float32, device=self.voc.device)
+        hin = self._host_in[: src.numel()].view(total_T, N_MEL)
+        if src.data_ptr() != hin.data_ptr():
+            hin.copy_(src)
+        dev = self._dev_in[: src.numel()].view(total_T, N_MEL)
+        dev.copy_(hin, non_blocking=True)
+        res = self.run_device(dev, T, seed=seed, read_back=True)
+        n = int(res.total_samples)
+        if self._host_out is None or self._host_out.numel() < n or self._host_out.dtype != res.audio.dtype:
+            self._host_out = torch.empty(max(n, 4), dtype=res.audio.dtype).pin_memory()
+        self._host_out[:n].copy_(res.audio[:n], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return JobResult(self._host_out[:n].numpy(), n, res.segments)
+
+    def pinned_input(self, total_T: int):
+        """A pinned host buffer [total_T, 80] callers can fill in place to skip the staging copy."""
+        torch = _torch()
+        n = total_T * N_MEL
+        if self._host_in is None or self._host_in.numel() < n:
+            self._host_in = torch.empty(n, dtype=torch.float32).pin_memory()
+            self._dev_in = torch.empty(n, dtype=torch.float32, device=self.voc.device)
+        return self._host_in[:n].view(total_T, N_MEL)

@@ -69,6 +69,11 @@ class _Workspace:
         return cls.buf
 
 
+def last_launch_count() -> int:
+    """Kernels launched by the calling thread's last post call (vt_last_launch_count)."""
+    return int(_lib.load_library().vt_last_launch_count())
+
+
 def make_params(*, sr=TARGET_SR, trim=0, silence_threshold=SILENCE_THRESHOLD, min_silence_frames=0,
                 snap_radius=-1, fade_in_frames=0, fade_out_frames=0, stitch=0, gap_frames=0,
                 normalize=0, clip=0, target_peak=1.0, concat=1, out_pcm16=0) -> PostParams:
