@@ -120,9 +120,31 @@ template <> struct Pack8<__nv_bfloat16> {
   }
 };
 
+template <typename T> struct Pack4;
+template <> struct Pack4<__half> {
+  static __device__ __forceinline__ uint2 pack(const float* y) {
+    __half2 a = __floats2half2_rn(y[0], y[1]), b = __floats2half2_rn(y[2], y[3]);
+    return make_uint2(*reinterpret_cast<unsigned*>(&a), *reinterpret_cast<unsigned*>(&b));
+  }
+};
+template <> struct Pack4<__nv_bfloat16> {
+  static __device__ __forceinline__ uint2 pack(const float* y) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(y[0], y[1]), b = __floats2bfloat162_rn(y[2], y[3]);
+    return make_uint2(*reinterpret_cast<unsigned*>(&a), *reinterpret_cast<unsigned*>(&b));
+  }
+};
+
+constexpr int kStageLd = 36;   // floats per staged row (32 + 4 pad: conflict-free 16-byte accesses both ways)
+
+// Snake with a two-constant Cody-Waite reduction to [-pi, pi] and the SFU sine: absolute error
+// ~1e-6 for |alpha*x| < 1e3, two orders below the operand rounding of the tensor-core path.
 __device__ __forceinline__ float snake_f(float v, float alpha) {
-  const float s = sinf(v * alpha);
-  return v + (1.0f / (alpha + 1e-9f)) * (s * s);
+  const float t = v * alpha;
+  const float n = rintf(t * 0.15915494309189535f);
+  float r = fmaf(n, -6.2831854820251465f, t);
+  r = fmaf(n, 1.7484555e-7f, r);
+  const float s = __sinf(r);
+  return fmaf(__fdividef(1.0f, alpha + 1e-9f), s * s, v);
 }
 
 template <int C, int MB>
@@ -150,6 +172,7 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
   uint64_t* acc_full = w_empty + W_ST;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* stage_all = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(tmem_slot) + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -244,7 +267,13 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
       }
     }
   } else {
-    // ---------------- epilogue warps 0-3: TMEM lanes 32*warp .. +31, one output row per thread
+    // ---------------- epilogue warps 0-3: TMEM lanes 32*warp .. +31
+    // tcgen05.ld gives every thread 32 columns of ITS row; global memory wants a warp to touch whole
+    // rows.  Each 32x32 fp32 block is transposed through a padded shared-memory stage so that every
+    // global instruction covers 4 rows x 128 contiguous bytes (4 wavefronts instead of 32).
+    float* stage = stage_all + warp * (32 * kStageLd);
+    const int sub = lane & 7;          // which float4 of a 32-column block
+    const int rsub = lane >> 3;        // which of the 4 rows of an iteration
     int it = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
       const int as = it & 1;
@@ -252,67 +281,63 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
       const ConvTile tile = a.tiles[t];
       mbar_wait(&acc_full[as], asph);
       tc_fence_after();
-#pragma unroll
+#pragma unroll 1
       for (int mb = 0; mb < MB; ++mb) {
-        const int rl = mb * 128 + warp * 32 + lane;
-        const bool valid = rl < tile.n;
-        const long long rowbase = (tile.out_row0 + tile.q0 + rl) * (long long)C;
+        const int row0 = mb * 128 + warp * 32;                       // tile-local row of this warp's lane 0
+        const long long base0 = (tile.out_row0 + tile.q0 + row0) * (long long)C;
+#pragma unroll 1
         for (int c0 = 0; c0 < C; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * K::ACC_COLS + mb * C + c0), v);
           tmem_ld_wait();
-          if (valid) {
+          __syncwarp();
 #pragma unroll
-            for (int g8 = 0; g8 < 4; ++g8) {
-              const int cc = c0 + g8 * 8;
-              const long long idx = rowbase + cc;
-              float x[8];
-              const float4 b0 = *reinterpret_cast<const float4*>(a.bias + cc);
-              const float4 b1 = *reinterpret_cast<const float4*>(a.bias + cc + 4);
-              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          for (int g = 0; g < 8; ++g)
+            *reinterpret_cast<float4*>(stage + lane * kStageLd + g * 4) =
+                make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]),
+                            __uint_as_float(v[4 * g + 3]));
+          __syncwarp();
+          const int cc = c0 + sub * 4;
+          const float4 bias = *reinterpret_cast<const float4*>(a.bias + cc);
+          float4 al[3];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[g8 * 8 + e]) + bb[e];
-              if (a.res1) {
-                const float4 r0 = *reinterpret_cast<const float4*>(a.res1 + idx);
-                const float4 r1 = *reinterpret_cast<const float4*>(a.res1 + idx + 4);
-                x[0] += r0.x; x[1] += r0.y; x[2] += r0.z; x[3] += r0.w;
-                x[4] += r1.x; x[5] += r1.y; x[6] += r1.z; x[7] += r1.w;
+          for (int s = 0; s < 3; ++s)
+            al[s] = (a.act[s].dst && a.act[s].kind == ACT_SNAKE) ? *reinterpret_cast<const float4*>(a.act[s].alpha + cc)
+                                                                  : make_float4(1.f, 1.f, 1.f, 1.f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + rsub;
+            if (row0 + r >= tile.n) continue;
+            const long long idx = base0 + (long long)r * C + cc;
+            const float4 acc = *reinterpret_cast<const float4*>(stage + r * kStageLd + sub * 4);
+            float x[4] = {acc.x + bias.x, acc.y + bias.y, acc.z + bias.z, acc.w + bias.w};
+            if (a.res1) {
+              const float4 q = *reinterpret_cast<const float4*>(a.res1 + idx);
+              x[0] += q.x; x[1] += q.y; x[2] += q.z; x[3] += q.w;
+            }
+            if (a.res2) {
+              const float4 q = *reinterpret_cast<const float4*>(a.res2 + idx);
+              x[0] += q.x; x[1] += q.y; x[2] += q.z; x[3] += q.w;
+            }
+            if (a.out) {
+              float4 o = make_float4(x[0] * a.out_scale, x[1] * a.out_scale, x[2] * a.out_scale, x[3] * a.out_scale);
+              if (a.out_accum) {
+                const float4 p = *reinterpret_cast<const float4*>(a.out + idx);
+                o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
               }
-              if (a.res2) {
-                const float4 r0 = *reinterpret_cast<const float4*>(a.res2 + idx);
-                const float4 r1 = *reinterpret_cast<const float4*>(a.res2 + idx + 4);
-                x[0] += r0.x; x[1] += r0.y; x[2] += r0.z; x[3] += r0.w;
-                x[4] += r1.x; x[5] += r1.y; x[6] += r1.z; x[7] += r1.w;
+              *reinterpret_cast<float4*>(a.out + idx) = o;
+            }
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+              if (!a.act[s].dst) continue;
+              float y[4];
+              if (a.act[s].kind == ACT_SNAKE) {
+                y[0] = snake_f(x[0], al[s].x); y[1] = snake_f(x[1], al[s].y);
+                y[2] = snake_f(x[2], al[s].z); y[3] = snake_f(x[3], al[s].w);
+              } else {
+                y[0] = x[0]; y[1] = x[1]; y[2] = x[2]; y[3] = x[3];
               }
-              if (a.out) {
-                float o[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] = x[e] * a.out_scale;
-                if (a.out_accum) {
-                  const float4 p0 = *reinterpret_cast<const float4*>(a.out + idx);
-                  const float4 p1 = *reinterpret_cast<const float4*>(a.out + idx + 4);
-                  o[0] += p0.x; o[1] += p0.y; o[2] += p0.z; o[3] += p0.w;
-                  o[4] += p1.x; o[5] += p1.y; o[6] += p1.z; o[7] += p1.w;
-                }
-                *reinterpret_cast<float4*>(a.out + idx) = make_float4(o[0], o[1], o[2], o[3]);
-                *reinterpret_cast<float4*>(a.out + idx + 4) = make_float4(o[4], o[5], o[6], o[7]);
-              }
-#pragma unroll
-              for (int s = 0; s < 3; ++s) {
-                if (!a.act[s].dst) continue;
-                float y[8];
-                if (a.act[s].kind == ACT_SNAKE) {
-                  const float4 a0 = *reinterpret_cast<const float4*>(a.act[s].alpha + cc);
-                  const float4 a1 = *reinterpret_cast<const float4*>(a.act[s].alpha + cc + 4);
-                  const float al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) y[e] = snake_f(x[e], al[e]);
-                } else {
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) y[e] = x[e];
-                }
-                *reinterpret_cast<uint4*>(reinterpret_cast<ActT*>(a.act[s].dst) + idx) = Pack8<ActT>::pack(y);
-              }
+              *reinterpret_cast<uint2*>(reinterpret_cast<ActT*>(a.act[s].dst) + idx) = Pack4<ActT>::pack(y);
             }
           }
         }
@@ -332,7 +357,8 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
 
 template <int C, int MB, int A_ST, int W_ST>
 constexpr int smem_bytes() {
-  return A_ST * Cfg<C, MB>::A_BYTES + W_ST * Cfg<C, MB>::W_BYTES + (2 * A_ST + 2 * W_ST + 4) * 8 + 16;
+  return A_ST * Cfg<C, MB>::A_BYTES + W_ST * Cfg<C, MB>::W_BYTES + (2 * A_ST + 2 * W_ST + 4) * 8 + 16 +
+         4 * 32 * kStageLd * 4;
 }
 
 template <int C, int MB, int A_ST, int W_ST, typename ActT>
@@ -415,8 +441,8 @@ int launch_conv_tc(const ConvArgs& a_in, const ConvLayer& L, int act_elem, const
       return h ? tc::launch<128, 2, 2, 3, __half>(a, L.w_tc, idesc, grid, st)
                : tc::launch<128, 2, 2, 3, __nv_bfloat16>(a, L.w_tc, idesc, grid, st);
     case 256:
-      return h ? tc::launch<256, 1, 1, 4, __half>(a, L.w_tc, idesc, grid, st)
-               : tc::launch<256, 1, 1, 4, __nv_bfloat16>(a, L.w_tc, idesc, grid, st);
+      return h ? tc::launch<256, 1, 1, 3, __half>(a, L.w_tc, idesc, grid, st)
+               : tc::launch<256, 1, 1, 3, __nv_bfloat16>(a, L.w_tc, idesc, grid, st);
     default:
       VT_REQUIRE(false, "conv_tc: unsupported channel count %d", L.cin);
   }

@@ -318,3 +318,17 @@ def apply_minimal_edit(raw_path: Path, output_path: Path, *, trim_enabled: bool,
         "peak_after": peak_after,
         "gain": gain,
     }
+
+
+def pcm16_encode(audio: np.ndarray) -> np.ndarray:
+    """float32 -> PCM_16 codes on the GPU (``lrintf(x * 32767)``, the libsndfile default the
+    reference writes with: tts_backends/chatterbox_runner.py:152, tts_pipeline.py:409)."""
+    torch = _torch()
+    lib = _lib.load_library()
+    x = _as_f32(audio)
+    if x.size == 0:
+        return np.zeros(0, np.int16)
+    xd = torch.from_numpy(x).cuda()
+    q = torch.empty(x.size, dtype=torch.int16, device="cuda")
+    check(lib.vt_pcm16_encode(_ptr(xd), _ptr(q), x.size, _stream(torch)), "vt_pcm16_encode")
+    return q.cpu().numpy()
