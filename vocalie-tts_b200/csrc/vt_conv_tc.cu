@@ -157,10 +157,15 @@ struct Cfg {
   static constexpr int TMEM_COLS = 2 * ACC_COLS;    // 256 or 512: a power of two
 };
 
-template <int C, int MB, int A_ST, int W_ST, typename ActT>
-__global__ void __launch_bounds__(256, 1)
+// Epilogue modes (compile-time specialisations of the shared ConvArgs epilogue)
+constexpr int EM_RES1 = 1, EM_RES2 = 2, EM_OUT = 4, EM_ACCUM = 8, EM_ACT1 = 16, EM_ACT3 = 32;
+
+template <int C, int MB, int A_ST, int W_ST, int NEPI, int EM, typename ActT>
+__global__ void __launch_bounds__((NEPI + 4) * 32, 1)
 k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t idesc) {
   using K = Cfg<C, MB>;
+  constexpr int W_MMA = NEPI, W_WP = NEPI + 1, W_AP = NEPI + 2;   // warp roles after the epilogue warps
+  constexpr int NACT = (EM & EM_ACT3) ? 3 : ((EM & EM_ACT1) ? 1 : 0);
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sW = sA + A_ST * K::A_BYTES;
@@ -178,10 +183,10 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
   if (threadIdx.x == 0) {
     for (int i = 0; i < A_ST; ++i) { mbar_init(&a_full[i], 64); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < W_ST; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], NEPI * 32); }
     fence_barrier_init();
   }
-  if (warp == 4) {
+  if (warp == W_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)K::TMEM_COLS)
                  : "memory");
@@ -195,9 +200,9 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
   const int nchunks = a.k * (C / 64);
   const int n_tiles = a.n_tiles;
 
-  if (warp >= 6) {
+  if (warp >= W_AP) {
     // ---------------- activation producers: halo tile -> K-major panels
-    const int pt = threadIdx.x - 192;
+    const int pt = threadIdx.x - W_AP * 32;
     const ActT* in = reinterpret_cast<const ActT*>(a.in_act);
     const int r_need = 128 * MB + (a.k - 1) * a.dil;
     const int pieces = r_need * K::KC;
@@ -217,7 +222,7 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
       fence_proxy_async();
       mbar_arrive(&a_full[ab]);
     }
-  } else if (warp == 5) {
+  } else if (warp == W_WP) {
     // ---------------- weight producer: one bulk copy per (tap, 64-channel block)
     if (lane == 0) {
       uint32_t g = 0;
@@ -230,7 +235,7 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
         }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == W_MMA) {
     // ---------------- MMA issuer (one thread)
     if (lane == 0) {
       uint32_t g = 0;
@@ -267,13 +272,16 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
       }
     }
   } else {
-    // ---------------- epilogue warps 0-3: TMEM lanes 32*warp .. +31
+    // ---------------- epilogue warps 0..NEPI-1.  Warp w may touch TMEM lanes 32*(w%4)..+31; the NEPI/4
+    // warps of a lane quarter split the tile's 32-column blocks round-robin.
     // tcgen05.ld gives every thread 32 columns of ITS row; global memory wants a warp to touch whole
     // rows.  Each 32x32 fp32 block is transposed through a padded shared-memory stage so that every
     // global instruction covers 4 rows x 128 contiguous bytes (4 wavefronts instead of 32).
     float* stage = stage_all + warp * (32 * kStageLd);
+    const int quarter = warp & 3, eg = warp >> 2;
     const int sub = lane & 7;          // which float4 of a 32-column block
     const int rsub = lane >> 3;        // which of the 4 rows of an iteration
+    constexpr int NBLK = MB * (C / 32);
     int it = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
       const int as = it & 1;
@@ -282,63 +290,56 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
       mbar_wait(&acc_full[as], asph);
       tc_fence_after();
 #pragma unroll 1
-      for (int mb = 0; mb < MB; ++mb) {
-        const int row0 = mb * 128 + warp * 32;                       // tile-local row of this warp's lane 0
+      for (int blk = eg; blk < NBLK; blk += NEPI / 4) {
+        const int mb = blk / (C / 32), c0 = (blk - mb * (C / 32)) * 32;
+        const int row0 = mb * 128 + quarter * 32;                    // tile-local row of this warp's lane 0
         const long long base0 = (tile.out_row0 + tile.q0 + row0) * (long long)C;
-#pragma unroll 1
-        for (int c0 = 0; c0 < C; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * K::ACC_COLS + mb * C + c0), v);
-          tmem_ld_wait();
-          __syncwarp();
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * K::ACC_COLS + mb * C + c0), v);
+        tmem_ld_wait();
+        __syncwarp();
 #pragma unroll
-          for (int g = 0; g < 8; ++g)
-            *reinterpret_cast<float4*>(stage + lane * kStageLd + g * 4) =
-                make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]),
-                            __uint_as_float(v[4 * g + 3]));
-          __syncwarp();
-          const int cc = c0 + sub * 4;
-          const float4 bias = *reinterpret_cast<const float4*>(a.bias + cc);
-          float4 al[3];
+        for (int g = 0; g < 8; ++g)
+          *reinterpret_cast<float4*>(stage + lane * kStageLd + g * 4) =
+              make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]),
+                          __uint_as_float(v[4 * g + 3]));
+        __syncwarp();
+        const int cc = c0 + sub * 4;
+        const float4 bias = *reinterpret_cast<const float4*>(a.bias + cc);
+        float4 al[NACT > 0 ? NACT : 1];
 #pragma unroll
-          for (int s = 0; s < 3; ++s)
-            al[s] = (a.act[s].dst && a.act[s].kind == ACT_SNAKE) ? *reinterpret_cast<const float4*>(a.act[s].alpha + cc)
-                                                                  : make_float4(1.f, 1.f, 1.f, 1.f);
+        for (int s = 0; s < NACT; ++s) al[s] = *reinterpret_cast<const float4*>(a.act[s].alpha + cc);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = i * 4 + rsub;
-            if (row0 + r >= tile.n) continue;
-            const long long idx = base0 + (long long)r * C + cc;
-            const float4 acc = *reinterpret_cast<const float4*>(stage + r * kStageLd + sub * 4);
-            float x[4] = {acc.x + bias.x, acc.y + bias.y, acc.z + bias.z, acc.w + bias.w};
-            if (a.res1) {
-              const float4 q = *reinterpret_cast<const float4*>(a.res1 + idx);
-              x[0] += q.x; x[1] += q.y; x[2] += q.z; x[3] += q.w;
-            }
-            if (a.res2) {
-              const float4 q = *reinterpret_cast<const float4*>(a.res2 + idx);
-              x[0] += q.x; x[1] += q.y; x[2] += q.z; x[3] += q.w;
-            }
-            if (a.out) {
-              float4 o = make_float4(x[0] * a.out_scale, x[1] * a.out_scale, x[2] * a.out_scale, x[3] * a.out_scale);
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 4 + rsub;
+          if (row0 + r >= tile.n) continue;
+          const long long idx = base0 + (long long)r * C + cc;
+          const float4 acc = *reinterpret_cast<const float4*>(stage + r * kStageLd + sub * 4);
+          float x[4] = {acc.x + bias.x, acc.y + bias.y, acc.z + bias.z, acc.w + bias.w};
+          if constexpr ((EM & EM_RES1) != 0) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(a.res1 + idx));
+            x[0] += q.x; x[1] += q.y; x[2] += q.z; x[3] += q.w;
+          }
+          if constexpr ((EM & EM_RES2) != 0) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(a.res2 + idx));
+            x[0] += q.x; x[1] += q.y; x[2] += q.z; x[3] += q.w;
+          }
+          if constexpr ((EM & EM_OUT) != 0) {
+            float4 o = make_float4(x[0] * a.out_scale, x[1] * a.out_scale, x[2] * a.out_scale, x[3] * a.out_scale);
+            if constexpr ((EM & EM_ACCUM) != 0) {
               if (a.out_accum) {
                 const float4 p = *reinterpret_cast<const float4*>(a.out + idx);
                 o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
               }
-              *reinterpret_cast<float4*>(a.out + idx) = o;
             }
+            *reinterpret_cast<float4*>(a.out + idx) = o;
+          }
 #pragma unroll
-            for (int s = 0; s < 3; ++s) {
-              if (!a.act[s].dst) continue;
-              float y[4];
-              if (a.act[s].kind == ACT_SNAKE) {
-                y[0] = snake_f(x[0], al[s].x); y[1] = snake_f(x[1], al[s].y);
-                y[2] = snake_f(x[2], al[s].z); y[3] = snake_f(x[3], al[s].w);
-              } else {
-                y[0] = x[0]; y[1] = x[1]; y[2] = x[2]; y[3] = x[3];
-              }
-              *reinterpret_cast<uint2*>(reinterpret_cast<ActT*>(a.act[s].dst) + idx) = Pack4<ActT>::pack(y);
-            }
+          for (int s = 0; s < NACT; ++s) {
+            float y[4];
+            y[0] = snake_f(x[0], al[s].x); y[1] = snake_f(x[1], al[s].y);
+            y[2] = snake_f(x[2], al[s].z); y[3] = snake_f(x[3], al[s].w);
+            *reinterpret_cast<uint2*>(reinterpret_cast<ActT*>(a.act[s].dst) + idx) = Pack4<ActT>::pack(y);
           }
         }
       }
@@ -349,28 +350,55 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == W_MMA) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)K::TMEM_COLS) : "memory");
   }
 }
 
-template <int C, int MB, int A_ST, int W_ST>
+template <int C, int MB, int A_ST, int W_ST, int NEPI>
 constexpr int smem_bytes() {
   return A_ST * Cfg<C, MB>::A_BYTES + W_ST * Cfg<C, MB>::W_BYTES + (2 * A_ST + 2 * W_ST + 4) * 8 + 16 +
-         4 * 32 * kStageLd * 4;
+         NEPI * 32 * kStageLd * 4;
 }
 
-template <int C, int MB, int A_ST, int W_ST, typename ActT>
-int launch(const ConvArgs& a, const void* wtc, uint32_t idesc, int grid, cudaStream_t st) {
-  constexpr int smem = smem_bytes<C, MB, A_ST, W_ST>();
+template <int C, int MB, int A_ST, int W_ST, int NEPI, int EM, typename ActT>
+int launch_em(const ConvArgs& a, const void* wtc, uint32_t idesc, int grid, cudaStream_t st) {
+  constexpr int smem = smem_bytes<C, MB, A_ST, W_ST, NEPI>();
+  static_assert(smem <= 232448, "shared memory budget exceeded");
   static bool configured = false;
   if (!configured) {
-    VT_CUDA_OK(cudaFuncSetAttribute(k_conv_tc<C, MB, A_ST, W_ST, ActT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    VT_CUDA_OK(cudaFuncSetAttribute(k_conv_tc<C, MB, A_ST, W_ST, NEPI, EM, ActT>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  k_conv_tc<C, MB, A_ST, W_ST, ActT><<<grid, 256, smem, st>>>(a, reinterpret_cast<const uint8_t*>(wtc), idesc);
+  k_conv_tc<C, MB, A_ST, W_ST, NEPI, EM, ActT><<<grid, (NEPI + 4) * 32, smem, st>>>(
+      a, reinterpret_cast<const uint8_t*>(wtc), idesc);
   VT_LAUNCHED();
+  return VT_OK;
+}
+
+// Map the runtime epilogue description onto one of the compiled specialisations.
+template <int C, int MB, int A_ST, int W_ST, int NEPI, typename ActT>
+int launch(const ConvArgs& a, const void* wtc, uint32_t idesc, int grid, cudaStream_t st) {
+  int nact = 0;
+  for (int s = 0; s < 3; ++s) {
+    if (!a.act[s].dst) break;
+    VT_REQUIRE(a.act[s].kind == ACT_SNAKE && a.act[s].alpha, "conv_tc: only Snake activation copies are supported");
+    ++nact;
+  }
+  for (int s = nact; s < 3; ++s) VT_REQUIRE(!a.act[s].dst, "conv_tc: activation outputs must be packed from slot 0");
+  const bool r1 = a.res1 != nullptr, r2 = a.res2 != nullptr, out = a.out != nullptr;
+  if (!r1 && !r2 && !out && nact == 1)
+    return launch_em<C, MB, A_ST, W_ST, NEPI, EM_ACT1, ActT>(a, wtc, idesc, grid, st);
+  if (r1 && !r2 && out && !a.out_accum && nact == 1)
+    return launch_em<C, MB, A_ST, W_ST, NEPI, EM_RES1 | EM_OUT | EM_ACT1, ActT>(a, wtc, idesc, grid, st);
+  if (r1 && r2 && out && !a.out_accum && nact == 3)
+    return launch_em<C, MB, A_ST, W_ST, NEPI, EM_RES1 | EM_RES2 | EM_OUT | EM_ACT3, ActT>(a, wtc, idesc, grid, st);
+  if (r1 && !r2 && out && nact == 0)
+    return launch_em<C, MB, A_ST, W_ST, NEPI, EM_RES1 | EM_OUT | EM_ACCUM, ActT>(a, wtc, idesc, grid, st);
+  VT_REQUIRE(false, "conv_tc: no compiled epilogue for res1=%d res2=%d out=%d accum=%d nact=%d", (int)r1, (int)r2, (int)out,
+             a.out_accum, nact);
   return VT_OK;
 }
 
@@ -435,14 +463,14 @@ int launch_conv_tc(const ConvArgs& a_in, const ConvLayer& L, int act_elem, const
   (void)tile_rows;
   switch (L.cin) {
     case 64:
-      return h ? tc::launch<64, 2, 2, 4, __half>(a, L.w_tc, idesc, grid, st)
-               : tc::launch<64, 2, 2, 4, __nv_bfloat16>(a, L.w_tc, idesc, grid, st);
+      return h ? tc::launch<64, 2, 2, 4, 16, __half>(a, L.w_tc, idesc, grid, st)
+               : tc::launch<64, 2, 2, 4, 16, __nv_bfloat16>(a, L.w_tc, idesc, grid, st);
     case 128:
-      return h ? tc::launch<128, 2, 2, 3, __half>(a, L.w_tc, idesc, grid, st)
-               : tc::launch<128, 2, 2, 3, __nv_bfloat16>(a, L.w_tc, idesc, grid, st);
+      return h ? tc::launch<128, 2, 1, 4, 16, __half>(a, L.w_tc, idesc, grid, st)
+               : tc::launch<128, 2, 1, 4, 16, __nv_bfloat16>(a, L.w_tc, idesc, grid, st);
     case 256:
-      return h ? tc::launch<256, 1, 1, 3, __half>(a, L.w_tc, idesc, grid, st)
-               : tc::launch<256, 1, 1, 3, __nv_bfloat16>(a, L.w_tc, idesc, grid, st);
+      return h ? tc::launch<256, 1, 1, 3, 8, __half>(a, L.w_tc, idesc, grid, st)
+               : tc::launch<256, 1, 1, 3, 8, __nv_bfloat16>(a, L.w_tc, idesc, grid, st);
     default:
       VT_REQUIRE(false, "conv_tc: unsupported channel count %d", L.cin);
   }
