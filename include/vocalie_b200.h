@@ -35,7 +35,7 @@ extern "C" {
 #define VT_ERR_UNSUPPORTED -3   /* not an sm_100 device / unsupported shape */
 #define VT_ERR_NOMEM       -4
 
-#define VT_ABI_VERSION 1
+#define VT_ABI_VERSION 2
 
 /* ---- library ------------------------------------------------------------------------- */
 int         vt_abi_version(void);
@@ -89,6 +89,11 @@ typedef struct vt_post_params {
   int32_t concat;             /* 1: outputs packed back to back (+gaps) in segment order;
                                  0: segment i is written at out + seg_off[i] (same layout as input) */
   int32_t out_pcm16;          /* 1: out is int16 PCM (lrintf(x*32767)), 0: float32 */
+  int32_t stitch_head;        /* stitch only: 1 = segment 0 is the first chunk of the whole job (no fade-in) */
+  int32_t stitch_tail;        /* stitch only: 1 = the last segment is the last chunk of the whole job (no
+                                 fade-out, no trailing gap).  A rank holding a middle shard of a sharded job
+                                 passes 0/0: every segment is faded on both sides and followed by a gap, so
+                                 the concatenation of the ranks' outputs equals the single-GPU result. */
 } vt_post_params;
 
 /* Per-segment results, 8 doubles per segment (device array `results`, may be NULL):

@@ -31,6 +31,7 @@ class PostParams(C.Structure):
         ("fade_in_frames", C.c_int32), ("fade_out_frames", C.c_int32), ("stitch", C.c_int32),
         ("gap_frames", C.c_int32), ("normalize", C.c_int32), ("clip", C.c_int32),
         ("target_peak", C.c_double), ("concat", C.c_int32), ("out_pcm16", C.c_int32),
+        ("stitch_head", C.c_int32), ("stitch_tail", C.c_int32),
     ]
 
 
@@ -87,7 +88,7 @@ def load_library():
                 raise BackendUnavailableError(f"{LIB_PATH} does not export {name}") from exc
             fn.restype = res
             fn.argtypes = args
-        if lib.vt_abi_version() != 1:
+        if lib.vt_abi_version() != 2:
             raise BackendUnavailableError("ABI version mismatch between Python shim and libvocalie_b200.so")
         _lib = lib
         return lib

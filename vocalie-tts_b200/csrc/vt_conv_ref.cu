@@ -164,8 +164,8 @@ k_conv_ref(const ConvArgs a) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) t[e] += r2[e];
       }
+      float o[4] = {t[0], t[1], t[2], t[3]};
       if (a.out) {
-        float o[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) o[e] = t[e] * a.out_scale;
         if (a.out_accum) {
@@ -181,9 +181,10 @@ k_conv_ref(const ConvArgs a) {
         if (!a.act[s].dst) continue;
         float al[4] = {1.f, 1.f, 1.f, 1.f};
         if (a.act[s].alpha) Elem<float>::ld4(a.act[s].alpha + co, al);
+        const float* srcv = (s == 0 && a.act_from_out) ? o : t;
         float y[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) y[e] = apply_act(t[e], a.act[s].kind, al[e], a.act[s].slope);
+        for (int e = 0; e < 4; ++e) y[e] = apply_act(srcv[e], a.act[s].kind, al[e], a.act[s].slope);
         Elem<ActT>::st4(reinterpret_cast<ActT*>(a.act[s].dst) + idx, y);
       }
     }

@@ -147,25 +147,33 @@ __device__ __forceinline__ float snake_f(float v, float alpha) {
   return fmaf(__fdividef(1.0f, alpha + 1e-9f), s * s, v);
 }
 
-template <int C, int MB>
+constexpr int pow2_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
+
+// CIN input channels (GEMM K per tap), NT output columns per CTA tile (GEMM N), MB 128-row M blocks
+// per tile, HALO = largest (k-1)*dil the instance accepts.
+template <int CIN, int NT, int MB, int HALO>
 struct Cfg {
-  static constexpr int RA = 128 * MB + 51;          // rows of the activation panels (odd; halo <= 50)
-  static constexpr int KC = C / 8;                  // 16-byte K chunks per row
+  static constexpr int RA = 128 * MB + HALO + 1;    // rows of the activation panels (odd)
+  static constexpr int KC = CIN / 8;                // 16-byte K chunks per row
   static constexpr int A_BYTES = KC * RA * 16;
-  static constexpr int W_BYTES = C * 128;           // one (tap, 64-channel block) weight chunk
-  static constexpr int ACC_COLS = MB * C;
-  static constexpr int TMEM_COLS = 2 * ACC_COLS;    // 256 or 512: a power of two
+  static constexpr int W_BYTES = NT * 128;          // one (n-tile, tap, 64-channel block) weight chunk
+  static constexpr int ACC_COLS = MB * NT;
+  static constexpr int TMEM_COLS = pow2_cols(2 * ACC_COLS);
+  static_assert(HALO % 2 == 0 && CIN % 64 == 0 && NT % 32 == 0 && 2 * ACC_COLS <= 512, "bad tile configuration");
 };
 
 // Epilogue modes (compile-time specialisations of the shared ConvArgs epilogue)
-constexpr int EM_RES1 = 1, EM_RES2 = 2, EM_OUT = 4, EM_ACCUM = 8, EM_ACT1 = 16, EM_ACT3 = 32;
+//   v = acc + bias (+res1) (+res2); o = v*scale (+ out if ACCUM and a.out_accum); out = o
+//   ACT1/ACT3: act[s] = Snake(v);  OACT: act[0] = leaky_relu(o) (operand copy for the next stage)
+constexpr int EM_RES1 = 1, EM_RES2 = 2, EM_OUT = 4, EM_ACCUM = 8, EM_ACT1 = 16, EM_ACT3 = 32, EM_OACT = 64;
 
-template <int C, int MB, int A_ST, int W_ST, int NEPI, int EM, typename ActT>
+template <int CIN, int NT, int MB, int A_ST, int W_ST, int NEPI, int HALO, int EM, typename ActT>
 __global__ void __launch_bounds__((NEPI + 4) * 32, 1)
 k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t idesc) {
-  using K = Cfg<C, MB>;
+  using K = Cfg<CIN, NT, MB, HALO>;
   constexpr int W_MMA = NEPI, W_WP = NEPI + 1, W_AP = NEPI + 2;   // warp roles after the epilogue warps
   constexpr int NACT = (EM & EM_ACT3) ? 3 : ((EM & EM_ACT1) ? 1 : 0);
+  constexpr int CB = CIN / 64;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sW = sA + A_ST * K::A_BYTES;
@@ -197,8 +205,9 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int nchunks = a.k * (C / 64);
-  const int n_tiles = a.n_tiles;
+  const int nchunks = a.k * CB;                 // weight chunks per tile
+  const int n_nt = a.cout / NT;                 // column tiles
+  const int n_tiles = a.n_tiles * n_nt;         // (row tile, column tile) pairs, column tile fastest
 
   if (warp >= W_AP) {
     // ---------------- activation producers: halo tile -> K-major panels
@@ -211,27 +220,29 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
       const int ab = it % A_ST;
       const uint32_t ph = (uint32_t)(it / A_ST) & 1u;
       mbar_wait(&a_empty[ab], ph ^ 1u);
-      const ConvTile tile = a.tiles[t];
-      const ActT* src = in + (tile.in_row0 + tile.q0 - a.pad) * (long long)C;
+      const ConvTile tile = a.tiles[t / n_nt];
+      const ActT* src = in + (tile.in_row0 + tile.q0 - a.pad) * (long long)CIN;
       const uint32_t dst = smem_u32(sA + ab * K::A_BYTES);
       for (int p = pt; p < pieces; p += 64) {
         const int r = p / K::KC, c = p - r * K::KC;
-        cp_async16(dst + (uint32_t)(c * K::RA + r) * 16u, src + (long long)r * C + c * 8);
+        cp_async16(dst + (uint32_t)(c * K::RA + r) * 16u, src + (long long)r * CIN + c * 8);
       }
       cp_async_wait_all();
       fence_proxy_async();
       mbar_arrive(&a_full[ab]);
     }
   } else if (warp == W_WP) {
-    // ---------------- weight producer: one bulk copy per (tap, 64-channel block)
+    // ---------------- weight producer: one bulk copy per (tap, 64-channel block) of this tile's column tile
     if (lane == 0) {
       uint32_t g = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int nt = t % n_nt;
+        const uint8_t* wsrc = wtc + (size_t)nt * nchunks * K::W_BYTES;
         for (int c = 0; c < nchunks; ++c, ++g) {
           const uint32_t ws = g % W_ST, ph = (g / W_ST) & 1u;
           mbar_wait(&w_empty[ws], ph ^ 1u);
           mbar_arrive_expect_tx(&w_full[ws], K::W_BYTES);
-          bulk_g2s(sW + ws * K::W_BYTES, wtc + (size_t)c * K::W_BYTES, K::W_BYTES, &w_full[ws]);
+          bulk_g2s(sW + ws * K::W_BYTES, wsrc + (size_t)c * K::W_BYTES, K::W_BYTES, &w_full[ws]);
         }
       }
     }
@@ -250,7 +261,7 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
         mbar_wait(&a_full[ab], aph);
         tc_fence_after();
         for (int c = 0; c < nchunks; ++c, ++g) {
-          const int j = c / (C / 64), cb = c - j * (C / 64);
+          const int j = c / CB, cb = c - j * CB;
           const uint32_t ws = g % W_ST, wph = (g / W_ST) & 1u;
           mbar_wait(&w_full[ws], wph);
           tc_fence_after();
@@ -260,9 +271,9 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
             for (int ks = 0; ks < 4; ++ks) {
               const uint32_t a_addr = sA_addr + ab * K::A_BYTES +
                                       (uint32_t)((cb * 8 + ks * 2) * K::RA + mb * 128 + j * a.dil) * 16u;
-              const uint32_t b_addr = sW_addr + ws * K::W_BYTES + (uint32_t)(ks * 2 * C) * 16u;
-              umma_f16(tmem_base + (uint32_t)(as * K::ACC_COLS + mb * C), make_desc(a_addr, K::RA * 16, 128),
-                       make_desc(b_addr, C * 16, 128), idesc, (c > 0 || ks > 0) ? 1u : 0u);
+              const uint32_t b_addr = sW_addr + ws * K::W_BYTES + (uint32_t)(ks * 2 * NT) * 16u;
+              umma_f16(tmem_base + (uint32_t)(as * K::ACC_COLS + mb * NT), make_desc(a_addr, K::RA * 16, 128),
+                       make_desc(b_addr, NT * 16, 128), idesc, (c > 0 || ks > 0) ? 1u : 0u);
             }
           }
           umma_commit(&w_empty[ws]);
@@ -281,21 +292,22 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
     const int quarter = warp & 3, eg = warp >> 2;
     const int sub = lane & 7;          // which float4 of a 32-column block
     const int rsub = lane >> 3;        // which of the 4 rows of an iteration
-    constexpr int NBLK = MB * (C / 32);
+    constexpr int NBLK = MB * (NT / 32);
+    const int ld = a.phase_c;
     int it = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t asph = (uint32_t)(it >> 1) & 1u;
-      const ConvTile tile = a.tiles[t];
+      const int rt = t / n_nt, nt = t - rt * n_nt;
+      const ConvTile tile = a.tiles[rt];
       mbar_wait(&acc_full[as], asph);
       tc_fence_after();
 #pragma unroll 1
       for (int blk = eg; blk < NBLK; blk += NEPI / 4) {
-        const int mb = blk / (C / 32), c0 = (blk - mb * (C / 32)) * 32;
+        const int mb = blk / (NT / 32), c0 = (blk - mb * (NT / 32)) * 32;
         const int row0 = mb * 128 + quarter * 32;                    // tile-local row of this warp's lane 0
-        const long long base0 = (tile.out_row0 + tile.q0 + row0) * (long long)C;
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * K::ACC_COLS + mb * C + c0), v);
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * K::ACC_COLS + mb * NT + c0), v);
         tmem_ld_wait();
         __syncwarp();
 #pragma unroll
@@ -304,16 +316,18 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
               make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]),
                           __uint_as_float(v[4 * g + 3]));
         __syncwarp();
-        const int cc = c0 + sub * 4;
-        const float4 bias = *reinterpret_cast<const float4*>(a.bias + cc);
+        const int cg = nt * NT + c0 + sub * 4;             // GEMM column of this lane's float4
+        const int phase = cg / ld, co = cg - phase * ld;   // transposed convs: column -> (output phase, channel)
+        const float4 bias = *reinterpret_cast<const float4*>(a.bias + cg);
         float4 al[NACT > 0 ? NACT : 1];
 #pragma unroll
-        for (int s = 0; s < NACT; ++s) al[s] = *reinterpret_cast<const float4*>(a.act[s].alpha + cc);
+        for (int s = 0; s < NACT; ++s) al[s] = *reinterpret_cast<const float4*>(a.act[s].alpha + co);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int r = i * 4 + rsub;
           if (row0 + r >= tile.n) continue;
-          const long long idx = base0 + (long long)r * C + cc;
+          const long long step = (long long)(tile.q0 + row0 + r) * a.out_mul + phase + a.out_shift;
+          const long long idx = (tile.out_row0 + step) * ld + co;
           const float4 acc = *reinterpret_cast<const float4*>(stage + r * kStageLd + sub * 4);
           float x[4] = {acc.x + bias.x, acc.y + bias.y, acc.z + bias.z, acc.w + bias.w};
           if constexpr ((EM & EM_RES1) != 0) {
@@ -333,6 +347,14 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
               }
             }
             *reinterpret_cast<float4*>(a.out + idx) = o;
+            if (a.dup_row2 && step == 2)                      // reflection pad (1, 0): padded[0] = unpadded[1]
+              *reinterpret_cast<float4*>(a.out + tile.out_row0 * ld + co) = o;
+            if constexpr ((EM & EM_OACT) != 0) {
+              const float sl = a.act[0].slope;
+              float y[4] = {o.x > 0.f ? o.x : o.x * sl, o.y > 0.f ? o.y : o.y * sl, o.z > 0.f ? o.z : o.z * sl,
+                            o.w > 0.f ? o.w : o.w * sl};
+              *reinterpret_cast<uint2*>(reinterpret_cast<ActT*>(a.act[0].dst) + idx) = Pack4<ActT>::pack(y);
+            }
           }
 #pragma unroll
           for (int s = 0; s < NACT; ++s) {
@@ -356,83 +378,134 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
   }
 }
 
-template <int C, int MB, int A_ST, int W_ST, int NEPI>
+template <int CIN, int NT, int MB, int A_ST, int W_ST, int NEPI, int HALO>
 constexpr int smem_bytes() {
-  return A_ST * Cfg<C, MB>::A_BYTES + W_ST * Cfg<C, MB>::W_BYTES + (2 * A_ST + 2 * W_ST + 4) * 8 + 16 +
-         NEPI * 32 * kStageLd * 4;
+  return A_ST * Cfg<CIN, NT, MB, HALO>::A_BYTES + W_ST * Cfg<CIN, NT, MB, HALO>::W_BYTES +
+         (2 * A_ST + 2 * W_ST + 4) * 8 + 16 + NEPI * 32 * kStageLd * 4;
 }
 
-template <int C, int MB, int A_ST, int W_ST, int NEPI, int EM, typename ActT>
+template <int CIN, int NT, int MB, int A_ST, int W_ST, int NEPI, int HALO, int EM, typename ActT>
 int launch_em(const ConvArgs& a, const void* wtc, uint32_t idesc, int grid, cudaStream_t st) {
-  constexpr int smem = smem_bytes<C, MB, A_ST, W_ST, NEPI>();
+  constexpr int smem = smem_bytes<CIN, NT, MB, A_ST, W_ST, NEPI, HALO>();
   static_assert(smem <= 232448, "shared memory budget exceeded");
+  static_assert(NEPI % 4 == 0 && (MB * (NT / 32)) % (NEPI / 4) == 0, "epilogue warps must divide the column blocks");
   static bool configured = false;
   if (!configured) {
-    VT_CUDA_OK(cudaFuncSetAttribute(k_conv_tc<C, MB, A_ST, W_ST, NEPI, EM, ActT>,
+    VT_CUDA_OK(cudaFuncSetAttribute(k_conv_tc<CIN, NT, MB, A_ST, W_ST, NEPI, HALO, EM, ActT>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  k_conv_tc<C, MB, A_ST, W_ST, NEPI, EM, ActT><<<grid, (NEPI + 4) * 32, smem, st>>>(
+  k_conv_tc<CIN, NT, MB, A_ST, W_ST, NEPI, HALO, EM, ActT><<<grid, (NEPI + 4) * 32, smem, st>>>(
       a, reinterpret_cast<const uint8_t*>(wtc), idesc);
   VT_LAUNCHED();
   return VT_OK;
 }
 
-// Map the runtime epilogue description onto one of the compiled specialisations.
+// ResBlock convolutions: map the runtime epilogue description onto a compiled specialisation.
 template <int C, int MB, int A_ST, int W_ST, int NEPI, typename ActT>
-int launch(const ConvArgs& a, const void* wtc, uint32_t idesc, int grid, cudaStream_t st) {
-  int nact = 0;
-  for (int s = 0; s < 3; ++s) {
-    if (!a.act[s].dst) break;
-    VT_REQUIRE(a.act[s].kind == ACT_SNAKE && a.act[s].alpha, "conv_tc: only Snake activation copies are supported");
-    ++nact;
-  }
-  for (int s = nact; s < 3; ++s) VT_REQUIRE(!a.act[s].dst, "conv_tc: activation outputs must be packed from slot 0");
+int launch_resblock(const ConvArgs& a, const void* wtc, uint32_t idesc, int grid, cudaStream_t st) {
+  int nsnake = 0;
+  while (nsnake < 3 && a.act[nsnake].dst && a.act[nsnake].kind == ACT_SNAKE) ++nsnake;
+  const bool oact = nsnake == 0 && a.act[0].dst && a.act[0].kind == ACT_LRELU && a.act_from_out;
+  for (int s = nsnake + (oact ? 1 : 0); s < 3; ++s)
+    VT_REQUIRE(!a.act[s].dst, "conv_tc: unsupported activation-copy combination");
   const bool r1 = a.res1 != nullptr, r2 = a.res2 != nullptr, out = a.out != nullptr;
-  if (!r1 && !r2 && !out && nact == 1)
-    return launch_em<C, MB, A_ST, W_ST, NEPI, EM_ACT1, ActT>(a, wtc, idesc, grid, st);
-  if (r1 && !r2 && out && !a.out_accum && nact == 1)
-    return launch_em<C, MB, A_ST, W_ST, NEPI, EM_RES1 | EM_OUT | EM_ACT1, ActT>(a, wtc, idesc, grid, st);
-  if (r1 && r2 && out && !a.out_accum && nact == 3)
-    return launch_em<C, MB, A_ST, W_ST, NEPI, EM_RES1 | EM_RES2 | EM_OUT | EM_ACT3, ActT>(a, wtc, idesc, grid, st);
-  if (r1 && !r2 && out && nact == 0)
-    return launch_em<C, MB, A_ST, W_ST, NEPI, EM_RES1 | EM_OUT | EM_ACCUM, ActT>(a, wtc, idesc, grid, st);
-  VT_REQUIRE(false, "conv_tc: no compiled epilogue for res1=%d res2=%d out=%d accum=%d nact=%d", (int)r1, (int)r2, (int)out,
-             a.out_accum, nact);
+  if (!r1 && !r2 && !out && nsnake == 1)
+    return launch_em<C, C, MB, A_ST, W_ST, NEPI, 50, EM_ACT1, ActT>(a, wtc, idesc, grid, st);
+  if (r1 && !r2 && out && !a.out_accum && nsnake == 1)
+    return launch_em<C, C, MB, A_ST, W_ST, NEPI, 50, EM_RES1 | EM_OUT | EM_ACT1, ActT>(a, wtc, idesc, grid, st);
+  if (r1 && r2 && out && !a.out_accum && nsnake == 3)
+    return launch_em<C, C, MB, A_ST, W_ST, NEPI, 50, EM_RES1 | EM_RES2 | EM_OUT | EM_ACT3, ActT>(a, wtc, idesc, grid, st);
+  if (r1 && !r2 && out && nsnake == 0 && !oact)
+    return launch_em<C, C, MB, A_ST, W_ST, NEPI, 50, EM_RES1 | EM_OUT | EM_ACCUM, ActT>(a, wtc, idesc, grid, st);
+  if (r1 && !r2 && out && nsnake == 0 && oact)
+    return launch_em<C, C, MB, A_ST, W_ST, NEPI, 50, EM_RES1 | EM_OUT | EM_ACCUM | EM_OACT, ActT>(a, wtc, idesc, grid, st);
+  VT_REQUIRE(false, "conv_tc: no compiled epilogue for res1=%d res2=%d out=%d accum=%d snake=%d", (int)r1, (int)r2, (int)out,
+             a.out_accum, nsnake);
   return VT_OK;
+}
+
+// Plain layers (transposed convs as 3-tap convs, conv_pre, conv_post): fp32 output, optional leaky-ReLU copy.
+template <int CIN, int NT, int MB, int A_ST, int W_ST, int NEPI, int HALO, typename ActT>
+int launch_plain(const ConvArgs& a, const void* wtc, uint32_t idesc, int grid, cudaStream_t st) {
+  VT_REQUIRE(a.out && !a.res1 && !a.res2 && !a.out_accum && !a.act[1].dst && !a.act[2].dst,
+             "conv_tc: plain layers write one fp32 output");
+  if (a.act[0].dst) {
+    VT_REQUIRE(a.act[0].kind == ACT_LRELU && a.act_from_out, "conv_tc: plain layers support a leaky-ReLU output copy only");
+    return launch_em<CIN, NT, MB, A_ST, W_ST, NEPI, HALO, EM_OUT | EM_OACT, ActT>(a, wtc, idesc, grid, st);
+  }
+  return launch_em<CIN, NT, MB, A_ST, W_ST, NEPI, HALO, EM_OUT, ActT>(a, wtc, idesc, grid, st);
 }
 
 }  // namespace tc
 
-bool conv_tc_supported(const ConvLayer& L) {
-  return L.cin == L.cout && (L.cin == 64 || L.cin == 128 || L.cin == 256) && L.stride == 1 && L.out_mul == 1 &&
-         L.k >= 1 && (L.k - 1) * L.dil <= 50 && L.pad <= kGap;
+// Which compiled instance a layer maps to (0 = none): 1..3 ResBlock C=64/128/256, 4..6 the three
+// transposed convs, 7 conv_post, 8 conv_pre.
+static int tc_instance(const ConvLayer& L) {
+  if (L.stride != 1 || L.pad > kGap) return 0;
+  if (L.out_mul == 1 && L.cin == L.cout && (L.k - 1) * L.dil <= 50) {
+    if (L.cin == 64 && L.k > 1) return 1;
+    if (L.cin == 128) return 2;
+    if (L.cin == 256) return 3;
+  }
+  if (L.out_mul > 1 && L.k == 3 && L.dil == 1) {
+    if (L.cin == 512 && L.phase_c == 256) return 4;
+    if (L.cin == 256 && L.phase_c == 128) return 5;
+    if (L.cin == 128 && L.phase_c == 64) return 6;
+  }
+  if (L.out_mul == 1 && L.cin == 64 && L.cout == 32 && (L.k - 1) * L.dil <= 6) return 7;
+  if (L.out_mul == 1 && L.cin == 128 && L.cout == 512 && (L.k - 1) * L.dil <= 6) return 8;
+  return 0;
 }
 
-int conv_tc_tile_rows(const ConvLayer& L) { return L.cin == 256 ? 128 : 256; }
+static int tc_nt(int inst) {
+  switch (inst) {
+    case 1: return 64;
+    case 2: return 128;
+    case 3: return 256;
+    case 4: return 128;
+    case 5: return 128;
+    case 6: return 64;
+    case 7: return 32;
+    case 8: return 128;
+  }
+  return 0;
+}
 
-// [k][cin][cout] fp32 -> per (tap j, 64-channel block cb) the shared-memory image [8][C][8] in the operand type
+bool conv_tc_supported(const ConvLayer& L) { return tc_instance(L) != 0; }
+
+int conv_tc_tile_rows(const ConvLayer& L) {
+  const int inst = tc_instance(L);
+  return (inst == 1 || inst == 2 || inst == 7) ? 256 : 128;
+}
+
+// [k][cin][cout] fp32 -> per (column tile nt, tap j, 64-channel block cb) the shared-memory image
+// [8][NT][8] in the operand type
 int pack_conv_tc(ConvLayer& L, const std::vector<float>& w, int act_elem, std::vector<void*>& allocs) {
-  const int C = L.cin, k = L.k;
-  const size_t n = (size_t)k * C * C;
+  const int inst = tc_instance(L);
+  VT_REQUIRE(inst != 0, "conv_tc: layer %s has no tensor-core instance", L.name.c_str());
+  const int CIN = L.cin, N = L.cout, k = L.k, NT = tc_nt(inst);
+  VT_REQUIRE(N % NT == 0 && CIN % 64 == 0, "conv_tc: layer %s does not tile (cin=%d cout=%d)", L.name.c_str(), CIN, N);
+  const size_t n = (size_t)k * CIN * N;
   std::vector<uint16_t> img(n);
   size_t o = 0;
-  for (int j = 0; j < k; ++j)
-    for (int cb = 0; cb < C / 64; ++cb)
-      for (int k8 = 0; k8 < 8; ++k8)
-        for (int co = 0; co < C; ++co)
-          for (int e = 0; e < 8; ++e) {
-            const float v = w[((size_t)j * C + cb * 64 + k8 * 8 + e) * C + co];
-            uint16_t bits;
-            if (act_elem == ELEM_F16) {
-              const __half hv = __float2half_rn(v);
-              std::memcpy(&bits, &hv, 2);
-            } else {
-              const __nv_bfloat16 bv = __float2bfloat16_rn(v);
-              std::memcpy(&bits, &bv, 2);
+  for (int nt = 0; nt < N / NT; ++nt)
+    for (int j = 0; j < k; ++j)
+      for (int cb = 0; cb < CIN / 64; ++cb)
+        for (int k8 = 0; k8 < 8; ++k8)
+          for (int co = 0; co < NT; ++co)
+            for (int e = 0; e < 8; ++e) {
+              const float v = w[((size_t)j * CIN + cb * 64 + k8 * 8 + e) * N + nt * NT + co];
+              uint16_t bits;
+              if (act_elem == ELEM_F16) {
+                const __half hv = __float2half_rn(v);
+                std::memcpy(&bits, &hv, 2);
+              } else {
+                const __nv_bfloat16 bv = __float2bfloat16_rn(v);
+                std::memcpy(&bits, &bv, 2);
+              }
+              img[o++] = bits;
             }
-            img[o++] = bits;
-          }
   void* p = nullptr;
   VT_CUDA_OK(cudaMalloc(&p, n * 2));
   allocs.push_back(p);
@@ -441,10 +514,29 @@ int pack_conv_tc(ConvLayer& L, const std::vector<float>& w, int act_elem, std::v
   return VT_OK;
 }
 
+template <typename ActT>
+static int launch_conv_tc_t(const ConvArgs& a, const ConvLayer& L, int inst, uint32_t idesc, int grid, cudaStream_t st) {
+  switch (inst) {
+    case 1: return tc::launch_resblock<64, 2, 2, 4, 16, ActT>(a, L.w_tc, idesc, grid, st);
+    case 2: return tc::launch_resblock<128, 2, 1, 4, 16, ActT>(a, L.w_tc, idesc, grid, st);
+    case 3: return tc::launch_resblock<256, 1, 1, 3, 8, ActT>(a, L.w_tc, idesc, grid, st);
+    case 4: return tc::launch_plain<512, 128, 1, 1, 4, 4, 2, ActT>(a, L.w_tc, idesc, grid, st);
+    case 5: return tc::launch_plain<256, 128, 1, 2, 4, 4, 2, ActT>(a, L.w_tc, idesc, grid, st);
+    case 6: return tc::launch_plain<128, 64, 1, 2, 4, 8, 2, ActT>(a, L.w_tc, idesc, grid, st);
+    case 7: return tc::launch_plain<64, 32, 2, 2, 4, 8, 6, ActT>(a, L.w_tc, idesc, grid, st);
+    case 8: return tc::launch_plain<128, 128, 1, 2, 4, 4, 6, ActT>(a, L.w_tc, idesc, grid, st);
+  }
+  VT_REQUIRE(false, "conv_tc: layer %s has no tensor-core instance", L.name.c_str());
+  return VT_OK;
+}
+
 int launch_conv_tc(const ConvArgs& a_in, const ConvLayer& L, int act_elem, const void* tc_tiles, int n_tc_tiles,
                    int tile_rows, cudaStream_t st) {
   VT_REQUIRE(L.w_tc && a_in.in_act && (act_elem == ELEM_F16 || act_elem == ELEM_BF16), "conv_tc: layer %s not packed", L.name.c_str());
   if (n_tc_tiles == 0) return VT_OK;
+  const int inst = tc_instance(L);
+  const int NT = tc_nt(inst);
+  VT_REQUIRE(inst != 0 && tile_rows == conv_tc_tile_rows(L), "conv_tc: tile table does not match layer %s", L.name.c_str());
   ConvArgs a = a_in;
   a.tiles = reinterpret_cast<const ConvTile*>(tc_tiles);
   a.n_tiles = n_tc_tiles;
@@ -454,27 +546,14 @@ int launch_conv_tc(const ConvArgs& a_in, const ConvLayer& L, int act_elem, const
     VT_CUDA_OK(cudaGetDevice(&dev));
     VT_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int grid = n_tc_tiles < sm_count ? n_tc_tiles : sm_count;
+  const long long total = (long long)n_tc_tiles * (L.cout / NT);
+  const int grid = total < sm_count ? (int)total : sm_count;
   const uint32_t fmt = act_elem == ELEM_F16 ? 0u : 1u;
   // instruction descriptor: D = f32 (bits 4-5 = 1), A/B format (bits 7-9, 10-12), K-major A and B,
   // N>>3 at bits 17-22, M>>4 at bits 24-28
-  const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(L.cout >> 3) << 17) | ((128u >> 4) << 24);
-  const bool h = act_elem == ELEM_F16;
-  (void)tile_rows;
-  switch (L.cin) {
-    case 64:
-      return h ? tc::launch<64, 2, 2, 4, 16, __half>(a, L.w_tc, idesc, grid, st)
-               : tc::launch<64, 2, 2, 4, 16, __nv_bfloat16>(a, L.w_tc, idesc, grid, st);
-    case 128:
-      return h ? tc::launch<128, 2, 1, 4, 16, __half>(a, L.w_tc, idesc, grid, st)
-               : tc::launch<128, 2, 1, 4, 16, __nv_bfloat16>(a, L.w_tc, idesc, grid, st);
-    case 256:
-      return h ? tc::launch<256, 1, 1, 3, 8, __half>(a, L.w_tc, idesc, grid, st)
-               : tc::launch<256, 1, 1, 3, 8, __nv_bfloat16>(a, L.w_tc, idesc, grid, st);
-    default:
-      VT_REQUIRE(false, "conv_tc: unsupported channel count %d", L.cin);
-  }
-  return VT_OK;
+  const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
+  return act_elem == ELEM_F16 ? launch_conv_tc_t<__half>(a, L, inst, idesc, grid, st)
+                              : launch_conv_tc_t<__nv_bfloat16>(a, L, inst, idesc, grid, st);
 }
 
 }  // namespace vt

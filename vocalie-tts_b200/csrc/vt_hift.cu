@@ -45,16 +45,19 @@ struct Plan {
   long long total_T = 0;
   int T_max = 0;
   long long rows[3] = {0, 0, 0};            // packed rows per level (incl. gaps, excl. slack)
+  long long rowsM = 0;                      // packed rows of the gapped mel-rate level (conv_pre output)
   // device tables
   int* d_T = nullptr;
   int* d_mel_off = nullptr;
   long long* d_off[3] = {nullptr, nullptr, nullptr};
+  long long* d_offM = nullptr;
   ConvTile* d_tiles = nullptr;
   // tile-table segments (offset, count) inside d_tiles
   struct Seg { int off = 0, n = 0; };
-  Seg mel, up[3], sd[3], lvl[3];
+  Seg mel, pre, up[3], sd[3], lvl[3];
   Seg tc[3][2];                             // tensor-core tiles per level, [0]: 128 rows, [1]: 256 rows
-  std::vector<long long> h_off[3];
+  Seg tcu[3];                               // tensor-core tiles of the transposed convs (128 input steps)
+  std::vector<long long> h_off[3], h_offM;
   std::vector<int> h_mel_off;
   void* d_block = nullptr;
   size_t d_block_bytes = 0;
@@ -65,7 +68,9 @@ struct Workspace {
   double* phase_base;
   float *U[3], *S[3], *X[3], *XR[3], *Y[3];
   void *A[3][4];                            // activation copies A0, A1, A2, Q per level
-  long long cap_rows[3];
+  void *Yact[3];                            // leaky_relu(stage output) operand copies (next ups / conv_post)
+  void *xpre_act;                           // leaky_relu(conv_pre) operand copy, gapped mel-rate layout
+  long long cap_rows[3], cap_rowsM;
   size_t bytes;
 };
 
@@ -166,7 +171,10 @@ int pack_convT(vt_hift* h, ConvLayer& L, const std::map<std::string, HostTensor>
   L.flops_per_step = 2.0 * cin * cout * k;   // per INPUT step (= per s output steps)
   int rc = dev_upload(h, w.data(), w.size() * 4, (void**)&L.w);
   if (rc) return rc;
-  return dev_upload(h, b.data(), b.size() * 4, (void**)&L.bias);
+  rc = dev_upload(h, b.data(), b.size() * 4, (void**)&L.bias);
+  if (rc) return rc;
+  if (h->use_tc && conv_tc_supported(L)) return pack_conv_tc(L, w, h->act_elem, h->allocs);
+  return VT_OK;
 }
 
 int upload_vec(vt_hift* h, const std::map<std::string, HostTensor>& tab, const std::string& name, int64_t n, float** out) {
@@ -208,6 +216,15 @@ int build_plan(vt_hift* h, const int32_t* T, int B, cudaStream_t st) {
     P.total_T += T[b];
     P.T_max = std::max(P.T_max, (int)T[b]);
   }
+  {
+    P.h_offM.resize(B);
+    long long o = kGap;
+    for (int b = 0; b < B; ++b) {
+      P.h_offM[b] = o;
+      o += T[b] + kGap;
+    }
+    P.rowsM = o;
+  }
   for (int l = 0; l < 3; ++l) {
     long long o = kGap;
     for (int b = 0; b < B; ++b) {
@@ -220,7 +237,11 @@ int build_plan(vt_hift* h, const int32_t* T, int B, cudaStream_t st) {
   std::vector<ConvTile> tiles;
   add_tiles(tiles, P.mel, B, melrow.data(), lenM.data(), melrow.data(), lenM.data(), kTileQ);
   // ups[i]: conv space = input steps; input is mel-level (i=0) or level i-1
-  add_tiles(tiles, P.up[0], B, melrow.data(), lenM.data(), P.h_off[0].data(), lenM.data(), kTileQ);
+  add_tiles(tiles, P.pre, B, melrow.data(), lenM.data(), P.h_offM.data(), lenM.data(), kTileQ);
+  add_tiles(tiles, P.up[0], B, P.h_offM.data(), lenM.data(), P.h_off[0].data(), lenM.data(), kTileQ);
+  add_tiles(tiles, P.tcu[0], B, P.h_offM.data(), lenM.data(), P.h_off[0].data(), lenM.data(), 128);
+  add_tiles(tiles, P.tcu[1], B, P.h_off[0].data(), len[0].data(), P.h_off[1].data(), len[0].data(), 128);
+  add_tiles(tiles, P.tcu[2], B, P.h_off[1].data(), len[1].data(), P.h_off[2].data(), len[1].data(), 128);
   add_tiles(tiles, P.up[1], B, P.h_off[0].data(), len[0].data(), P.h_off[1].data(), len[0].data(), kTileQ);
   add_tiles(tiles, P.up[2], B, P.h_off[1].data(), len[1].data(), P.h_off[2].data(), len[1].data(), kTileQ);
   for (int l = 0; l < 3; ++l) {
@@ -231,7 +252,7 @@ int build_plan(vt_hift* h, const int32_t* T, int B, cudaStream_t st) {
   }
   // one device block: T | mel_off | off[3] | tiles
   const size_t nI = align_up((size_t)B * 4, 256), nL = align_up((size_t)B * 8, 256);
-  const size_t bytes = 2 * nI + 3 * nL + align_up(tiles.size() * sizeof(ConvTile), 256);
+  const size_t bytes = 2 * nI + 4 * nL + align_up(tiles.size() * sizeof(ConvTile), 256);
   if (bytes > P.d_block_bytes) {
     if (P.d_block) cudaFree(P.d_block);
     P.d_block = nullptr;
@@ -248,8 +269,10 @@ int build_plan(vt_hift* h, const int32_t* T, int B, cudaStream_t st) {
     std::memcpy(hp + 2 * nI + l * nL, P.h_off[l].data(), (size_t)B * 8);
     P.d_off[l] = (long long*)(dp + 2 * nI + l * nL);
   }
-  std::memcpy(hp + 2 * nI + 3 * nL, tiles.data(), tiles.size() * sizeof(ConvTile));
-  P.d_tiles = (ConvTile*)(dp + 2 * nI + 3 * nL);
+  std::memcpy(hp + 2 * nI + 3 * nL, P.h_offM.data(), (size_t)B * 8);
+  P.d_offM = (long long*)(dp + 2 * nI + 3 * nL);
+  std::memcpy(hp + 2 * nI + 4 * nL, tiles.data(), tiles.size() * sizeof(ConvTile));
+  P.d_tiles = (ConvTile*)(dp + 2 * nI + 4 * nL);
   // synchronous copy: `host` dies at scope exit; plans are cached per shape so this is off the steady state
   VT_CUDA_OK(cudaStreamSynchronize(st));
   VT_CUDA_OK(cudaMemcpy(P.d_block, host.data(), bytes, cudaMemcpyHostToDevice));
@@ -271,7 +294,9 @@ Workspace carve_ws(const vt_hift* h, int B, long long total_T, void* base) {
   w.f0 = (float*)take((size_t)rowsM * 4);
   w.phase_base = (double*)take((size_t)kHarm * rowsM * 8);
   w.s = (float*)take((size_t)total_T * kSPF * 4 + 64);
-  w.xpre = (float*)take((size_t)rowsM * kBase * 4);
+  w.cap_rowsM = total_T + (long long)B * kGap + kGap + 512;
+  w.xpre = (float*)take((size_t)w.cap_rowsM * kBase * 4);
+  w.xpre_act = take((size_t)w.cap_rowsM * kBase * es);
   for (int l = 0; l < 3; ++l) {
     const long long cap = (long long)kLevelMul[l] * total_T + (long long)B * (kGap + 1) + kGap + 512;
     w.cap_rows[l] = cap;
@@ -282,6 +307,7 @@ Workspace carve_ws(const vt_hift* h, int B, long long total_T, void* base) {
     w.XR[l] = (float*)take((size_t)cap * C * 4);
     w.Y[l] = (float*)take((size_t)cap * C * 4);
     for (int i = 0; i < 4; ++i) w.A[l][i] = take((size_t)cap * C * es);
+    w.Yact[l] = take((size_t)cap * C * es);
   }
   w.spec = (float*)take((size_t)w.cap_rows[2] * kSpecCh * 4);
   w.post = (float*)take((size_t)w.cap_rows[2] * kSpecCh * 4);
@@ -467,11 +493,13 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
 
   if (h->use_tc) {
     for (int l = 0; l < 3; ++l)
-      for (int i = 0; i < 4; ++i) {
-        k_zero_gaps<<<B + 1, 256, 0, st>>>(w.A[l][i], (kBase >> (l + 1)) * (int)elem_size(ae), P.d_off[l], P.d_T, B,
-                                           kLevelMul[l], l == 2 ? 1 : 0, P.rows[l]);
+      for (int i = 0; i < 5; ++i) {
+        k_zero_gaps<<<B + 1, 256, 0, st>>>(i < 4 ? w.A[l][i] : w.Yact[l], (kBase >> (l + 1)) * (int)elem_size(ae), P.d_off[l],
+                                           P.d_T, B, kLevelMul[l], l == 2 ? 1 : 0, P.rows[l]);
         VT_LAUNCHED();
       }
+    k_zero_gaps<<<B + 1, 256, 0, st>>>(w.xpre_act, kBase * (int)elem_size(ae), P.d_offM, P.d_T, B, 1, 0, P.rowsM);
+    VT_LAUNCHED();
   }
 
   // ---- F0 (ConvRNNF0Predictor) unless injected
@@ -501,9 +529,13 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
   if (rc) return rc;
   // ---- conv_pre
   {
-    ConvArgs a = base_args(h->conv_pre, P, P.mel);
+    ConvArgs a = base_args(h->conv_pre, P, P.pre);
     a.in = mel;
     a.out = w.xpre;
+    if (h->use_tc) {
+      a.act[0] = {w.xpre_act, nullptr, ACT_LRELU, 0.1f};
+      a.act_from_out = 1;
+    }
     rc = launch_conv_ref(a, ae, st);
     if (rc) return rc;
   }
@@ -511,11 +543,16 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
     // ups[i]( leaky_relu(x, 0.1) ), reflection pad (1, 0) on the last stage
     {
       ConvArgs a = base_args(h->ups[i], P, P.up[i]);
-      a.in = i == 0 ? w.xpre : w.Y[i - 1];
-      a.pro_act = ACT_LRELU; a.pro_slope = 0.1f;
       a.out = w.U[i];
       if (i == 2) { a.out_shift = 1; a.dup_row2 = 1; }
-      rc = launch_conv_ref(a, ae, st);
+      if (h->use_tc && h->ups[i].w_tc) {
+        a.in_act = i == 0 ? w.xpre_act : w.Yact[i - 1];   // leaky_relu already applied by the producer
+        rc = launch_conv_tc(a, h->ups[i], ae, P.d_tiles + P.tcu[i].off, P.tcu[i].n, 128, st);
+      } else {
+        a.in = i == 0 ? w.xpre : w.Y[i - 1];
+        a.pro_act = ACT_LRELU; a.pro_slope = 0.1f;
+        rc = launch_conv_ref(a, ae, st);
+      }
       if (rc) return rc;
     }
     // source_downs[i](s_stft) -> S stream + Snake copy for the first source-resblock conv
@@ -574,6 +611,10 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
           c.out = w.Y[i];
           c.out_accum = r > 0;
           c.out_scale = 1.0f / 3.0f;
+          if (h->use_tc && r == 2) {   // the mean is complete: emit the next layer's leaky_relu operand copy
+            c.act[0] = {w.Yact[i], nullptr, ACT_LRELU, i < 2 ? 0.1f : 0.01f};
+            c.act_from_out = 1;
+          }
         }
         rc = run_conv(h, c, h->rb_c2[R][j], i, st);
         if (rc) return rc;
@@ -584,10 +625,17 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
   // ---- conv_post( leaky_relu(x) ) with the default slope 0.01, then the spectral head
   {
     ConvArgs a = base_args(h->conv_post, P, P.lvl[2]);
-    a.in = w.Y[2];
-    a.pro_act = ACT_LRELU; a.pro_slope = 0.01f;
     a.out = w.post;
-    rc = launch_conv_ref(a, ae, st);
+    if (h->use_tc && h->conv_post.w_tc) {
+      a.in_act = w.Yact[2];
+      const int rows = conv_tc_tile_rows(h->conv_post);
+      const Plan::Seg& seg = P.tc[2][rows == 256 ? 1 : 0];
+      rc = launch_conv_tc(a, h->conv_post, ae, P.d_tiles + seg.off, seg.n, rows, st);
+    } else {
+      a.in = w.Y[2];
+      a.pro_act = ACT_LRELU; a.pro_slope = 0.01f;
+      rc = launch_conv_ref(a, ae, st);
+    }
     if (rc) return rc;
   }
   rc = launch_istft_head(w.post, P.d_mel_off, P.d_T, P.d_off[2], B, P.T_max, h->trim_fade, wav, st);
@@ -647,7 +695,7 @@ int64_t vt_hift_read_tap(vt_hift* h, const char* tap, int seq, float* out, int64
   else if (name == "s") { src = w.s; row0 = (long long)P.h_mel_off[seq] * kSPF; rows = (long long)T * kSPF; ld = ch = 1; }
   else if (name == "s_stft") { src = w.spec; row0 = P.h_off[2][seq]; rows = 120LL * T + 1; ld = kSpecCh; ch = kNfft + 2; }
   else if (name == "conv_post") { src = w.post; row0 = P.h_off[2][seq]; rows = 120LL * T + 1; ld = kSpecCh; ch = kNfft + 2; }
-  else if (name == "conv_pre") { src = w.xpre; row0 = P.h_mel_off[seq]; rows = T; ld = ch = kBase; }
+  else if (name == "conv_pre") { src = w.xpre; row0 = P.h_offM[seq]; rows = T; ld = ch = kBase; }
   else if (name.size() == 4 && name.compare(0, 3, "ups") == 0) level(name[3] - '0', w.U[name[3] - '0'], ELEM_F32);
   else if (name.size() == 2 && name[0] == 'x') level(name[1] - '0', w.X[name[1] - '0'], ELEM_F32);
   else if (name.size() == 6 && name.compare(0, 5, "stage") == 0) level(name[5] - '0', w.Y[name[5] - '0'], ELEM_F32);

@@ -69,6 +69,7 @@ struct ConvArgs {
   int out_accum;
   float out_scale;
   ActOut act[3];
+  int act_from_out;     // 1: act[0] is computed from the final output value (after scale/accumulate), not from v
   // output row mapping: column c' -> phase r = c'/phase_c, channel c'%phase_c, packed row
   //   out_row0 + q*out_mul + r + out_shift ; dup_row2: value landing on row 2 is also written to row 0
   int out_mul, out_shift, phase_c, dup_row2;

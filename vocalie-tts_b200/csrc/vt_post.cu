@@ -261,7 +261,8 @@ __global__ void k_range_out(const SegPlan* plan, const int64_t* seg_off, int n_s
 // Per segment: min-silence rule, snap, fallback, fade lengths (one block per segment).
 __global__ void __launch_bounds__(kThreads)
 k_fix(const float* __restrict__ audio, const int64_t* __restrict__ seg_off, int n_seg, SegPlan* plan,
-      int trim, int min_sil, int snap_radius, int fade_in, int fade_out, int stitch, int has_override) {
+      int trim, int min_sil, int snap_radius, int fade_in, int fade_out, int stitch, int has_override,
+      int head, int tail) {
   __shared__ unsigned long long sh_key[kThreads / 32];
   const int seg = blockIdx.x;
   const long long a = seg_off[seg], n = seg_off[seg + 1] - a;
@@ -293,8 +294,8 @@ k_fix(const float* __restrict__ audio, const int64_t* __restrict__ seg_off, int 
     if ((long long)fi > len) fi = (int)len;
     if ((long long)fo > len) fo = (int)len;
     if (stitch) {
-      if (seg == 0) fi = 0;
-      if (seg == n_seg - 1) fo = 0;
+      if (seg == 0 && head) fi = 0;
+      if (seg == n_seg - 1 && tail) fo = 0;
     }
     p.start = s;
     p.end = e;
@@ -344,7 +345,7 @@ k_peak(const float* __restrict__ audio, const int64_t* __restrict__ seg_off, int
 
 // ------------------------------------------------------------------------------------ plan
 __global__ void k_plan(SegPlan* plan, PostHeader* hdr, const int64_t* seg_off, int n_seg, int normalize,
-                       double target_peak, const float* peak_override, int concat, int gap_frames,
+                       double target_peak, const float* peak_override, int concat, int gap_frames, int tail,
                        double* results) {
   for (int i = threadIdx.x; i < n_seg; i += blockDim.x) {
     SegPlan& p = plan[i];
@@ -359,7 +360,7 @@ __global__ void k_plan(SegPlan* plan, PostHeader* hdr, const int64_t* seg_off, i
     }
     p.scale = __double2float_rn(scale);
     p.apply_scale = apply;
-    p.gap_after = (concat && i < n_seg - 1) ? gap_frames : 0;
+    p.gap_after = (concat && (i < n_seg - 1 || !tail)) ? gap_frames : 0;
     if (results) {
       double* r = results + (size_t)i * VT_POST_RESULT_STRIDE;
       r[0] = (double)p.start;
@@ -564,7 +565,7 @@ int vt_post_analyze(const float* audio, const int64_t* seg_off, int n_seg, int64
   }
   k_fix<<<n_seg, kThreads, 0, st>>>(audio, seg_off, n_seg, w.plan, prm->trim, prm->min_silence_frames,
                                     prm->snap_radius, prm->fade_in_frames, prm->fade_out_frames, prm->stitch,
-                                    range_override ? 1 : 0);
+                                    range_override ? 1 : 0, prm->stitch_head, prm->stitch_tail);
   VT_LAUNCHED();
   if (prm->normalize) {
     dim3 g(grid_x_for(n_seg, max_seg_len, kScanTile * kThreads), n_seg);
@@ -592,7 +593,8 @@ int vt_post_write(const float* audio, const int64_t* seg_off, int n_seg, int64_t
   PostWs w = carve(workspace, n_seg, n_samples);
   const int out_first = prm->stitch ? 1 : 0;
   k_plan<<<1, 256, 0, st>>>(w.plan, w.hdr, seg_off, n_seg, prm->normalize, prm->target_peak,
-                            peak_override, prm->concat, prm->stitch ? prm->gap_frames : 0, results);
+                            peak_override, prm->concat, prm->stitch ? prm->gap_frames : 0,
+                            prm->stitch ? prm->stitch_tail : 1, results);
   VT_LAUNCHED();
   if (total_out) {
     k_total_out<<<1, 32, 0, st>>>(w.hdr, total_out);

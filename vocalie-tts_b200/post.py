@@ -76,11 +76,11 @@ def last_launch_count() -> int:
 
 def make_params(*, sr=TARGET_SR, trim=0, silence_threshold=SILENCE_THRESHOLD, min_silence_frames=0,
                 snap_radius=-1, fade_in_frames=0, fade_out_frames=0, stitch=0, gap_frames=0,
-                normalize=0, clip=0, target_peak=1.0, concat=1, out_pcm16=0) -> PostParams:
+                normalize=0, clip=0, target_peak=1.0, concat=1, out_pcm16=0, stitch_head=1, stitch_tail=1) -> PostParams:
     return PostParams(int(sr), int(trim), float(silence_threshold), int(min_silence_frames),
                       int(snap_radius), int(fade_in_frames), int(fade_out_frames), int(stitch),
                       int(gap_frames), int(normalize), int(clip), float(target_peak), int(concat),
-                      int(out_pcm16))
+                      int(out_pcm16), int(stitch_head), int(stitch_tail))
 
 
 def _seg_arrays(torch, seg_off):
@@ -109,7 +109,7 @@ def post_process_device(audio, seg_off, params: PostParams, *, out=None, range_o
     seg_np, seg_dev, n_seg, n_samples, max_len = _seg_arrays(torch, seg_off)
     if n_samples > audio.numel():
         raise ValueError("seg_off exceeds the audio buffer")
-    cap = n_samples + max(n_seg - 1, 0) * max(int(params.gap_frames), 0) if params.concat else n_samples
+    cap = n_samples + n_seg * max(int(params.gap_frames), 0) if params.concat else n_samples
     odt = torch.int16 if params.out_pcm16 else torch.float32
     if out is None:
         out = torch.empty(max(cap, 4), dtype=odt, device="cuda") if params.concat else \
