@@ -181,18 +181,36 @@ def run_ours(args, rank, world, local_rank):
     audio_s_rank = n_chunks * T * SPF / SR
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
-    gather_buf = None
-    shard_cap = n_chunks * T * SPF + n_chunks * (GAP_MS * SR // 1000)
+    from vocalie_tts_b200 import distributed as D
+    gap_frames = GAP_MS * SR // 1000
+    shards = D.contiguous_shards(n_chunks * world, world)
+    pipe.set_shard(shards[rank], n_chunks * world)
+    shard_cap = n_chunks * T * SPF + n_chunks * gap_frames
+    final = [torch.empty(world * shard_cap, dtype=torch.float32, device=dev) if (world > 1 and rank == 0) else None]
+    host_final = torch.empty(world * shard_cap, dtype=torch.float32).pin_memory() if (world > 1 and rank == 0) else None
+    totals = [0]
 
     def step_device(seed):
-        res = pipe.run_device(mel_dev, Ts, seed=seed)
+        res = pipe.run_device(mel_dev, Ts, seed=seed, read_back=world > 1)
         if world > 1:
-            nonlocal gather_buf
-            shard = res.audio[:shard_cap]
-            if rank == 0 and gather_buf is None:
-                gather_buf = [torch.empty_like(shard) for _ in range(world)]
-            dist.gather(shard, gather_buf if rank == 0 else None, dst=0)
+            # output assembly: all-gather of per-chunk lengths + NCCL gather of the stitched shards to rank 0
+            lens = res.segments[:, 5].astype(np.int64)
+            out, total = D.assemble_on_rank0(res.audio[: res.total_samples], lens, shards[rank], n_chunks * world,
+                                             gap_frames, shards, out=final[0])
+            totals[0] = total
         return res
+
+    def step_e2e(seed):
+        """Host mels in, host audio out.  One GPU: the public VocoderPipeline.run().  Several GPUs: the same
+        copies around the sharded step; rank 0 reads the assembled job back."""
+        if world == 1:
+            return pipe.run(mel_host, Ts, seed=seed).audio.nbytes
+        mel_dev.copy_(mel_host, non_blocking=True)
+        step_device(seed)
+        if rank == 0:
+            host_final[: totals[0]].copy_(final[0][: totals[0]], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return totals[0] * 4 if rank == 0 else 0
 
     def barrier():
         if world > 1:
@@ -229,7 +247,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- end to end through the public API: pinned host mels in, host audio out, every step
     for _ in range(2):
-        pipe.run(mel_host, Ts, seed=7)
+        step_e2e(7)
     barrier()
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
@@ -238,8 +256,7 @@ def run_ours(args, rank, world, local_rank):
     t0.record()
     d2h = 0
     for i in range(e2e_steps):
-        res = pipe.run(mel_host, Ts, seed=200 + i)
-        d2h = res.audio.nbytes
+        d2h = step_e2e(200 + i)
     t1.record()
     barrier()
     wall = (time.perf_counter() - wall0) / e2e_steps

@@ -18,6 +18,7 @@
 //   warp 5 weight producer (bulk TMA), warps 6-7 activation producers (cp.async).
 #include "vt_hift.cuh"
 
+#include <cstdlib>
 #include <cstring>
 
 namespace vt {
@@ -71,6 +72,22 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // 8 rows x 16 B core matrices; SBO = byte distance between 8-row groups, LBO = between the two
 // 8-element K halves of one UMMA_K = 16 step.  Bits: [0,14) addr>>4, [16,30) LBO>>4, [32,46) SBO>>4,
 // [46,48) version = 1 (sm_100), [61,64) layout = 0.
+// Operand layout switch.  1: K-major SWIZZLE_128B (rows of 64 elements = 128 B, 16-byte chunk c of row r
+// stored at chunk c ^ (r & 7); 8-row atoms of 1024 B, SBO = 1024): the layout the tensor core fetches at
+// full rate.  The swizzle is a function of the shared-memory address bits, so a descriptor whose start
+// address is advanced by whole rows (128 B each) still addresses the right chunks: conv taps remain pure
+// descriptor shifts.  0: the no-swizzle panels described above (kept for reference; ~4x slower operand fetch).
+#ifndef VT_TC_SWIZZLE
+#define VT_TC_SWIZZLE 1
+#endif
+constexpr bool kSwz = VT_TC_SWIZZLE != 0;
+
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t addr) {
+  // [0,14) addr>>4, [16,30) LBO (unused for swizzled K-major; 1), [32,46) SBO = 1024>>4, [46,48) version 1,
+  // [61,64) layout type 2 = SWIZZLE_128B
+  return (uint64_t)((addr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
 __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
@@ -147,15 +164,25 @@ __device__ __forceinline__ float snake_f(float v, float alpha) {
   return fmaf(__fdividef(1.0f, alpha + 1e-9f), s * s, v);
 }
 
+// Debug timeline (VT_TC_TRACE): CTA 0 records clock64 at role events of its first kTraceTiles tiles.
+constexpr int kTraceTiles = 48, kTraceEvents = 10;
+__device__ __forceinline__ void trace_ev(long long* trace, int it, int ev) {
+  if (trace && blockIdx.x == 0 && it < kTraceTiles) trace[it * kTraceEvents + ev] = clock64();
+}
+
+constexpr int kProdWarps = 4;            // activation-producer warps
+constexpr int kProd = kProdWarps * 32;
+
 constexpr int pow2_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
 
 // CIN input channels (GEMM K per tap), NT output columns per CTA tile (GEMM N), MB 128-row M blocks
 // per tile, HALO = largest (k-1)*dil the instance accepts.
 template <int CIN, int NT, int MB, int HALO>
 struct Cfg {
-  static constexpr int RA = 128 * MB + HALO + 1;    // rows of the activation panels (odd)
+  // rows of the activation tile: a multiple of 8 (1024-byte swizzle atoms) or odd (no-swizzle panels)
+  static constexpr int RA = kSwz ? 128 * MB + ((HALO + 7) / 8) * 8 : 128 * MB + HALO + 1;
   static constexpr int KC = CIN / 8;                // 16-byte K chunks per row
-  static constexpr int A_BYTES = KC * RA * 16;
+  static constexpr int A_BYTES = KC * RA * 16;      // = (CIN/64) blocks x RA rows x 128 B when swizzled
   static constexpr int W_BYTES = NT * 128;          // one (n-tile, tap, 64-channel block) weight chunk
   static constexpr int ACC_COLS = MB * NT;
   static constexpr int TMEM_COLS = pow2_cols(2 * ACC_COLS);
@@ -168,13 +195,13 @@ struct Cfg {
 constexpr int EM_RES1 = 1, EM_RES2 = 2, EM_OUT = 4, EM_ACCUM = 8, EM_ACT1 = 16, EM_ACT3 = 32, EM_OACT = 64;
 
 template <int CIN, int NT, int MB, int A_ST, int W_ST, int NEPI, int HALO, int EM, typename ActT>
-__global__ void __launch_bounds__((NEPI + 4) * 32, 1)
+__global__ void __launch_bounds__((NEPI + 2 + kProdWarps) * 32, 1)
 k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t idesc) {
   using K = Cfg<CIN, NT, MB, HALO>;
   constexpr int W_MMA = NEPI, W_WP = NEPI + 1, W_AP = NEPI + 2;   // warp roles after the epilogue warps
   constexpr int NACT = (EM & EM_ACT3) ? 3 : ((EM & EM_ACT1) ? 1 : 0);
   constexpr int CB = CIN / 64;
-  extern __shared__ __align__(128) uint8_t smem[];
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sW = sA + A_ST * K::A_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sW + W_ST * K::W_BYTES);
@@ -189,7 +216,7 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < A_ST; ++i) { mbar_init(&a_full[i], 64); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < A_ST; ++i) { mbar_init(&a_full[i], kProd); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < W_ST; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], NEPI * 32); }
     fence_barrier_init();
@@ -220,15 +247,20 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
       const int ab = it % A_ST;
       const uint32_t ph = (uint32_t)(it / A_ST) & 1u;
       mbar_wait(&a_empty[ab], ph ^ 1u);
+      if (pt == 0) trace_ev(a.trace, it, 0);
       const ConvTile tile = a.tiles[t / n_nt];
       const ActT* src = in + (tile.in_row0 + tile.q0 - a.pad) * (long long)CIN;
       const uint32_t dst = smem_u32(sA + ab * K::A_BYTES);
-      for (int p = pt; p < pieces; p += 64) {
+      for (int p = pt; p < pieces; p += kProd) {
         const int r = p / K::KC, c = p - r * K::KC;
-        cp_async16(dst + (uint32_t)(c * K::RA + r) * 16u, src + (long long)r * CIN + c * 8);
+        const uint32_t off = kSwz ? (uint32_t)((c >> 3) * K::RA + r) * 128u + (uint32_t)(((c & 7) ^ (r & 7)) << 4)
+                                  : (uint32_t)(c * K::RA + r) * 16u;
+        cp_async16(dst + off, src + (long long)r * CIN + c * 8);
       }
+      if (pt == 0) trace_ev(a.trace, it, 1);
       cp_async_wait_all();
       fence_proxy_async();
+      if (pt == 0) trace_ev(a.trace, it, 2);
       mbar_arrive(&a_full[ab]);
     }
   } else if (warp == W_WP) {
@@ -258,28 +290,40 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
         const int as = it & 1;
         const uint32_t asph = (uint32_t)(it >> 1) & 1u;
         mbar_wait(&acc_empty[as], asph ^ 1u);
+        trace_ev(a.trace, it, 3);
         mbar_wait(&a_full[ab], aph);
+        trace_ev(a.trace, it, 4);
         tc_fence_after();
+        long long wwait = 0;
         for (int c = 0; c < nchunks; ++c, ++g) {
           const int j = c / CB, cb = c - j * CB;
           const uint32_t ws = g % W_ST, wph = (g / W_ST) & 1u;
+          const long long tw0 = a.trace ? clock64() : 0;
           mbar_wait(&w_full[ws], wph);
+          if (a.trace) wwait += clock64() - tw0;
           tc_fence_after();
 #pragma unroll
           for (int mb = 0; mb < MB; ++mb) {
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
-              const uint32_t a_addr = sA_addr + ab * K::A_BYTES +
-                                      (uint32_t)((cb * 8 + ks * 2) * K::RA + mb * 128 + j * a.dil) * 16u;
-              const uint32_t b_addr = sW_addr + ws * K::W_BYTES + (uint32_t)(ks * 2 * NT) * 16u;
-              umma_f16(tmem_base + (uint32_t)(as * K::ACC_COLS + mb * NT), make_desc(a_addr, K::RA * 16, 128),
-                       make_desc(b_addr, NT * 16, 128), idesc, (c > 0 || ks > 0) ? 1u : 0u);
+              uint64_t da, db;
+              if constexpr (kSwz) {
+                da = make_desc_sw128(sA_addr + ab * K::A_BYTES + (uint32_t)(cb * K::RA + mb * 128 + j * a.dil) * 128u + ks * 32u);
+                db = make_desc_sw128(sW_addr + ws * K::W_BYTES + ks * 32u);
+              } else {
+                da = make_desc(sA_addr + ab * K::A_BYTES + (uint32_t)((cb * 8 + ks * 2) * K::RA + mb * 128 + j * a.dil) * 16u,
+                               K::RA * 16, 128);
+                db = make_desc(sW_addr + ws * K::W_BYTES + (uint32_t)(ks * 2 * NT) * 16u, NT * 16, 128);
+              }
+              umma_f16(tmem_base + (uint32_t)(as * K::ACC_COLS + mb * NT), da, db, idesc, (c > 0 || ks > 0) ? 1u : 0u);
             }
           }
           umma_commit(&w_empty[ws]);
         }
         umma_commit(&a_empty[ab]);
         umma_commit(&acc_full[as]);
+        trace_ev(a.trace, it, 5);
+        if (a.trace && blockIdx.x == 0 && it < kTraceTiles) a.trace[it * kTraceEvents + 8] = wwait;
       }
     }
   } else {
@@ -301,6 +345,7 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
       const int rt = t / n_nt, nt = t - rt * n_nt;
       const ConvTile tile = a.tiles[rt];
       mbar_wait(&acc_full[as], asph);
+      if (threadIdx.x == 0) trace_ev(a.trace, it, 6);
       tc_fence_after();
 #pragma unroll 1
       for (int blk = eg; blk < NBLK; blk += NEPI / 4) {
@@ -322,30 +367,49 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
         float4 al[NACT > 0 ? NACT : 1];
 #pragma unroll
         for (int s = 0; s < NACT; ++s) al[s] = *reinterpret_cast<const float4*>(a.act[s].alpha + co);
+        // phase 1: issue every global read of this block (8 rows per lane) before any use, so the
+        // loads overlap instead of serialising behind the per-row control flow
+        const long long step0 = (long long)(tile.q0 + row0 + rsub) * a.out_mul + phase + a.out_shift;
+        const long long idx0 = (tile.out_row0 + step0) * ld + co;
+        const long long istride = 4LL * a.out_mul * ld;        // 4 rows per iteration
+        const int nvalid = tile.n - row0 - rsub;                // rows r = 4i + rsub are valid while 4i < nvalid
+        constexpr bool kLoads = (EM & (EM_RES1 | EM_RES2 | EM_ACCUM)) != 0;
+        float4 pre[kLoads ? 8 : 1];
+        if constexpr (kLoads) {
+          const bool accum = ((EM & EM_ACCUM) != 0) && a.out_accum;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (4 * i < nvalid) {
+              const long long idx = idx0 + i * istride;
+              if constexpr ((EM & EM_RES1) != 0) q = __ldg(reinterpret_cast<const float4*>(a.res1 + idx));
+              if constexpr ((EM & EM_RES2) != 0) {
+                const float4 q2 = __ldg(reinterpret_cast<const float4*>(a.res2 + idx));
+                q.x += q2.x; q.y += q2.y; q.z += q2.z; q.w += q2.w;
+              }
+              if (accum) {
+                // fold the previous partial mean into the residual term: (v + res)*s + prev = (v + res + prev/s)*s
+                const float4 pv = *reinterpret_cast<const float4*>(a.out + idx);
+                const float inv = 1.0f / a.out_scale;
+                q.x = fmaf(pv.x, inv, q.x); q.y = fmaf(pv.y, inv, q.y); q.z = fmaf(pv.z, inv, q.z); q.w = fmaf(pv.w, inv, q.w);
+              }
+            }
+            pre[i] = q;
+          }
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int r = i * 4 + rsub;
-          if (row0 + r >= tile.n) continue;
-          const long long step = (long long)(tile.q0 + row0 + r) * a.out_mul + phase + a.out_shift;
-          const long long idx = (tile.out_row0 + step) * ld + co;
+          if (4 * i >= nvalid) continue;
+          const long long step = step0 + 4LL * i * a.out_mul;
+          const long long idx = idx0 + i * istride;
           const float4 acc = *reinterpret_cast<const float4*>(stage + r * kStageLd + sub * 4);
           float x[4] = {acc.x + bias.x, acc.y + bias.y, acc.z + bias.z, acc.w + bias.w};
-          if constexpr ((EM & EM_RES1) != 0) {
-            const float4 q = __ldg(reinterpret_cast<const float4*>(a.res1 + idx));
-            x[0] += q.x; x[1] += q.y; x[2] += q.z; x[3] += q.w;
-          }
-          if constexpr ((EM & EM_RES2) != 0) {
-            const float4 q = __ldg(reinterpret_cast<const float4*>(a.res2 + idx));
-            x[0] += q.x; x[1] += q.y; x[2] += q.z; x[3] += q.w;
+          if constexpr (kLoads) {
+            x[0] += pre[i].x; x[1] += pre[i].y; x[2] += pre[i].z; x[3] += pre[i].w;
           }
           if constexpr ((EM & EM_OUT) != 0) {
             float4 o = make_float4(x[0] * a.out_scale, x[1] * a.out_scale, x[2] * a.out_scale, x[3] * a.out_scale);
-            if constexpr ((EM & EM_ACCUM) != 0) {
-              if (a.out_accum) {
-                const float4 p = *reinterpret_cast<const float4*>(a.out + idx);
-                o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
-              }
-            }
             *reinterpret_cast<float4*>(a.out + idx) = o;
             if (a.dup_row2 && step == 2)                      // reflection pad (1, 0): padded[0] = unpadded[1]
               *reinterpret_cast<float4*>(a.out + tile.out_row0 * ld + co) = o;
@@ -367,6 +431,7 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[as]);
+      if (threadIdx.x == 0) trace_ev(a.trace, it, 7);
     }
   }
 
@@ -395,7 +460,7 @@ int launch_em(const ConvArgs& a, const void* wtc, uint32_t idesc, int grid, cuda
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  k_conv_tc<CIN, NT, MB, A_ST, W_ST, NEPI, HALO, EM, ActT><<<grid, (NEPI + 4) * 32, smem, st>>>(
+  k_conv_tc<CIN, NT, MB, A_ST, W_ST, NEPI, HALO, EM, ActT><<<grid, (NEPI + 2 + kProdWarps) * 32, smem, st>>>(
       a, reinterpret_cast<const uint8_t*>(wtc), idesc);
   VT_LAUNCHED();
   return VT_OK;
@@ -488,24 +553,32 @@ int pack_conv_tc(ConvLayer& L, const std::vector<float>& w, int act_elem, std::v
   VT_REQUIRE(N % NT == 0 && CIN % 64 == 0, "conv_tc: layer %s does not tile (cin=%d cout=%d)", L.name.c_str(), CIN, N);
   const size_t n = (size_t)k * CIN * N;
   std::vector<uint16_t> img(n);
-  size_t o = 0;
+  auto to_bits = [&](float v) {
+    uint16_t bits;
+    if (act_elem == ELEM_F16) {
+      const __half hv = __float2half_rn(v);
+      std::memcpy(&bits, &hv, 2);
+    } else {
+      const __nv_bfloat16 bv = __float2bfloat16_rn(v);
+      std::memcpy(&bits, &bv, 2);
+    }
+    return bits;
+  };
+  size_t chunk = 0;
   for (int nt = 0; nt < N / NT; ++nt)
     for (int j = 0; j < k; ++j)
-      for (int cb = 0; cb < CIN / 64; ++cb)
-        for (int k8 = 0; k8 < 8; ++k8)
-          for (int co = 0; co < NT; ++co)
+      for (int cb = 0; cb < CIN / 64; ++cb, ++chunk) {
+        uint16_t* dst = img.data() + chunk * (size_t)NT * 64;
+        for (int co = 0; co < NT; ++co)
+          for (int k8 = 0; k8 < 8; ++k8)
             for (int e = 0; e < 8; ++e) {
               const float v = w[((size_t)j * CIN + cb * 64 + k8 * 8 + e) * N + nt * NT + co];
-              uint16_t bits;
-              if (act_elem == ELEM_F16) {
-                const __half hv = __float2half_rn(v);
-                std::memcpy(&bits, &hv, 2);
-              } else {
-                const __nv_bfloat16 bv = __float2bfloat16_rn(v);
-                std::memcpy(&bits, &bv, 2);
-              }
-              img[o++] = bits;
+              // swizzled: row co is 128 B, its 16-byte chunk k8 sits at k8 ^ (co & 7); else panels [k8][co][e]
+              const size_t pos = tc::kSwz ? (size_t)co * 64 + (size_t)((k8 ^ (co & 7)) * 8 + e)
+                                          : ((size_t)k8 * NT + co) * 8 + e;
+              dst[pos] = to_bits(v);
             }
+      }
   void* p = nullptr;
   VT_CUDA_OK(cudaMalloc(&p, n * 2));
   allocs.push_back(p);
@@ -546,14 +619,40 @@ int launch_conv_tc(const ConvArgs& a_in, const ConvLayer& L, int act_elem, const
     VT_CUDA_OK(cudaGetDevice(&dev));
     VT_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
   }
+  // debug timeline: VT_TC_TRACE=<layer name> dumps CTA 0's per-tile role timestamps to stderr
+  static const char* trace_name = getenv("VT_TC_TRACE");
+  static long long* d_trace = nullptr;
+  const bool tracing = trace_name && L.name == trace_name;
+  if (tracing) {
+    if (!d_trace) VT_CUDA_OK(cudaMalloc(&d_trace, tc::kTraceTiles * tc::kTraceEvents * 8));
+    VT_CUDA_OK(cudaMemsetAsync(d_trace, 0, tc::kTraceTiles * tc::kTraceEvents * 8, st));
+    a.trace = d_trace;
+  }
   const long long total = (long long)n_tc_tiles * (L.cout / NT);
   const int grid = total < sm_count ? (int)total : sm_count;
   const uint32_t fmt = act_elem == ELEM_F16 ? 0u : 1u;
   // instruction descriptor: D = f32 (bits 4-5 = 1), A/B format (bits 7-9, 10-12), K-major A and B,
   // N>>3 at bits 17-22, M>>4 at bits 24-28
   const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
-  return act_elem == ELEM_F16 ? launch_conv_tc_t<__half>(a, L, inst, idesc, grid, st)
-                              : launch_conv_tc_t<__nv_bfloat16>(a, L, inst, idesc, grid, st);
+  const int rc = act_elem == ELEM_F16 ? launch_conv_tc_t<__half>(a, L, inst, idesc, grid, st)
+                                      : launch_conv_tc_t<__nv_bfloat16>(a, L, inst, idesc, grid, st);
+  if (tracing && rc == VT_OK) {
+    std::vector<long long> h(tc::kTraceTiles * tc::kTraceEvents);
+    VT_CUDA_OK(cudaStreamSynchronize(st));
+    VT_CUDA_OK(cudaMemcpy(h.data(), d_trace, h.size() * 8, cudaMemcpyDeviceToHost));
+    long long t0 = 0;
+    for (long long v : h) if (v && (!t0 || v < t0)) t0 = v;
+    fprintf(stderr, "[vt trace] layer %s k=%d dil=%d tiles=%lld grid=%d  (cycles since first event; "
+            "A:wait_empty issued landed | MMA:acc_free a_full issued | EPI:acc_full done)\n", L.name.c_str(), L.k, L.dil, total, grid);
+    for (int it = 0; it < tc::kTraceTiles; ++it) {
+      if (!h[it * tc::kTraceEvents + 6]) break;
+      fprintf(stderr, "[vt trace] %2d", it);
+      for (int e = 0; e < 8; ++e) fprintf(stderr, " %8lld", h[it * tc::kTraceEvents + e] ? h[it * tc::kTraceEvents + e] - t0 : -1);
+      fprintf(stderr, "  w_wait=%lld", h[it * tc::kTraceEvents + 8]);
+      fprintf(stderr, "\n");
+    }
+  }
+  return rc;
 }
 
 }  // namespace vt

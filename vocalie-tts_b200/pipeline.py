@@ -38,6 +38,7 @@ class VocoderPipeline:
                          target_dbfs=float(target_dbfs), fade_ms=int(fade_ms), zero_cross_radius_ms=int(zero_cross_radius_ms),
                          silence_threshold=float(silence_threshold), silence_min_ms=int(silence_min_ms),
                          out_pcm16=bool(out_pcm16))
+        self.stitch_head, self.stitch_tail = 1, 1     # single-GPU job; a shard of a multi-GPU job sets these
         self._host_in = None
         self._host_out = None
         self._dev_in = None
@@ -45,10 +46,17 @@ class VocoderPipeline:
         self._out = None
         self.last_launches = 0
 
+    def set_shard(self, chunk_ids, n_total_chunks: int) -> None:
+        """Declare that this pipeline holds ``chunk_ids`` (sorted job-order indices) of a job sharded
+        over several GPUs: only the job's first chunk skips the fade-in, only its last chunk skips the
+        fade-out and the trailing gap (see distributed.py)."""
+        from .distributed import stitch_flags
+        self.stitch_head, self.stitch_tail = stitch_flags(chunk_ids, n_total_chunks)
+
     def post_params(self, n_chunks: int):
         o = self.opts
         sr = self.sr
-        gap_on = o["chunk_gap_ms"] > 0 and n_chunks > 1
+        gap_on = o["chunk_gap_ms"] > 0 and (n_chunks > 1 or not (self.stitch_head and self.stitch_tail))
         fade = _post._ms_to_frames(sr, o["fade_ms"])
         return _post.make_params(
             sr=sr, trim=1 if o["trim_silence"] else 0, silence_threshold=o["silence_threshold"],
@@ -57,7 +65,7 @@ class VocoderPipeline:
             fade_in_frames=fade if gap_on else 0, fade_out_frames=fade if gap_on else 0, stitch=1,
             gap_frames=_post._ms_to_frames(sr, o["chunk_gap_ms"]) if gap_on else 0,
             normalize=1 if o["normalize"] else 0, target_peak=float(10 ** (o["target_dbfs"] / 20.0)), concat=1,
-            out_pcm16=1 if o["out_pcm16"] else 0)
+            out_pcm16=1 if o["out_pcm16"] else 0, stitch_head=self.stitch_head, stitch_tail=self.stitch_tail)
 
     def run_device(self, mel, T, *, f0=None, phase_vec=None, noise=None, seed: int = 0, read_back: bool = False) -> JobResult:
         """``mel``: float32 CUDA [sum_T, 80]; ``T``: int32 frames per chunk (host)."""
@@ -69,7 +77,7 @@ class VocoderPipeline:
         wav = self.voc.forward_packed(mel, T, f0=f0, phase_vec=phase_vec, noise=noise, seed=seed, out=self._wav)
         seg_off = np.concatenate([[0], np.cumsum(T.astype(np.int64) * SAMPLES_PER_FRAME)])
         prm = self.post_params(len(T))
-        cap = n + max(len(T) - 1, 0) * int(prm.gap_frames)
+        cap = n + len(T) * int(prm.gap_frames)
         odt = torch.int16 if prm.out_pcm16 else torch.float32
         if self._out is None or self._out.numel() < max(cap, 4) or self._out.dtype != odt:
             self._out = torch.empty(max(cap, 4), dtype=odt, device=self.voc.device)
