@@ -184,6 +184,11 @@ int vt_hift_set_profiling(vt_hift* h, int enable);
 int vt_hift_read_profile(vt_hift* h, double* total_ms, double* resblock_ms, double* resblock_flops,
                          int* resblock_launches);
 
+/* Profiling timeline of the last forward as text, one "section=milliseconds" line per section
+ * (zero_gaps, f0_predictor, source_stft, conv_pre, ups<i>, source_down<i>, source_resblock<i>,
+ * resblocks<i>, conv_post, istft_head).  `out` is a HOST buffer of `capacity` bytes. */
+int vt_hift_read_timeline(vt_hift* h, char* out /* HOST */, int capacity);
+
 /* Number of kernels launched by the last vt_hift_forward / vt_post_process on this thread. */
 int vt_last_launch_count(void);
 

@@ -62,6 +62,7 @@ _SIGS = {
     "vt_hift_set_profiling": (C.c_int, [_P, C.c_int]),
     "vt_hift_read_profile": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                        C.POINTER(C.c_int)]),
+    "vt_hift_read_timeline": (C.c_int, [_P, C.c_char_p, C.c_int]),
     "vt_hift_read_tap": (_I64, [_P, C.c_char_p, C.c_int, _P, _I64, _P, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGS)

@@ -36,22 +36,36 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// Bounded wait: a protocol bug must fault the launch, not hang the GPU.
+// Bounded wait: a protocol bug must fault the launch, not hang the GPU.  The clock is only read
+// once the first probe has failed.
+__device__ __forceinline__ bool mbar_try(uint32_t addr, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(addr), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+__device__ __noinline__ void mbar_wait_slow(uint32_t addr, uint32_t parity) {
+  const long long t0 = clock64();
+  while (!mbar_try(addr, parity))
+    if (clock64() - t0 > 4000000000LL) __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
-  uint32_t done = 0;
-  const long long t0 = clock64();
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (done) break;
-    if (clock64() - t0 > 4000000000LL) __trap();
-  }
+  if (!mbar_try(addr, parity)) mbar_wait_slow(addr, parity);
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -99,6 +113,19 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Same MMA with the descriptors given as (lo, hi) words: the hi words are compile-time constants of the
+// layout, the lo words advance by plain adds (address >> 4).
+__device__ __forceinline__ void umma_f16_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -153,15 +180,12 @@ template <> struct Pack4<__nv_bfloat16> {
 
 constexpr int kStageLd = 36;   // floats per staged row (32 + 4 pad: conflict-free 16-byte accesses both ways)
 
-// Snake with a two-constant Cody-Waite reduction to [-pi, pi] and the SFU sine: absolute error
-// ~1e-6 for |alpha*x| < 1e3, two orders below the operand rounding of the tensor-core path.
-__device__ __forceinline__ float snake_f(float v, float alpha) {
-  const float t = v * alpha;
-  const float n = rintf(t * 0.15915494309189535f);
-  float r = fmaf(n, -6.2831854820251465f, t);
-  r = fmaf(n, 1.7484555e-7f, r);
-  const float s = __sinf(r);
-  return fmaf(__fdividef(1.0f, alpha + 1e-9f), s * s, v);
+// Snake x + sin^2(alpha x) / alpha on the SFU: sin.approx takes the angle in revolutions after one
+// multiply, and the hardware reduces the range exactly, so the only error is the rounding of
+// alpha*x/2pi: ~4e-7 * |alpha x| radians, orders below the fp16 rounding of the operand it feeds.
+__device__ __forceinline__ float snake_f(float v, float alpha, float inv_alpha) {
+  const float s = __sinf(v * alpha);
+  return fmaf(inv_alpha, s * s, v);
 }
 
 // Debug timeline (VT_TC_TRACE): CTA 0 records clock64 at role events of its first kTraceTiles tiles.
@@ -251,7 +275,7 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
       const ConvTile tile = a.tiles[t / n_nt];
       const ActT* src = in + (tile.in_row0 + tile.q0 - a.pad) * (long long)CIN;
       const uint32_t dst = smem_u32(sA + ab * K::A_BYTES);
-      for (int p = pt; p < pieces; p += kProd) {
+      for (int p = pt; p < pieces && !(a.dbg & 2); p += kProd) {
         const int r = p / K::KC, c = p - r * K::KC;
         const uint32_t off = kSwz ? (uint32_t)((c >> 3) * K::RA + r) * 128u + (uint32_t)(((c & 7) ^ (r & 7)) << 4)
                                   : (uint32_t)(c * K::RA + r) * 16u;
@@ -266,65 +290,71 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
   } else if (warp == W_WP) {
     // ---------------- weight producer: one bulk copy per (tap, 64-channel block) of this tile's column tile
     if (lane == 0) {
-      uint32_t g = 0;
+      uint32_t ws = 0, ph = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const int nt = t % n_nt;
         const uint8_t* wsrc = wtc + (size_t)nt * nchunks * K::W_BYTES;
-        for (int c = 0; c < nchunks; ++c, ++g) {
-          const uint32_t ws = g % W_ST, ph = (g / W_ST) & 1u;
+        for (int c = 0; c < nchunks; ++c, ws = (ws + 1 == (uint32_t)W_ST ? 0u : ws + 1), ph ^= (ws == 0 ? 1u : 0u)) {
           mbar_wait(&w_empty[ws], ph ^ 1u);
+          if (a.dbg & 1) { mbar_arrive(&w_full[ws]); continue; }
           mbar_arrive_expect_tx(&w_full[ws], K::W_BYTES);
           bulk_g2s(sW + ws * K::W_BYTES, wsrc + (size_t)c * K::W_BYTES, K::W_BYTES, &w_full[ws]);
         }
       }
     }
   } else if (warp == W_MMA) {
-    // ---------------- MMA issuer (one thread)
-    if (lane == 0) {
-      uint32_t g = 0;
-      int it = 0;
-      const uint32_t sA_addr = smem_u32(sA), sW_addr = smem_u32(sW);
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-        const int ab = it % A_ST;
-        const uint32_t aph = (uint32_t)(it / A_ST) & 1u;
-        const int as = it & 1;
-        const uint32_t asph = (uint32_t)(it >> 1) & 1u;
-        mbar_wait(&acc_empty[as], asph ^ 1u);
-        trace_ev(a.trace, it, 3);
-        mbar_wait(&a_full[ab], aph);
-        trace_ev(a.trace, it, 4);
-        tc_fence_after();
-        long long wwait = 0;
-        for (int c = 0; c < nchunks; ++c, ++g) {
-          const int j = c / CB, cb = c - j * CB;
-          const uint32_t ws = g % W_ST, wph = (g / W_ST) & 1u;
-          const long long tw0 = a.trace ? clock64() : 0;
+    // ---------------- MMA issuer: the whole warp runs the loop (convergent waits), one elected lane
+    // issues.  Descriptors are (lo, hi) pairs: hi is a constant of the layout, lo advances by adds.
+    static_assert(kSwz, "the issue loop assumes the SWIZZLE_128B operand layout");
+    constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t a_lo0 = ((smem_u32(sA) >> 4) & 0x3FFFu) | (1u << 16);
+    const uint32_t w_lo0 = ((smem_u32(sW) >> 4) & 0x3FFFu) | (1u << 16);
+    const uint32_t tap16 = (uint32_t)a.dil * 8u;                 // one tap = dil rows of 128 B, in 16-byte units
+    const bool mma_on = !(a.dbg & 16);
+    uint32_t ws = 0, wph = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      const int ab = it % A_ST;
+      const uint32_t aph = (uint32_t)(it / A_ST) & 1u;
+      const int as = it & 1;
+      const uint32_t asph = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(&acc_empty[as], asph ^ 1u);
+      if (lane == 0) trace_ev(a.trace, it, 3);
+      mbar_wait(&a_full[ab], aph);
+      if (lane == 0) trace_ev(a.trace, it, 4);
+      tc_fence_after();
+      const uint32_t d0 = tmem_base + (uint32_t)(as * K::ACC_COLS);
+      const uint32_t a_tile = a_lo0 + (uint32_t)ab * (uint32_t)(K::A_BYTES >> 4);
+      uint32_t acc = 0;
+      for (int j = 0; j < a.k; ++j) {
+        uint32_t a_chunk = a_tile + (uint32_t)j * tap16;
+#pragma unroll 1
+        for (int cb = 0; cb < CB; ++cb, a_chunk += (uint32_t)K::RA * 8u) {
           mbar_wait(&w_full[ws], wph);
-          if (a.trace) wwait += clock64() - tw0;
           tc_fence_after();
+          if (elect_one()) {
+            const uint32_t b_lo = w_lo0 + ws * (uint32_t)(K::W_BYTES >> 4);
+            if (mma_on) {
 #pragma unroll
-          for (int mb = 0; mb < MB; ++mb) {
+              for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              uint64_t da, db;
-              if constexpr (kSwz) {
-                da = make_desc_sw128(sA_addr + ab * K::A_BYTES + (uint32_t)(cb * K::RA + mb * 128 + j * a.dil) * 128u + ks * 32u);
-                db = make_desc_sw128(sW_addr + ws * K::W_BYTES + ks * 32u);
-              } else {
-                da = make_desc(sA_addr + ab * K::A_BYTES + (uint32_t)((cb * 8 + ks * 2) * K::RA + mb * 128 + j * a.dil) * 16u,
-                               K::RA * 16, 128);
-                db = make_desc(sW_addr + ws * K::W_BYTES + (uint32_t)(ks * 2 * NT) * 16u, NT * 16, 128);
-              }
-              umma_f16(tmem_base + (uint32_t)(as * K::ACC_COLS + mb * NT), da, db, idesc, (c > 0 || ks > 0) ? 1u : 0u);
+                for (int ks = 0; ks < 4; ++ks)
+                  umma_f16_lh(d0 + (uint32_t)(mb * NT), a_chunk + (uint32_t)(mb * 1024 + ks * 2), b_lo + (uint32_t)(ks * 2),
+                              kDescHi, idesc, ks == 0 ? acc : 1u);
             }
+            umma_commit(&w_empty[ws]);
           }
-          umma_commit(&w_empty[ws]);
+          __syncwarp();
+          acc = 1u;
+          if (++ws == (uint32_t)W_ST) { ws = 0; wph ^= 1u; }
         }
+      }
+      if (elect_one()) {
         umma_commit(&a_empty[ab]);
         umma_commit(&acc_full[as]);
-        trace_ev(a.trace, it, 5);
-        if (a.trace && blockIdx.x == 0 && it < kTraceTiles) a.trace[it * kTraceEvents + 8] = wwait;
       }
+      __syncwarp();
+      if (lane == 0) trace_ev(a.trace, it, 5);
     }
   } else {
     // ---------------- epilogue warps 0..NEPI-1.  Warp w may touch TMEM lanes 32*(w%4)..+31; the NEPI/4
@@ -349,6 +379,7 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
       tc_fence_after();
 #pragma unroll 1
       for (int blk = eg; blk < NBLK; blk += NEPI / 4) {
+        if (a.dbg & 4) break;
         const int mb = blk / (NT / 32), c0 = (blk - mb * (NT / 32)) * 32;
         const int row0 = mb * 128 + quarter * 32;                    // tile-local row of this warp's lane 0
         uint32_t v[32];
@@ -361,12 +392,17 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
               make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]),
                           __uint_as_float(v[4 * g + 3]));
         __syncwarp();
+        if (a.dbg & 8) continue;
         const int cg = nt * NT + c0 + sub * 4;             // GEMM column of this lane's float4
         const int phase = cg / ld, co = cg - phase * ld;   // transposed convs: column -> (output phase, channel)
         const float4 bias = *reinterpret_cast<const float4*>(a.bias + cg);
-        float4 al[NACT > 0 ? NACT : 1];
+        float4 al[NACT > 0 ? NACT : 1], ia[NACT > 0 ? NACT : 1];
 #pragma unroll
-        for (int s = 0; s < NACT; ++s) al[s] = *reinterpret_cast<const float4*>(a.act[s].alpha + co);
+        for (int s = 0; s < NACT; ++s) {
+          al[s] = *reinterpret_cast<const float4*>(a.act[s].alpha + co);
+          ia[s] = make_float4(__fdividef(1.0f, al[s].x + 1e-9f), __fdividef(1.0f, al[s].y + 1e-9f),
+                              __fdividef(1.0f, al[s].z + 1e-9f), __fdividef(1.0f, al[s].w + 1e-9f));
+        }
         // phase 1: issue every global read of this block (8 rows per lane) before any use, so the
         // loads overlap instead of serialising behind the per-row control flow
         const long long step0 = (long long)(tile.q0 + row0 + rsub) * a.out_mul + phase + a.out_shift;
@@ -423,8 +459,8 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
 #pragma unroll
           for (int s = 0; s < NACT; ++s) {
             float y[4];
-            y[0] = snake_f(x[0], al[s].x); y[1] = snake_f(x[1], al[s].y);
-            y[2] = snake_f(x[2], al[s].z); y[3] = snake_f(x[3], al[s].w);
+            y[0] = snake_f(x[0], al[s].x, ia[s].x); y[1] = snake_f(x[1], al[s].y, ia[s].y);
+            y[2] = snake_f(x[2], al[s].z, ia[s].z); y[3] = snake_f(x[3], al[s].w, ia[s].w);
             *reinterpret_cast<uint2*>(reinterpret_cast<ActT*>(a.act[s].dst) + idx) = Pack4<ActT>::pack(y);
           }
         }
@@ -623,6 +659,10 @@ int launch_conv_tc(const ConvArgs& a_in, const ConvLayer& L, int act_elem, const
   static const char* trace_name = getenv("VT_TC_TRACE");
   static long long* d_trace = nullptr;
   const bool tracing = trace_name && L.name == trace_name;
+  // timing ablation (results are wrong): VT_TC_DBG bits 1 = no weight copies, 2 = no activation copies,
+  // 4 = no epilogue, 8 = epilogue without global traffic, 16 = no MMAs
+  static const int dbg = getenv("VT_TC_DBG") ? atoi(getenv("VT_TC_DBG")) : 0;
+  a.dbg = dbg;
   if (tracing) {
     if (!d_trace) VT_CUDA_OK(cudaMalloc(&d_trace, tc::kTraceTiles * tc::kTraceEvents * 8));
     VT_CUDA_OK(cudaMemsetAsync(d_trace, 0, tc::kTraceTiles * tc::kTraceEvents * 8, st));

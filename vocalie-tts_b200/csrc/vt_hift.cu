@@ -95,6 +95,9 @@ struct vt_hift {
   cudaEvent_t ev_rb[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
   double rb_flops = 0;
   int rb_launches = 0;
+  // named timeline marks of the last forward (profiling only): events are created once and reused
+  std::vector<std::pair<std::string, cudaEvent_t>> marks;
+  size_t n_marks = 0;
 };
 
 namespace vt {
@@ -330,6 +333,20 @@ __global__ void k_zero_gaps(void* buf, int row_bytes, const long long* off, cons
 
 }  // namespace
 
+// Profiling timeline: record a named event after the work enqueued so far.
+static int mark(vt_hift* h, const char* name, cudaStream_t st) {
+  if (!h->profiling) return VT_OK;
+  if (h->n_marks == h->marks.size()) {
+    cudaEvent_t e;
+    VT_CUDA_OK(cudaEventCreate(&e));
+    h->marks.emplace_back(name, e);
+  }
+  h->marks[h->n_marks].first = name;
+  VT_CUDA_OK(cudaEventRecord(h->marks[h->n_marks].second, st));
+  ++h->n_marks;
+  return VT_OK;
+}
+
 static ConvArgs base_args(const ConvLayer& L, const Plan& P, const Plan::Seg& seg) {
   ConvArgs a{};
   a.w = L.w; a.bias = L.bias;
@@ -450,6 +467,7 @@ void vt_hift_destroy(vt_hift* h) {
   for (int i = 0; i < 2; ++i) if (h->ev_fwd[i]) cudaEventDestroy(h->ev_fwd[i]);
   for (int l = 0; l < 3; ++l)
     for (int i = 0; i < 2; ++i) if (h->ev_rb[l][i]) cudaEventDestroy(h->ev_rb[l][i]);
+  for (auto& m : h->marks) cudaEventDestroy(m.second);
   delete h;
 }
 
@@ -489,6 +507,8 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
     VT_CUDA_OK(cudaEventRecord(h->ev_fwd[0], st));
     h->rb_flops = 0;
     h->rb_launches = 0;
+    h->n_marks = 0;
+    mark(h, "start", st);
   }
 
   if (h->use_tc) {
@@ -502,6 +522,7 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
     VT_LAUNCHED();
   }
 
+  mark(h, "zero_gaps", st);
   // ---- F0 (ConvRNNF0Predictor) unless injected
   const float* f0 = f0_in;
   if (!f0) {
@@ -521,12 +542,14 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
   } else {
     VT_CUDA_OK(cudaMemcpyAsync(w.f0, f0_in, (size_t)total_T * 4, cudaMemcpyDeviceToDevice, st));  // keeps the "f0" tap valid
   }
+  mark(h, "f0_predictor", st);
   // ---- source: SineGen -> tanh(Linear) -> STFT
   rc = launch_sine_source(f0, P.d_mel_off, P.d_T, B, total_T, phase_vec, noise, seed, h->lin_w, h->lin_b,
                           w.phase_base, w.s, st);
   if (rc) return rc;
   rc = launch_stft(w.s, P.d_mel_off, P.d_T, P.d_off[2], B, total_T, w.spec, st);
   if (rc) return rc;
+  mark(h, "source_stft", st);
   // ---- conv_pre
   {
     ConvArgs a = base_args(h->conv_pre, P, P.pre);
@@ -539,7 +562,9 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
     rc = launch_conv_ref(a, ae, st);
     if (rc) return rc;
   }
+  mark(h, "conv_pre", st);
   for (int i = 0; i < 3; ++i) {
+    const std::string sfx = std::to_string(i);
     // ups[i]( leaky_relu(x, 0.1) ), reflection pad (1, 0) on the last stage
     {
       ConvArgs a = base_args(h->ups[i], P, P.up[i]);
@@ -555,6 +580,7 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
       }
       if (rc) return rc;
     }
+    mark(h, ("ups" + sfx).c_str(), st);
     // source_downs[i](s_stft) -> S stream + Snake copy for the first source-resblock conv
     {
       ConvArgs a = base_args(h->sdown[i], P, P.sd[i]);
@@ -564,6 +590,7 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
       rc = launch_conv_ref(a, ae, st);
       if (rc) return rc;
     }
+    mark(h, ("source_down" + sfx).c_str(), st);
     // source_resblocks[i]; its last conv also adds the upsampled stream: x = ups + si
     if (prof) {
       VT_CUDA_OK(cudaEventRecord(h->ev_rb[i][0], st));
@@ -592,6 +619,7 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
       rc = run_conv(h, c, h->src_c2[i][j], i, st);
       if (rc) return rc;
     }
+    mark(h, ("source_resblock" + sfx).c_str(), st);
     // three multi-receptive-field resblocks, averaged
     for (int r = 0; r < 3; ++r) {
       const int R = i * 3 + r;
@@ -621,6 +649,7 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
       }
     }
     if (prof) VT_CUDA_OK(cudaEventRecord(h->ev_rb[i][1], st));
+    mark(h, ("resblocks" + sfx).c_str(), st);
   }
   // ---- conv_post( leaky_relu(x) ) with the default slope 0.01, then the spectral head
   {
@@ -638,8 +667,10 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
     }
     if (rc) return rc;
   }
+  mark(h, "conv_post", st);
   rc = launch_istft_head(w.post, P.d_mel_off, P.d_T, P.d_off[2], B, P.T_max, h->trim_fade, wav, st);
   if (rc) return rc;
+  mark(h, "istft_head", st);
   if (prof) VT_CUDA_OK(cudaEventRecord(h->ev_fwd[1], st));
   return VT_OK;
 }
@@ -673,6 +704,23 @@ int vt_hift_read_profile(vt_hift* h, double* total_ms, double* resblock_ms, doub
   return VT_OK;
 }
 
+
+int vt_hift_read_timeline(vt_hift* h, char* out, int capacity) {
+  VT_REQUIRE(h != nullptr && out && capacity > 0, "vt_hift_read_timeline: NULL argument");
+  VT_REQUIRE(h->profiling && h->have_forward && h->n_marks > 0, "vt_hift_read_timeline: profiling is off or no forward ran");
+  VT_CUDA_OK(cudaEventSynchronize(h->marks[h->n_marks - 1].second));
+  std::string txt;
+  for (size_t i = 1; i < h->n_marks; ++i) {
+    float ms = 0.f;
+    VT_CUDA_OK(cudaEventElapsedTime(&ms, h->marks[i - 1].second, h->marks[i].second));
+    char line[96];
+    snprintf(line, sizeof line, "%s=%.4f\n", h->marks[i].first.c_str(), ms);
+    txt += line;
+  }
+  VT_REQUIRE((int)txt.size() < capacity, "vt_hift_read_timeline: capacity %d too small (need %d)", capacity, (int)txt.size() + 1);
+  std::memcpy(out, txt.c_str(), txt.size() + 1);
+  return VT_OK;
+}
 
 int64_t vt_hift_read_tap(vt_hift* h, const char* tap, int seq, float* out, int64_t capacity, void* workspace,
                          void* stream_v) {

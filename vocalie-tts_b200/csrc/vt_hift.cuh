@@ -75,6 +75,7 @@ struct ConvArgs {
   int out_mul, out_shift, phase_c, dup_row2;
   const ConvTile* tiles;
   int n_tiles;
+  int dbg;              // debug: timing-ablation bits (VT_TC_DBG), 0 normally
   long long* trace;     // debug: per-tile role timestamps of CTA 0 (VT_TC_TRACE=<layer>), nullptr normally
 };
 

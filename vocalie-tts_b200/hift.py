@@ -207,6 +207,16 @@ class HiFTVocoder:
         check(self._lib.vt_hift_read_profile(self._h, C.byref(t), C.byref(r), C.byref(f), C.byref(n)), "vt_hift_read_profile")
         return {"total_ms": t.value, "resblock_ms": r.value, "resblock_flops": f.value, "resblock_launches": n.value}
 
+    def read_timeline(self) -> Dict[str, float]:
+        """Device milliseconds per section of the last forward (profiling must be on)."""
+        buf = C.create_string_buffer(4096)
+        check(self._lib.vt_hift_read_timeline(self._h, buf, len(buf)), "vt_hift_read_timeline")
+        out: Dict[str, float] = {}
+        for line in buf.value.decode().splitlines():
+            k, v = line.split("=")
+            out[k] = float(v)
+        return out
+
     def read_tap(self, name: str, seq: int, channels: int = 1):
         """Intermediate of the last forward as float32 ``[rows, channels]`` (parity tests)."""
         torch = _torch()
