@@ -136,6 +136,22 @@ def test_f0_predictor_matches_oracle(torch, weights, vocoders):
         assert H.snr_db(ref, wavs[b].cpu()) >= 60.0
 
 
+def test_f0_predictor_tensor_core_split_precision(torch, weights, vocoders):
+    """In the tensor-core modes the F0 trunk runs on tcgen05 with two-term fp16 operands (x = hi + lo,
+    three products): F0 feeds a phase integral over the whole chunk, so it keeps ~fp32 accuracy while the
+    rest of the vocoder runs on single fp16 operands.  Lengths cross the 256-row tile boundary."""
+    Ts = [300, 17, 256]
+    mels, _, pvs, nzs = _inputs(torch, Ts, seed=11)
+    voc = vocoders("unit", "fp16")
+    wavs = voc.inference(mels, phase_vec=pvs, noise=nzs)
+    W = H.fold_weight_norm(weights["unit"])
+    for b, T in enumerate(Ts):
+        want = H.f0_predictor(mels[b].unsqueeze(0), W)[0]
+        got = voc.read_tap("f0", b, 1).cpu().reshape(-1)
+        assert got.numel() == T and wavs[b].numel() == 480 * T
+        assert _rel_err(want, got) < 2e-5, (b, _rel_err(want, got))
+
+
 def test_internal_noise_mode_is_deterministic_and_bounded(torch, vocoders):
     Ts = [40, 21]
     mels, f0s, _, _ = _inputs(torch, Ts, seed=9)

@@ -57,6 +57,8 @@ struct Plan {
   Seg mel, pre, up[3], sd[3], lvl[3];
   Seg tc[3][2];                             // tensor-core tiles per level, [0]: 128 rows, [1]: 256 rows
   Seg tcu[3];                               // tensor-core tiles of the transposed convs (128 input steps)
+  Seg g_mel, g_melu, g_sd[3];               // 256-step tiles of the K-blocked kernel: gapped mel -> gapped mel,
+                                            // gapped mel -> ungapped mel, level-2 STFT rows -> level l
   std::vector<long long> h_off[3], h_offM;
   std::vector<int> h_mel_off;
   void* d_block = nullptr;
@@ -70,6 +72,9 @@ struct Workspace {
   void *A[3][4];                            // activation copies A0, A1, A2, Q per level
   void *Yact[3];                            // leaky_relu(stage output) operand copies (next ups / conv_post)
   void *xpre_act;                           // leaky_relu(conv_pre) operand copy, gapped mel-rate layout
+  void *mel_hi, *mel_lo;                    // fp16 split of the mel, gapped mel-rate layout, kMelOp channels
+  void *fx[2][2];                           // F0 trunk activations, fp16 split [ping-pong][hi, lo], gapped mel-rate layout
+  void *spec_op;                            // STFT operand rows (kSpecOp elements) for the tensor-core source_downs
   long long cap_rows[3], cap_rowsM;
   size_t bytes;
 };
@@ -115,8 +120,49 @@ int dev_upload(vt_hift* h, const void* src, size_t bytes, void** out) {
 }
 
 // conv weight [cout][cin][k] -> [k][cin_pad][cout_pad]
+// K-blocked tensor-core packing of a layer (vt_gemm_tc.cu).  `w` is [k][cin_pad][cout].
+//   GEMM_CONV  : one K block per (tap, 64-channel block) of an operand buffer with `op_ld` channels
+//   GEMM_SPLIT : the same three times - (x_hi, w_hi), (x_hi, w_lo), (x_lo, w_hi) - always fp16
+//   GEMM_IM2COL: strided conv over operand rows of `op_ld` elements: K blocks walk the k*op_ld contiguous run
+enum GemmMode { GEMM_NONE = 0, GEMM_CONV = 1, GEMM_SPLIT = 2, GEMM_IM2COL = 3 };
+
+int pack_gemm(vt_hift* h, ConvLayer& L, const std::vector<float>& w, int cin_real, int cin_pad, int mode, int op_ld) {
+  const int N = L.cout, k = L.k;
+  std::vector<KBlock> kbs;
+  std::vector<int> part;
+  std::vector<float> wkb;
+  auto add_block = [&](int src, int shift, int ch_off, int prt, auto&& weight_of /* (e, co) -> float */) {
+    kbs.push_back(KBlock{src, shift, ch_off, 0});
+    part.push_back(prt);
+    const size_t base = wkb.size();
+    wkb.resize(base + (size_t)64 * N);
+    for (int e = 0; e < 64; ++e)
+      for (int co = 0; co < N; ++co) wkb[base + (size_t)e * N + co] = weight_of(e, co);
+  };
+  if (mode == GEMM_IM2COL) {
+    const int K = k * op_ld;
+    for (int cb = 0; cb * 64 < K; ++cb)
+      add_block(0, -L.pad, cb * 64, 0, [&](int e, int co) {
+        const int q = cb * 64 + e, j = q / op_ld, ci = q - j * op_ld;
+        return (j < k && ci < cin_real) ? w[((size_t)j * cin_pad + ci) * N + co] : 0.0f;
+      });
+  } else {
+    const int terms = mode == GEMM_SPLIT ? 3 : 1;
+    for (int t = 0; t < terms; ++t)
+      for (int j = 0; j < k; ++j)
+        for (int cb = 0; cb * 64 < op_ld; ++cb)
+          add_block(t == 2 ? 1 : 0, j * L.dil - L.pad, cb * 64, t == 1 ? 1 : 0, [&](int e, int co) {
+            const int ci = cb * 64 + e;
+            return ci < cin_real ? w[((size_t)j * cin_pad + ci) * N + co] : 0.0f;
+          });
+  }
+  const int elem = mode == GEMM_SPLIT ? (int)ELEM_F16 : h->act_elem;
+  return pack_gemm_tc(L, kbs, part, wkb, N % 128 == 0 ? 128 : 64, elem, h->allocs);
+}
+
 int pack_conv(vt_hift* h, ConvLayer& L, const std::map<std::string, HostTensor>& tab, const std::string& name,
-              int cin, int cout, int k, int dil, int stride, int pad, int cin_pad, int cout_pad) {
+              int cin, int cout, int k, int dil, int stride, int pad, int cin_pad, int cout_pad,
+              int gemm_mode = GEMM_NONE, int op_ld = 0) {
   auto wi = tab.find(name + ".weight"), bi = tab.find(name + ".bias");
   VT_REQUIRE(wi != tab.end() && bi != tab.end(), "missing tensor %s.weight/.bias", name.c_str());
   const HostTensor& W = wi->second;
@@ -137,6 +183,7 @@ int pack_conv(vt_hift* h, ConvLayer& L, const std::map<std::string, HostTensor>&
   if (rc) return rc;
   rc = dev_upload(h, b.data(), b.size() * 4, (void**)&L.bias);
   if (rc) return rc;
+  if (h->use_tc && gemm_mode != GEMM_NONE) return pack_gemm(h, L, w, cin, cin_pad, gemm_mode, op_ld);
   if (h->use_tc && conv_tc_supported(L)) return pack_conv_tc(L, w, h->act_elem, h->allocs);
   return VT_OK;
 }
@@ -247,7 +294,10 @@ int build_plan(vt_hift* h, const int32_t* T, int B, cudaStream_t st) {
   add_tiles(tiles, P.tcu[2], B, P.h_off[1].data(), len[1].data(), P.h_off[2].data(), len[1].data(), 128);
   add_tiles(tiles, P.up[1], B, P.h_off[0].data(), len[0].data(), P.h_off[1].data(), len[0].data(), kTileQ);
   add_tiles(tiles, P.up[2], B, P.h_off[1].data(), len[1].data(), P.h_off[2].data(), len[1].data(), kTileQ);
+  add_tiles(tiles, P.g_mel, B, P.h_offM.data(), lenM.data(), P.h_offM.data(), lenM.data(), 256);
+  add_tiles(tiles, P.g_melu, B, P.h_offM.data(), lenM.data(), melrow.data(), lenM.data(), 256);
   for (int l = 0; l < 3; ++l) {
+    add_tiles(tiles, P.g_sd[l], B, P.h_off[2].data(), len[2].data(), P.h_off[l].data(), len[l].data(), 256);
     add_tiles(tiles, P.sd[l], B, P.h_off[2].data(), len[2].data(), P.h_off[l].data(), len[l].data(), kTileQ);
     add_tiles(tiles, P.lvl[l], B, P.h_off[l].data(), len[l].data(), P.h_off[l].data(), len[l].data(), kTileQ);
     add_tiles(tiles, P.tc[l][0], B, P.h_off[l].data(), len[l].data(), P.h_off[l].data(), len[l].data(), 128);
@@ -300,6 +350,10 @@ Workspace carve_ws(const vt_hift* h, int B, long long total_T, void* base) {
   w.cap_rowsM = total_T + (long long)B * kGap + kGap + 512;
   w.xpre = (float*)take((size_t)w.cap_rowsM * kBase * 4);
   w.xpre_act = take((size_t)w.cap_rowsM * kBase * es);
+  w.mel_hi = take((size_t)w.cap_rowsM * kMelOp * 2);
+  w.mel_lo = take((size_t)w.cap_rowsM * kMelOp * 2);
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 2; ++j) w.fx[i][j] = take((size_t)w.cap_rowsM * kF0Ch * 2);
   for (int l = 0; l < 3; ++l) {
     const long long cap = (long long)kLevelMul[l] * total_T + (long long)B * (kGap + 1) + kGap + 512;
     w.cap_rows[l] = cap;
@@ -314,6 +368,7 @@ Workspace carve_ws(const vt_hift* h, int B, long long total_T, void* base) {
   }
   w.spec = (float*)take((size_t)w.cap_rows[2] * kSpecCh * 4);
   w.post = (float*)take((size_t)w.cap_rows[2] * kSpecCh * 4);
+  w.spec_op = take((size_t)w.cap_rows[2] * kSpecOp * 2);
   w.bytes = off;
   return w;
 }
@@ -408,13 +463,13 @@ int vt_hift_create(const vt_tensor* tensors, int n_tensors, int operand_dtype, v
   int rc = VT_OK;
   auto fail = [&](int code) { vt_hift_destroy(h); return code; };
 #define TRY(expr) do { rc = (expr); if (rc) return fail(rc); } while (0)
-  TRY(pack_conv(h, h->conv_pre, tab, "conv_pre", kMel, kBase, 7, 1, 1, 3, kMel, kBase));
+  TRY(pack_conv(h, h->conv_pre, tab, "conv_pre", kMel, kBase, 7, 1, 1, 3, kMel, kBase, GEMM_SPLIT, kMelOp));
   for (int i = 0; i < 3; ++i) {
     const int cin = kBase >> i, cout = kBase >> (i + 1);
     TRY(pack_convT(h, h->ups[i], tab, "ups." + std::to_string(i), cin, cout, kUpKernels[i], kUpRates[i],
                    (kUpKernels[i] - kUpRates[i]) / 2));
     TRY(pack_conv(h, h->sdown[i], tab, "source_downs." + std::to_string(i), kNfft + 2, cout, kSdK[i], 1, kSdS[i],
-                  kSdP[i], kSpecCh, cout));
+                  kSdP[i], kSpecCh, cout, GEMM_IM2COL, kSpecOp));
     for (int j = 0; j < 3; ++j) {
       const std::string p = "source_resblocks." + std::to_string(i);
       const int k = kSrcRbKernels[i];
@@ -439,7 +494,7 @@ int vt_hift_create(const vt_tensor* tensors, int n_tensors, int operand_dtype, v
   TRY(pack_conv(h, h->conv_post, tab, "conv_post", kBase >> 3, kNfft + 2, 7, 1, 1, 3, kBase >> 3, kSpecCh));
   for (int i = 0; i < 5; ++i)
     TRY(pack_conv(h, h->f0c[i], tab, "f0_predictor.condnet." + std::to_string(2 * i), i == 0 ? kMel : kF0Ch, kF0Ch, 3, 1, 1, 1,
-                  i == 0 ? kMel : kF0Ch, kF0Ch));
+                  i == 0 ? kMel : kF0Ch, kF0Ch, GEMM_SPLIT, i == 0 ? kMelOp : kF0Ch));
   TRY(upload_vec(h, tab, "f0_predictor.classifier.weight", kF0Ch, &h->f0_w));
   TRY(upload_vec(h, tab, "f0_predictor.classifier.bias", 1, &h->f0_b));
   TRY(upload_vec(h, tab, "m_source.l_linear.weight", kHarm, &h->lin_w));
@@ -520,6 +575,16 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
       }
     k_zero_gaps<<<B + 1, 256, 0, st>>>(w.xpre_act, kBase * (int)elem_size(ae), P.d_offM, P.d_T, B, 1, 0, P.rowsM);
     VT_LAUNCHED();
+    // operands of the K-blocked layers: mel split, F0 trunk ping-pong, STFT rows
+    void* mbufs[6] = {w.mel_hi, w.mel_lo, w.fx[0][0], w.fx[0][1], w.fx[1][0], w.fx[1][1]};
+    for (int i = 0; i < (f0_in ? 2 : 6); ++i) {
+      k_zero_gaps<<<B + 1, 256, 0, st>>>(mbufs[i], (i < 2 ? kMelOp : kF0Ch) * 2, P.d_offM, P.d_T, B, 1, 0, P.rowsM);
+      VT_LAUNCHED();
+    }
+    k_zero_gaps<<<B + 1, 256, 0, st>>>(w.spec_op, kSpecOp * 2, P.d_off[2], P.d_T, B, kLevelMul[2], 1, P.rows[2]);
+    VT_LAUNCHED();
+    rc = launch_pack_mel(mel, P.d_mel_off, P.d_T, P.d_offM, B, total_T, w.mel_hi, w.mel_lo, st);
+    if (rc) return rc;
   }
 
   mark(h, "zero_gaps", st);
@@ -527,7 +592,24 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
   const float* f0 = f0_in;
   if (!f0) {
     float* bufs[2] = {w.f0a, w.f0b};
-    for (int i = 0; i < 5; ++i) {
+    for (int i = 0; i < 5 && h->use_tc; ++i) {
+      // tensor-core trunk on two-term fp16 operands (x = hi + lo): ~fp32 accuracy for the value that
+      // feeds the phase integral; the last layer writes fp32 ELU rows (ungapped) for the classifier head
+      ConvArgs a = base_args(h->f0c[i], P, i < 4 ? P.g_mel : P.g_melu);
+      a.in_act = i == 0 ? w.mel_hi : w.fx[(i - 1) & 1][0];
+      a.in_act2 = i == 0 ? w.mel_lo : w.fx[(i - 1) & 1][1];
+      a.in_ld = i == 0 ? kMelOp : kF0Ch;
+      if (i < 4) {
+        a.act[0] = {w.fx[i & 1][0], nullptr, ACT_ELU, 0.f};
+        a.act[1] = {w.fx[i & 1][1], nullptr, ACT_ELU, 0.f};
+      } else {
+        a.out = bufs[0];
+        a.act[0] = {nullptr, nullptr, ACT_ELU, 0.f};
+      }
+      rc = launch_gemm_tc(a, h->f0c[i], ae, st);
+      if (rc) return rc;
+    }
+    for (int i = 0; i < 5 && !h->use_tc; ++i) {
       ConvArgs a = base_args(h->f0c[i], P, P.mel);
       a.in = i == 0 ? mel : bufs[(i - 1) & 1];
       // the F0 trunk is fp32 end to end: its ELU output is the next conv's fp32 input
@@ -547,19 +629,22 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
   rc = launch_sine_source(f0, P.d_mel_off, P.d_T, B, total_T, phase_vec, noise, seed, h->lin_w, h->lin_b,
                           w.phase_base, w.s, st);
   if (rc) return rc;
-  rc = launch_stft(w.s, P.d_mel_off, P.d_T, P.d_off[2], B, total_T, w.spec, st);
+  rc = launch_stft(w.s, P.d_mel_off, P.d_T, P.d_off[2], B, total_T, w.spec, h->use_tc ? w.spec_op : nullptr, ae, st);
   if (rc) return rc;
   mark(h, "source_stft", st);
   // ---- conv_pre
   {
-    ConvArgs a = base_args(h->conv_pre, P, P.pre);
-    a.in = mel;
+    ConvArgs a = base_args(h->conv_pre, P, h->use_tc ? P.g_mel : P.pre);
     a.out = w.xpre;
     if (h->use_tc) {
+      a.in_act = w.mel_hi; a.in_act2 = w.mel_lo; a.in_ld = kMelOp;
       a.act[0] = {w.xpre_act, nullptr, ACT_LRELU, 0.1f};
       a.act_from_out = 1;
+      rc = launch_gemm_tc(a, h->conv_pre, ae, st);
+    } else {
+      a.in = mel;
+      rc = launch_conv_ref(a, ae, st);
     }
-    rc = launch_conv_ref(a, ae, st);
     if (rc) return rc;
   }
   mark(h, "conv_pre", st);
@@ -583,11 +668,16 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
     mark(h, ("ups" + sfx).c_str(), st);
     // source_downs[i](s_stft) -> S stream + Snake copy for the first source-resblock conv
     {
-      ConvArgs a = base_args(h->sdown[i], P, P.sd[i]);
-      a.in = w.spec;
+      ConvArgs a = base_args(h->sdown[i], P, h->use_tc ? P.g_sd[i] : P.sd[i]);
       a.out = w.S[i];
       a.act[0] = {w.A[i][1], h->src_a1[i][0], ACT_SNAKE, 0.f};
-      rc = launch_conv_ref(a, ae, st);
+      if (h->use_tc) {
+        a.in_act = w.spec_op; a.in_ld = kSpecOp;
+        rc = launch_gemm_tc(a, h->sdown[i], ae, st);
+      } else {
+        a.in = w.spec;
+        rc = launch_conv_ref(a, ae, st);
+      }
       if (rc) return rc;
     }
     mark(h, ("source_down" + sfx).c_str(), st);

@@ -30,6 +30,8 @@ constexpr int kSPF = 480;          // samples per mel frame
 constexpr int kNfft = 16;
 constexpr int kHop = 4;
 constexpr int kSpecCh = 32;        // 18 STFT / conv_post channels padded to 32 (zeros)
+constexpr int kSpecOp = 24;        // STFT operand rows of the tensor-core source_downs: 18 channels + 6 zeros (48 B)
+constexpr int kMelOp = 128;        // mel operand rows: 80 channels + 48 zeros
 constexpr int kTileQ = 64;         // output steps per tile of the CUDA-core conv kernel
 
 enum ActKind : int { ACT_NONE = 0, ACT_SNAKE = 1, ACT_LRELU = 2, ACT_ELU = 3 };
@@ -56,6 +58,7 @@ struct ActOut {
 struct ConvArgs {
   const float* in;      // fp32 input [rows][in_ld]  (CUDA-core path)
   const void* in_act;   // activation-typed input [rows][in_ld] (resblock convs)
+  const void* in_act2;  // second operand source of the K-blocked kernel (low term of a split operand)
   int in_ld;
   const float* w;       // [k][cin][cout] fp32
   const float* bias;    // [cout]
@@ -79,6 +82,14 @@ struct ConvArgs {
   long long* trace;     // debug: per-tile role timestamps of CTA 0 (VT_TC_TRACE=<layer>), nullptr normally
 };
 
+// One 64-element K block of the K-blocked tensor-core kernel (vt_gemm_tc.cu).
+struct __align__(16) KBlock {
+  int src;              // operand source buffer: 0 = in_act, 1 = in_act2
+  int row_shift;        // input row = in_row0 + q*stride + row_shift
+  int ch_off;           // element offset inside the input row (may run past in_ld: im2col of strided convs)
+  int reserved;
+};
+
 struct ConvLayer {
   std::string name;
   int cin = 0, cout = 0, k = 1, dil = 1, stride = 1, pad = 0;
@@ -86,10 +97,16 @@ struct ConvLayer {
   float* w = nullptr;               // device [k][cin][cout] fp32
   float* bias = nullptr;            // device [cout]
   void* w_tc = nullptr;             // device, tensor-core operand packing (vt_conv_tc.cu)
+  void* w_gemm = nullptr;           // device, K-blocked tensor-core packing (vt_gemm_tc.cu)
+  void* d_kb = nullptr;             // device KBlock table
+  int n_kb = 0, gemm_nt = 0, gemm_elem = 0;
   double flops_per_step = 0;        // algorithmic 2*MAC per output step of the ORIGINAL layer
 };
 
 int launch_conv_ref(const ConvArgs& a, int act_elem, cudaStream_t st);
+int pack_gemm_tc(ConvLayer& L, const std::vector<KBlock>& kbs, const std::vector<int>& part, const std::vector<float>& wkb,
+                 int NT, int elem, std::vector<void*>& allocs);
+int launch_gemm_tc(const ConvArgs& a, const ConvLayer& L, int act_elem, cudaStream_t st);
 
 // Source path (vt_source.cu)
 int launch_f0_head(const float* h, const float* w, const float* b, float* f0, long long rows, cudaStream_t st);
@@ -97,7 +114,10 @@ int launch_sine_source(const float* f0, const int* mel_off, const int* T, int B,
                        const float* phase_vec, const float* noise, unsigned long long seed,
                        const float* lin_w, const float* lin_b, double* phase_base, float* s, cudaStream_t st);
 int launch_stft(const float* s, const int* mel_off, const int* T, const long long* off2, int B, long long total_T,
-                float* spec, cudaStream_t st);
+                float* spec, void* spec_op, int op_elem, cudaStream_t st);
+// mel fp32 [total_T][80] -> two fp16 terms [gapped rows][128] (hi, lo), channels 80..127 zero
+int launch_pack_mel(const float* mel, const int* mel_off, const int* T, const long long* offM, int B, long long total_T,
+                    void* mel_hi, void* mel_lo, cudaStream_t st);
 // Spectral head (vt_head.cu): conv_post output -> exp/sin -> iSTFT -> clamp -> trim_fade
 int launch_istft_head(const float* post, const int* mel_off, const int* T, const long long* off2, int B,
                       int T_max, const float* trim_fade, float* wav, cudaStream_t st);

@@ -165,9 +165,22 @@ int launch_sine_source(const float* f0, const int* mel_off, const int* T, int B,
 // One thread per frame: 16 windowed samples -> 9 real + 9 imaginary bins, written channel-last
 // into the level-2 packed layout (row off2[b] + frame, 32 channels, 18..31 zero).
 
+template <typename OpT>
+__device__ __forceinline__ unsigned pack2_op(float a, float b);
+template <> __device__ __forceinline__ unsigned pack2_op<__half>(float a, float b) {
+  const __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const unsigned*>(&v);
+}
+template <> __device__ __forceinline__ unsigned pack2_op<__nv_bfloat16>(float a, float b) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const unsigned*>(&v);
+}
+
+// `spec_op` (tensor-core modes): the same 18 channels as operand-typed rows of kSpecOp = 24 elements.
+template <typename OpT>
 __global__ void __launch_bounds__(256)
 k_stft(const float* __restrict__ s, const int* __restrict__ mel_off, const int* __restrict__ T,
-       const long long* __restrict__ off2, int B, float* __restrict__ spec) {
+       const long long* __restrict__ off2, int B, float* __restrict__ spec, OpT* __restrict__ spec_op) {
   const int b = blockIdx.y;
   const long long L = (long long)T[b] * kSPF;
   const long long frames = L / kHop + 1;
@@ -200,15 +213,56 @@ k_stft(const float* __restrict__ s, const int* __restrict__ mel_off, const int* 
 #pragma unroll
     for (int c = 0; c < kSpecCh; c += 4)
       *reinterpret_cast<float4*>(dst + c) = make_float4(outv[c], outv[c + 1], outv[c + 2], outv[c + 3]);
+    if (spec_op) {
+      uint4* od = reinterpret_cast<uint4*>(spec_op + (off2[b] + f) * kSpecOp);
+#pragma unroll
+      for (int c = 0; c < kSpecOp; c += 8)
+        od[c / 8] = make_uint4(pack2_op<OpT>(outv[c], outv[c + 1]), pack2_op<OpT>(outv[c + 2], outv[c + 3]),
+                               pack2_op<OpT>(outv[c + 4], outv[c + 5]), pack2_op<OpT>(outv[c + 6], outv[c + 7]));
+    }
   }
 }
 
 int launch_stft(const float* s, const int* mel_off, const int* T, const long long* off2, int B, long long total_T,
-                float* spec, cudaStream_t st) {
+                float* spec, void* spec_op, int op_elem, cudaStream_t st) {
   if (B == 0 || total_T == 0) return VT_OK;
   int gx = (148 * 8 + B - 1) / B;
   dim3 grid(gx < 1 ? 1 : gx, B);
-  k_stft<<<grid, 256, 0, st>>>(s, mel_off, T, off2, B, spec);
+  if (spec_op && op_elem == ELEM_BF16)
+    k_stft<__nv_bfloat16><<<grid, 256, 0, st>>>(s, mel_off, T, off2, B, spec, reinterpret_cast<__nv_bfloat16*>(spec_op));
+  else
+    k_stft<__half><<<grid, 256, 0, st>>>(s, mel_off, T, off2, B, spec, reinterpret_cast<__half*>(spec_op));
+  VT_LAUNCHED();
+  return VT_OK;
+}
+
+// ---- mel operand pack: fp32 [total_T][80] -> fp16 hi / lo terms in the gapped mel-rate layout ----------
+__global__ void __launch_bounds__(256)
+k_pack_mel(const float* __restrict__ mel, const int* __restrict__ mel_off, const int* __restrict__ T,
+           const long long* __restrict__ offM, int B, __half* __restrict__ hi, __half* __restrict__ lo) {
+  const int b = blockIdx.y;
+  const long long n = (long long)T[b] * (kMelOp / 4);
+  const float* src = mel + (long long)mel_off[b] * kMel;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long t = i / (kMelOp / 4);
+    const int c = (int)(i - t * (kMelOp / 4)) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < kMel) v = *reinterpret_cast<const float4*>(src + t * kMel + c);
+    const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+    const __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
+    const long long o = (offM[b] + t) * kMelOp + c;
+    *reinterpret_cast<uint2*>(hi + o) = make_uint2(*reinterpret_cast<const unsigned*>(&h0), *reinterpret_cast<const unsigned*>(&h1));
+    *reinterpret_cast<uint2*>(lo + o) = make_uint2(*reinterpret_cast<const unsigned*>(&l0), *reinterpret_cast<const unsigned*>(&l1));
+  }
+}
+
+int launch_pack_mel(const float* mel, const int* mel_off, const int* T, const long long* offM, int B, long long total_T,
+                    void* mel_hi, void* mel_lo, cudaStream_t st) {
+  if (B == 0 || total_T == 0) return VT_OK;
+  int gx = (148 * 4 + B - 1) / B;
+  dim3 grid(gx < 1 ? 1 : gx, B);
+  k_pack_mel<<<grid, 256, 0, st>>>(mel, mel_off, T, offM, B, reinterpret_cast<__half*>(mel_hi), reinterpret_cast<__half*>(mel_lo));
   VT_LAUNCHED();
   return VT_OK;
 }
