@@ -200,6 +200,8 @@ int launch_gemm_nt(const ConvArgs& a, const ConvLayer& L, uint32_t idesc, int gr
     return launch_gemm_em<NT, 2, 4, 4, EM_OUT | EM_OACT, ActT>(a, L, idesc, grid, st);
   if (a.out && a.act[0].dst && a.act[0].kind == ACT_SNAKE && !a.act[1].dst)
     return launch_gemm_em<NT, 2, 4, 4, EM_OUT | EM_ACT1, ActT>(a, L, idesc, grid, st);
+  if (a.out && !a.act[0].dst && a.act[0].kind == ACT_NONE && !a.act[1].dst)
+    return launch_gemm_em<NT, 2, 4, 4, EM_OUT, ActT>(a, L, idesc, grid, st);
   VT_REQUIRE(false, "gemm_tc: no compiled epilogue for layer %s", L.name.c_str());
   return VT_OK;
 }

@@ -16,6 +16,10 @@ int launch_conv_tc(const ConvArgs& a, const ConvLayer& L, int act_elem, const vo
 int pack_conv_tc(ConvLayer& L, const std::vector<float>& w_kcico, int act_elem, std::vector<void*>& allocs);
 bool conv_tc_supported(const ConvLayer& L);
 int conv_tc_tile_rows(const ConvLayer& L);
+bool pair_tc_supported(const ConvLayer& c1, const ConvLayer& c2);
+int pair_tc_tile_rows(int k);
+int launch_pair_tc(const ConvArgs& a, const ConvLayer& c1, const ConvLayer& c2, const float* alpha1, const float* alpha2,
+                   int act_elem, cudaStream_t st);
 
 namespace {
 
@@ -57,6 +61,7 @@ struct Plan {
   Seg mel, pre, up[3], sd[3], lvl[3];
   Seg tc[3][2];                             // tensor-core tiles per level, [0]: 128 rows, [1]: 256 rows
   Seg tcu[3];                               // tensor-core tiles of the transposed convs (128 input steps)
+  Seg pair[3][3];                           // fused ResBlock-pair tiles per level and kernel size 3 / 7 / 11
   Seg g_mel, g_melu, g_sd[3];               // 256-step tiles of the K-blocked kernel: gapped mel -> gapped mel,
                                             // gapped mel -> ungapped mel, level-2 STFT rows -> level l
   std::vector<long long> h_off[3], h_offM;
@@ -69,6 +74,7 @@ struct Workspace {
   float *f0a, *f0b, *f0, *s, *spec, *xpre, *post;
   double* phase_base;
   float *U[3], *S[3], *X[3], *XR[3], *Y[3];
+  float *S2[3], *XR2[3];                    // ping-pong partners of S / XR for the fused pairs (no in-place update)
   void *A[3][4];                            // activation copies A0, A1, A2, Q per level
   void *Yact[3];                            // leaky_relu(stage output) operand copies (next ups / conv_post)
   void *xpre_act;                           // leaky_relu(conv_pre) operand copy, gapped mel-rate layout
@@ -92,6 +98,7 @@ struct vt_hift {
   float *f0_w = nullptr, *f0_b = nullptr, *lin_w = nullptr, *lin_b = nullptr, *trim_fade = nullptr;
   Plan plan;
   Workspace ws{};
+  bool fuse[3] = {false, false, false};     // level runs its ResBlock pairs on the fused kernel (vt_pair_tc.cu)
   bool have_forward = false;
   // profiling (vt_hift_set_profiling): events around the whole forward and around each stage's
   // run of resblock convolutions (the dominant kernel class)
@@ -302,6 +309,9 @@ int build_plan(vt_hift* h, const int32_t* T, int B, cudaStream_t st) {
     add_tiles(tiles, P.lvl[l], B, P.h_off[l].data(), len[l].data(), P.h_off[l].data(), len[l].data(), kTileQ);
     add_tiles(tiles, P.tc[l][0], B, P.h_off[l].data(), len[l].data(), P.h_off[l].data(), len[l].data(), 128);
     add_tiles(tiles, P.tc[l][1], B, P.h_off[l].data(), len[l].data(), P.h_off[l].data(), len[l].data(), 256);
+    for (int kk = 0; kk < 3; ++kk)
+      add_tiles(tiles, P.pair[l][kk], B, P.h_off[l].data(), len[l].data(), P.h_off[l].data(), len[l].data(),
+                pair_tc_tile_rows(kRbKernels[kk]));
   }
   // one device block: T | mel_off | off[3] | tiles
   const size_t nI = align_up((size_t)B * 4, 256), nL = align_up((size_t)B * 8, 256);
@@ -363,6 +373,8 @@ Workspace carve_ws(const vt_hift* h, int B, long long total_T, void* base) {
     w.X[l] = (float*)take((size_t)cap * C * 4);
     w.XR[l] = (float*)take((size_t)cap * C * 4);
     w.Y[l] = (float*)take((size_t)cap * C * 4);
+    w.S2[l] = (float*)take((size_t)cap * C * 4);
+    w.XR2[l] = (float*)take((size_t)cap * C * 4);
     for (int i = 0; i < 4; ++i) w.A[l][i] = take((size_t)cap * C * es);
     w.Yact[l] = take((size_t)cap * C * es);
   }
@@ -491,6 +503,15 @@ int vt_hift_create(const vt_tensor* tensors, int n_tensors, int operand_dtype, v
       }
     }
   }
+  for (int i = 0; i < 3 && h->use_tc; ++i) {
+    const char* nf = getenv("VT_NO_FUSE");
+    bool ok = !(nf && nf[0] == '1');
+    for (int j = 0; j < 3 && ok; ++j) {
+      ok = ok && pair_tc_supported(h->src_c1[i][j], h->src_c2[i][j]);
+      for (int kk = 0; kk < 3; ++kk) ok = ok && pair_tc_supported(h->rb_c1[i * 3 + kk][j], h->rb_c2[i * 3 + kk][j]);
+    }
+    h->fuse[i] = ok;
+  }
   TRY(pack_conv(h, h->conv_post, tab, "conv_post", kBase >> 3, kNfft + 2, 7, 1, 1, 3, kBase >> 3, kSpecCh));
   for (int i = 0; i < 5; ++i)
     TRY(pack_conv(h, h->f0c[i], tab, "f0_predictor.condnet." + std::to_string(2 * i), i == 0 ? kMel : kF0Ch, kF0Ch, 3, 1, 1, 1,
@@ -575,6 +596,15 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
       }
     k_zero_gaps<<<B + 1, 256, 0, st>>>(w.xpre_act, kBase * (int)elem_size(ae), P.d_offM, P.d_T, B, 1, 0, P.rowsM);
     VT_LAUNCHED();
+    // fused pairs read the fp32 streams with their halo: the gap rows of those buffers must be zero
+    for (int l = 0; l < 3; ++l) {
+      if (!h->fuse[l]) continue;
+      float* fb[5] = {w.S[l], w.S2[l], w.X[l], w.XR[l], w.XR2[l]};
+      for (int i = 0; i < 5; ++i) {
+        k_zero_gaps<<<B + 1, 256, 0, st>>>(fb[i], (kBase >> (l + 1)) * 4, P.d_off[l], P.d_T, B, kLevelMul[l], l == 2 ? 1 : 0, P.rows[l]);
+        VT_LAUNCHED();
+      }
+    }
     // operands of the K-blocked layers: mel split, F0 trunk ping-pong, STFT rows
     void* mbufs[6] = {w.mel_hi, w.mel_lo, w.fx[0][0], w.fx[0][1], w.fx[1][0], w.fx[1][1]};
     for (int i = 0; i < (f0_in ? 2 : 6); ++i) {
@@ -670,7 +700,7 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
     {
       ConvArgs a = base_args(h->sdown[i], P, h->use_tc ? P.g_sd[i] : P.sd[i]);
       a.out = w.S[i];
-      a.act[0] = {w.A[i][1], h->src_a1[i][0], ACT_SNAKE, 0.f};
+      if (!h->fuse[i]) a.act[0] = {w.A[i][1], h->src_a1[i][0], ACT_SNAKE, 0.f};
       if (h->use_tc) {
         a.in_act = w.spec_op; a.in_ld = kSpecOp;
         rc = launch_gemm_tc(a, h->sdown[i], ae, st);
@@ -689,7 +719,41 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
       h->rb_flops += steps * 2.0 * c * c * 6.0 * (kSrcRbKernels[i] + kRbKernels[0] + kRbKernels[1] + kRbKernels[2]);
       h->rb_launches += 24;
     }
-    for (int j = 0; j < 3; ++j) {
+    if (h->fuse[i]) {
+      // fused pairs: fp32 stream in, fp32 stream out, no operand copies in HBM
+      float* sbuf[2] = {w.S[i], w.S2[i]};
+      const int ksrc = kSrcRbKernels[i] == 3 ? 0 : (kSrcRbKernels[i] == 7 ? 1 : 2);
+      for (int j = 0; j < 3; ++j) {
+        ConvArgs c = base_args(h->src_c2[i][j], P, P.pair[i][ksrc]);
+        c.res1 = sbuf[j & 1];
+        if (j < 2) c.out = sbuf[(j + 1) & 1];
+        else { c.res2 = w.U[i]; c.out = w.X[i]; }
+        rc = launch_pair_tc(c, h->src_c1[i][j], h->src_c2[i][j], h->src_a1[i][j], h->src_a2[i][j], ae, st);
+        if (rc) return rc;
+      }
+      mark(h, ("source_resblock" + sfx).c_str(), st);
+      for (int r = 0; r < 3; ++r) {
+        const int R = i * 3 + r;
+        float* xin[3] = {w.X[i], w.XR[i], w.XR2[i]};
+        for (int j = 0; j < 3; ++j) {
+          ConvArgs c = base_args(h->rb_c2[R][j], P, P.pair[i][r]);
+          c.res1 = xin[j];
+          if (j < 2) c.out = xin[j + 1];
+          else {
+            c.out = w.Y[i];
+            c.out_accum = r > 0;
+            c.out_scale = 1.0f / 3.0f;
+            if (r == 2) {
+              c.act[0] = {w.Yact[i], nullptr, ACT_LRELU, i < 2 ? 0.1f : 0.01f};
+              c.act_from_out = 1;
+            }
+          }
+          rc = launch_pair_tc(c, h->rb_c1[R][j], h->rb_c2[R][j], h->rb_a1[R][j], h->rb_a2[R][j], ae, st);
+          if (rc) return rc;
+        }
+      }
+    }
+    for (int j = 0; j < 3 && !h->fuse[i]; ++j) {
       ConvArgs a = base_args(h->src_c1[i][j], P, P.lvl[i]);
       a.in_act = w.A[i][1];
       a.act[0] = {w.A[i][3], h->src_a2[i][j], ACT_SNAKE, 0.f};
@@ -709,9 +773,9 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
       rc = run_conv(h, c, h->src_c2[i][j], i, st);
       if (rc) return rc;
     }
-    mark(h, ("source_resblock" + sfx).c_str(), st);
+    if (!h->fuse[i]) mark(h, ("source_resblock" + sfx).c_str(), st);
     // three multi-receptive-field resblocks, averaged
-    for (int r = 0; r < 3; ++r) {
+    for (int r = 0; r < 3 && !h->fuse[i]; ++r) {
       const int R = i * 3 + r;
       for (int j = 0; j < 3; ++j) {
         ConvArgs a = base_args(h->rb_c1[R][j], P, P.lvl[i]);

@@ -1,0 +1,577 @@
+// Fused ResBlock pair on tcgen05:  x_out = conv2(Snake2(conv1(Snake1(x)))) + x  in ONE kernel
+// (upstream hifigan.py ResBlock.forward, one iteration of its dilation loop).
+//
+// Why: run as two launches the pair moves 1 KB of HBM per time step at C = 64 (operand copy in and
+// out of conv1, operand copy + fp32 residual in and fp32 stream + operand copy out of conv2) for
+// 2*C*C*k*2 FLOP - below the B200 ridge (210 FLOP/B) for every kernel size at C = 64.  Fused, the only
+// HBM traffic of a pair is the fp32 residual stream read once and written once (512 B per step at C = 64).
+//
+// Per CTA tile (256 conv1 rows = 256 - (k-1) output steps):
+//   producers (4 warps)  x fp32 [256 + (k-1)*dil rows] --Snake1--> fp16 A1 tile in shared memory (SWIZZLE_128B)
+//   MMA warp   conv1     A1 (taps = row-shifted descriptors) x W1 (bulk-TMA ring)      -> D1 in TMEM
+//   mid warps            D1 + b1 --Snake2--> fp16 A2 tile in shared memory; rows outside the sequence -> 0
+//   MMA warp   conv2     A2 x W2                                                        -> D2 in TMEM
+//   fin warps  (4)       D2 + b2 + x (+ second residual) -> fp32 stream / 1/3-mean accumulate / leaky-ReLU copy
+// With NBUF = 2 (C = 64) every buffer (A1, A2, D1, D2) is double buffered and the MMA warp issues
+// conv1(i+1) before conv2(i), so the tensor pipe never waits for the mid epilogue; with NBUF = 1
+// (C = 128, TMEM and shared memory are full) conv2(i) waits for mid(i) while producers and the fin
+// epilogue still overlap.
+#include "vt_tc.cuh"
+
+#include <cstdlib>
+
+namespace vt {
+
+struct PairArgs {
+  const float* x_in;      // fp32 residual stream [rows][C]; gap rows are zero
+  const float* alpha1;    // Snake before conv1
+  const float* alpha2;    // Snake before conv2
+  const float* bias1;     // conv1 bias
+  const uint8_t* w1;      // conv1 / conv2 weights, pack_conv_tc images (chunk = (tap, 64-channel block))
+  const uint8_t* w2;
+  int k, dil;
+};
+
+namespace tc {
+
+constexpr int kPairRA1 = 312;   // A1 rows: 256 + (k-1)*dil <= 306, multiple of 8
+constexpr int kPairRA2 = 272;   // A2 rows: 256 + (k-1) <= 266, multiple of 8
+
+__device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]),
+      "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]),
+      "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// Warp roles: [0, NEPI) fin epilogue; then (NBUF == 2) NEPI mid-epilogue warps, or (NBUF == 1, "combined") the
+// fin warps also run the mid epilogue - conv2(i) waits for mid(i) anyway, and the fin staging can then live in
+// the A2 tile, which is idle between conv2(i) and mid(i+1); then the MMA warp, the weight producer, NPROD
+// activation-producer warps.
+template <int C, int NBUF, int NEPI, int NPROD>
+struct PairCfg {
+  static constexpr bool kCombined = NBUF == 1;
+  static constexpr int W_MID = kCombined ? 0 : NEPI;
+  static constexpr int W_MMA = kCombined ? NEPI : 2 * NEPI;
+  static constexpr int WARPS = W_MMA + 2 + NPROD;
+};
+
+template <int C, int NBUF, int W_ST, int NEPI, int NPROD, int EM, typename ActT>
+__global__ void __launch_bounds__(PairCfg<C, NBUF, NEPI, NPROD>::WARPS * 32, 1)
+k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
+  using PC = PairCfg<C, NBUF, NEPI, NPROD>;
+  constexpr bool kCombined = PC::kCombined;
+  constexpr int NMID = NEPI, kFin = NEPI, kProdT = NPROD * 32;
+  static_assert(kSwz, "the fused pair kernel assumes the SWIZZLE_128B operand layout");
+  constexpr int CB = C / 64;
+  constexpr int A1_BYTES = CB * kPairRA1 * 128, A2_BYTES = CB * kPairRA2 * 128, W_BYTES = C * 128;
+  constexpr int ACC_COLS = 2 * C;                        // two 128-row M blocks
+  constexpr int SKEW = NBUF - 1;
+  constexpr int W_MID = PC::W_MID, W_MMA = PC::W_MMA, W_WP = W_MMA + 1, W_AP = W_MMA + 2;
+  static_assert(4 * C * NBUF <= 512 && NEPI % 4 == 0 && kProdT % (C / 8) == 0, "bad configuration");
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA1 = smem;
+  uint8_t* sA2 = sA1 + NBUF * A1_BYTES;
+  uint8_t* sW = sA2 + NBUF * A2_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + W_ST * W_BYTES);
+  uint64_t* a1_full = bars;
+  uint64_t* a1_empty = a1_full + NBUF;
+  uint64_t* a2_full = a1_empty + NBUF;
+  uint64_t* a2_empty = a2_full + NBUF;
+  uint64_t* d1_full = a2_empty + NBUF;
+  uint64_t* d1_empty = d1_full + NBUF;
+  uint64_t* d2_full = d1_empty + NBUF;
+  uint64_t* d2i_full = d2_full + NBUF;   // D2 free AND preloaded with the residual terms
+  uint64_t* w_full = d2i_full + NBUF;
+  uint64_t* w_empty = w_full + W_ST;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_empty + W_ST);
+  float* prm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(tmem_slot) + 16);   // al1 | ia1 | b1 | al2 | ia2
+  // fin staging (32 x kStageLd floats per warp): its own region, or the idle A2 tile in combined mode
+  float* stage_all = kCombined ? reinterpret_cast<float*>(sA2) : prm + 5 * C;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NBUF; ++i) {
+      mbar_init(&a1_full[i], kProdT); mbar_init(&a1_empty[i], 1);
+      mbar_init(&a2_full[i], NMID * 32); mbar_init(&a2_empty[i], 1);
+      mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], NMID * 32);
+      mbar_init(&d2_full[i], 1); mbar_init(&d2i_full[i], kFin * 32);
+    }
+    for (int i = 0; i < W_ST; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    fence_barrier_init();
+  }
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float a1 = p.alpha1[c], a2 = p.alpha2[c];
+    prm[c] = a1; prm[C + c] = __fdividef(1.0f, a1 + 1e-9f); prm[2 * C + c] = p.bias1[c];
+    prm[3 * C + c] = a2; prm[4 * C + c] = __fdividef(1.0f, a2 + 1e-9f);
+  }
+  if (warp == W_MMA) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_tiles = a.n_tiles;
+  const int n_my = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int H2 = (p.k - 1) / 2, H1 = (p.k - 1) * p.dil / 2;
+  const int nchunks = p.k * CB;
+
+  if (warp >= W_AP) {
+    // ---------------- producers: fp32 stream rows -> Snake1 -> fp16 A1 tile.  One task = one 16-byte operand
+    // chunk (8 channels) of one row; a thread keeps the same 8 channels for every task (128 % (C/8) == 0).
+    constexpr int CPR = C / 8, RSTEP = kProdT / CPR, U = 4;
+    const int pt = threadIdx.x - W_AP * 32;
+    const int ch = pt % CPR, r_first = pt / CPR;
+    float al[8], ia[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { al[e] = prm[ch * 8 + e]; ia[e] = prm[C + ch * 8 + e]; }
+    const int R1 = 256 + 2 * H1;
+    const uint32_t col_off = (uint32_t)(ch >> 3) * (uint32_t)(kPairRA1 * 128);
+    // Rolling prefetch: inside a tile every register slot q re-issues its next row's 32-byte load right after it
+    // is consumed; the first round of the NEXT tile is issued after this tile's arrive (the proxy fence before the
+    // arrive is a full membar - it must not find global loads in flight) and flies during the a1_empty wait.
+    auto tile_src = [&](int i) {
+      const ConvTile tl = a.tiles[blockIdx.x + i * gridDim.x];
+      return p.x_in + (tl.in_row0 + tl.q0 - H1 - H2) * (long long)C + ch * 8;
+    };
+    float4 lo[U], hi[U];
+    const bool loads_on = !(a.dbg & 2);
+    auto first_round = [&](const float* src) {
+#pragma unroll
+      for (int q = 0; q < U; ++q) {
+        const int r = r_first + q * RSTEP;
+        lo[q] = hi[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < R1 && loads_on) { lo[q] = ldg_f4(src + (long long)r * C); hi[q] = ldg_f4(src + (long long)r * C + 4); }
+      }
+    };
+    const float* src = n_my > 0 ? tile_src(0) : p.x_in;
+    if (n_my > 0) first_round(src);
+    for (int i = 0; i < n_my; ++i) {
+      const int b = i % NBUF;
+      const uint32_t u = (uint32_t)(i / NBUF);
+      mbar_wait(&a1_empty[b], (u & 1u) ^ 1u);
+      if (pt == 0) trace_ev(a.trace, i, 0);
+      const uint32_t dst = smem_u32(sA1 + b * A1_BYTES) + col_off;
+      for (int r0 = r_first; r0 < R1; r0 += RSTEP * U) {
+#pragma unroll
+        for (int q = 0; q < U; ++q) {
+          const int r = r0 + q * RSTEP;
+          if (r < R1) {
+            float y[8];
+            y[0] = snake_f(lo[q].x, al[0], ia[0]); y[1] = snake_f(lo[q].y, al[1], ia[1]);
+            y[2] = snake_f(lo[q].z, al[2], ia[2]); y[3] = snake_f(lo[q].w, al[3], ia[3]);
+            y[4] = snake_f(hi[q].x, al[4], ia[4]); y[5] = snake_f(hi[q].y, al[5], ia[5]);
+            y[6] = snake_f(hi[q].z, al[6], ia[6]); y[7] = snake_f(hi[q].w, al[7], ia[7]);
+            const uint4 pk = Pack8<ActT>::pack(y);
+            const uint32_t addr = dst + (uint32_t)r * 128u + (uint32_t)(((ch & 7) ^ (r & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk.x), "r"(pk.y), "r"(pk.z), "r"(pk.w) : "memory");
+            const int rn = r + RSTEP * U;
+            if (rn < R1 && loads_on) { lo[q] = ldg_f4(src + (long long)rn * C); hi[q] = ldg_f4(src + (long long)rn * C + 4); }
+          }
+        }
+      }
+      fence_proxy_async();
+      if (pt == 0) trace_ev(a.trace, i, 1);
+      mbar_arrive(&a1_full[b]);
+      if (i + 1 < n_my) {
+        src = tile_src(i + 1);
+        first_round(src);
+      }
+    }
+  } else if (warp == W_WP) {
+    // ---------------- weight producer: the chunk order mirrors the MMA issue order
+    if (lane == 0) {
+      uint32_t ws = 0, ph = 0;
+      for (int s = 0; s < n_my + SKEW; ++s)
+        for (int pass = 0; pass < 2; ++pass) {
+          if (pass == 0 ? s >= n_my : s < SKEW) continue;
+          const uint8_t* wsrc = pass == 0 ? p.w1 : p.w2;
+          for (int c = 0; c < nchunks; ++c) {
+            mbar_wait(&w_empty[ws], ph ^ 1u);
+            if (a.dbg & 1) mbar_arrive(&w_full[ws]);
+            else {
+              mbar_arrive_expect_tx(&w_full[ws], W_BYTES);
+              bulk_g2s(sW + ws * W_BYTES, wsrc + (size_t)c * W_BYTES, W_BYTES, &w_full[ws]);
+            }
+            if (++ws == (uint32_t)W_ST) { ws = 0; ph ^= 1u; }
+          }
+        }
+    }
+  } else if (warp == W_MMA) {
+    // ---------------- MMA issuer: conv1(s) then conv2(s - SKEW)
+    constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t a1_lo0 = ((smem_u32(sA1) >> 4) & 0x3FFFu) | (1u << 16);
+    const uint32_t a2_lo0 = ((smem_u32(sA2) >> 4) & 0x3FFFu) | (1u << 16);
+    const uint32_t w_lo0 = ((smem_u32(sW) >> 4) & 0x3FFFu) | (1u << 16);
+    const bool mma_on = !(a.dbg & 16);
+    uint32_t ws = 0, wph = 0;
+    for (int s = 0; s < n_my + SKEW; ++s)
+      for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 0 ? s >= n_my : s < SKEW) continue;
+        const int i = pass == 0 ? s : s - SKEW;
+        const int b = i % NBUF;
+        const uint32_t u = (uint32_t)(i / NBUF);
+        uint64_t* src_full = pass == 0 ? &a1_full[b] : &a2_full[b];
+        uint64_t* src_empty = pass == 0 ? &a1_empty[b] : &a2_empty[b];
+        uint64_t* dst_full = pass == 0 ? &d1_full[b] : &d2_full[b];
+        // conv1 needs D1 drained by the mid epilogue; conv2 needs D2 preloaded by the fin warps (x + b2 + ...)
+        if (pass == 0) mbar_wait(&d1_empty[b], (u & 1u) ^ 1u);
+        else mbar_wait(&d2i_full[b], u & 1u);
+        mbar_wait(src_full, u & 1u);
+        tc_fence_after();
+        if (lane == 0) trace_ev(a.trace, i, 6 + 2 * pass);
+        const uint32_t d0 = tmem_base + (uint32_t)((pass * NBUF + b) * ACC_COLS);
+        const uint32_t a_tile = pass == 0 ? a1_lo0 + (uint32_t)b * (uint32_t)(A1_BYTES >> 4) : a2_lo0 + (uint32_t)b * (uint32_t)(A2_BYTES >> 4);
+        const uint32_t blk16 = (uint32_t)(pass == 0 ? kPairRA1 : kPairRA2) * 8u;   // 64-channel block stride, 16-byte units
+        const uint32_t tap16 = (uint32_t)(pass == 0 ? p.dil : 1) * 8u;              // one tap = dil rows of 128 B
+        uint32_t acc = pass == 0 ? 0u : 1u;
+        for (int j = 0; j < p.k; ++j) {
+          uint32_t a_chunk = a_tile + (uint32_t)j * tap16;
+#pragma unroll 1
+          for (int cb = 0; cb < CB; ++cb, a_chunk += blk16) {
+            mbar_wait(&w_full[ws], wph);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t b_lo = w_lo0 + ws * (uint32_t)(W_BYTES >> 4);
+              if (mma_on) {
+#pragma unroll
+                for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks)
+                    umma_f16_lh(d0 + (uint32_t)(mb * C), a_chunk + (uint32_t)(mb * 1024 + ks * 2), b_lo + (uint32_t)(ks * 2), kDescHi,
+                                idesc, ks == 0 ? acc : 1u);
+              }
+              umma_commit(&w_empty[ws]);
+            }
+            __syncwarp();
+            acc = 1u;
+            if (++ws == (uint32_t)W_ST) { ws = 0; wph ^= 1u; }
+          }
+        }
+        if (elect_one()) {
+          umma_commit(src_empty);
+          umma_commit(dst_full);
+        }
+        __syncwarp();
+        if (lane == 0) trace_ev(a.trace, i, 7 + 2 * pass);
+      }
+  } else {
+    // ---------------- epilogue warps.  mid: D1 + b1 -> Snake2 -> fp16 A2 rows (zero outside the sequence);
+    // fin: D2 -> fp32 stream, then the residual terms of the tile that uses D2 next are preloaded into it.
+    const bool do_mid = kCombined || warp >= W_MID;
+    const bool do_fin = kCombined || warp < W_MID;
+    const int ew = kCombined ? warp : (warp >= W_MID ? warp - W_MID : warp);   // index inside the role group
+    const int quarter = warp & 3, grp = ew >> 2;
+    constexpr int NBLK = 2 * (C / 32);
+    float* stage = stage_all + ew * (32 * kStageLd);
+    // ---- fin helpers.  A block = 32 rows (this warp's TMEM lanes of one M block) x 32 columns.  Global memory
+    // is touched as 4 rows x 128 contiguous bytes per instruction (lane -> (rsub, sub)); TMEM wants lane = row;
+    // the shared-memory stage transposes between the two in both directions.
+    const int sub = lane & 7, rsub = lane >> 3;
+    constexpr bool kRes2 = (EM & EM_RES2) != 0, kAccum = (EM & EM_ACCUM) != 0;
+    auto blk_geom = [&](const ConvTile& tl, int blk, int& mb, int& c0, long long& idx0, int& nvalid) {
+      mb = blk / (C / 32);
+      c0 = (blk - mb * (C / 32)) * 32;
+      const int row0 = mb * 128 + quarter * 32;
+      idx0 = (tl.out_row0 + tl.q0 + row0 + rsub) * (long long)C + c0 + sub * 4;
+      nvalid = tl.n - row0 - rsub;                 // rows 4i + rsub of the block are valid while 4i < nvalid
+    };
+    // residual rows of a FUTURE tile -> registers (asynchronous: nothing below depends on them until fin_store)
+    auto fin_issue = [&](const ConvTile& tl, int blk, float4 (&pre)[8]) {
+      int mb, c0, nvalid; long long idx0;
+      blk_geom(tl, blk, mb, c0, idx0, nvalid);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        pre[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (4 * q < nvalid && !(a.dbg & 32)) pre[q] = ldg_f4(a.res1 + idx0 + (long long)q * 4 * C);
+      }
+    };
+    // x + b2 (+ second residual) (+ previous partial mean / scale) -> D2[b]: conv2 accumulates on top of it
+    auto fin_store = [&](const ConvTile& tl, int blk, int b, float4 (&pre)[8]) {
+      int mb, c0, nvalid; long long idx0;
+      blk_geom(tl, blk, mb, c0, idx0, nvalid);
+      const float4 bias = *reinterpret_cast<const float4*>(a.bias + c0 + sub * 4);
+      const bool accum = kAccum && a.out_accum;
+      const float inv = 1.0f / a.out_scale;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (4 * q < nvalid) {
+          t = make_float4(pre[q].x + bias.x, pre[q].y + bias.y, pre[q].z + bias.z, pre[q].w + bias.w);
+          const long long idx = idx0 + (long long)q * 4 * C;
+          if constexpr (kRes2) {
+            const float4 r2 = ldg_f4(a.res2 + idx);
+            t.x += r2.x; t.y += r2.y; t.z += r2.z; t.w += r2.w;
+          }
+          if (accum) {
+            const float4 pv = *reinterpret_cast<const float4*>(a.out + idx);
+            t.x = fmaf(pv.x, inv, t.x); t.y = fmaf(pv.y, inv, t.y); t.z = fmaf(pv.z, inv, t.z); t.w = fmaf(pv.w, inv, t.w);
+          }
+        }
+        *reinterpret_cast<float4*>(stage + (q * 4 + rsub) * kStageLd + sub * 4) = t;
+      }
+      __syncwarp();
+      uint32_t v[32];
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const float4 t = *reinterpret_cast<const float4*>(stage + lane * kStageLd + g * 4);
+        v[4 * g] = __float_as_uint(t.x); v[4 * g + 1] = __float_as_uint(t.y);
+        v[4 * g + 2] = __float_as_uint(t.z); v[4 * g + 3] = __float_as_uint(t.w);
+      }
+      __syncwarp();
+      tmem_st32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((NBUF + b) * ACC_COLS + mb * C + c0), v);
+    };
+    // D2[b] -> out = acc * scale (+ leaky-ReLU operand copy): no global reads on this path
+    auto fin_out = [&](const ConvTile& tl, int blk, int b) {
+      int mb, c0, nvalid; long long idx0;
+      blk_geom(tl, blk, mb, c0, idx0, nvalid);
+      // two 16-column loads: the prefetched residual registers of fin_issue are live across this function
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((NBUF + b) * ACC_COLS + mb * C + c0 + hh * 16), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          *reinterpret_cast<float4*>(stage + lane * kStageLd + hh * 16 + g * 4) =
+              make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]),
+                          __uint_as_float(v[4 * g + 3]));
+      }
+      __syncwarp();
+      if (!(a.dbg & 8)) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (4 * q >= nvalid) continue;
+          const long long idx = idx0 + (long long)q * 4 * C;
+          const float4 acc = *reinterpret_cast<const float4*>(stage + (q * 4 + rsub) * kStageLd + sub * 4);
+          const float4 o = make_float4(acc.x * a.out_scale, acc.y * a.out_scale, acc.z * a.out_scale, acc.w * a.out_scale);
+          if (!(a.dbg & 64)) *reinterpret_cast<float4*>(a.out + idx) = o;
+          if constexpr ((EM & EM_OACT) != 0) {
+            const float sl = a.act[0].slope;
+            float y[4] = {o.x > 0.f ? o.x : o.x * sl, o.y > 0.f ? o.y : o.y * sl, o.z > 0.f ? o.z : o.z * sl,
+                          o.w > 0.f ? o.w : o.w * sl};
+            *reinterpret_cast<uint2*>(reinterpret_cast<ActT*>(a.act[0].dst) + idx) = Pack4<ActT>::pack(y);
+          }
+        }
+      }
+      __syncwarp();
+    };
+    // prologue: preload D2 for the first NBUF tiles
+    if (do_fin) {
+      for (int j = 0; j < NBUF && j < n_my; ++j) {
+        const ConvTile tl = a.tiles[blockIdx.x + j * gridDim.x];
+#pragma unroll 1
+        for (int blk = grp; blk < NBLK; blk += NEPI / 4) {
+          float4 pre[8];
+          fin_issue(tl, blk, pre);
+          fin_store(tl, blk, j, pre);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&d2i_full[j]);
+      }
+    }
+    for (int i = 0; i < n_my; ++i) {
+      const int b = i % NBUF;
+      const uint32_t u = (uint32_t)(i / NBUF);
+      const ConvTile tile = a.tiles[blockIdx.x + i * gridDim.x];
+      if (do_mid) {
+        mbar_wait(&d1_full[b], u & 1u);
+        mbar_wait(&a2_empty[b], (u & 1u) ^ 1u);
+        tc_fence_after();
+        if (ew == 0 && lane == 0 && (kCombined || warp == W_MID)) trace_ev(a.trace, i, 2);
+        const uint32_t dst0 = smem_u32(sA2 + b * A2_BYTES);
+#pragma unroll 1
+        for (int blk = grp; blk < NBLK && !(a.dbg & 4); blk += NMID / 4) {
+          const int mb = blk / (C / 32), c0 = (blk - mb * (C / 32)) * 32;
+          const int row = mb * 128 + quarter * 32 + lane;              // A2 row = conv1 output row of the tile
+          const int pseq = tile.q0 - H2 + row;                         // step inside the sequence
+          const bool valid = pseq >= 0 && pseq < tile.out_len;
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * ACC_COLS + mb * C + c0), v);
+          tmem_ld_wait();
+          const uint32_t rowaddr = dst0 + (uint32_t)(c0 >> 6) * (uint32_t)(kPairRA2 * 128) + (uint32_t)row * 128u;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float y[8];
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const int c = c0 + g * 8 + hh * 4;
+              const float4 bb = *reinterpret_cast<const float4*>(prm + 2 * C + c);
+              const float4 aa = *reinterpret_cast<const float4*>(prm + 3 * C + c);
+              const float4 ii = *reinterpret_cast<const float4*>(prm + 4 * C + c);
+              y[hh * 4 + 0] = snake_f(__uint_as_float(v[g * 8 + hh * 4 + 0]) + bb.x, aa.x, ii.x);
+              y[hh * 4 + 1] = snake_f(__uint_as_float(v[g * 8 + hh * 4 + 1]) + bb.y, aa.y, ii.y);
+              y[hh * 4 + 2] = snake_f(__uint_as_float(v[g * 8 + hh * 4 + 2]) + bb.z, aa.z, ii.z);
+              y[hh * 4 + 3] = snake_f(__uint_as_float(v[g * 8 + hh * 4 + 3]) + bb.w, aa.w, ii.w);
+            }
+            uint4 pk = Pack8<ActT>::pack(y);
+            if (!valid) pk = make_uint4(0u, 0u, 0u, 0u);
+            const uint32_t addr = rowaddr + (uint32_t)(((((c0 & 63) >> 3) + g) ^ (row & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk.x), "r"(pk.y), "r"(pk.z), "r"(pk.w) : "memory");
+          }
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        if (ew == 0 && lane == 0) trace_ev(a.trace, i, 3);
+        mbar_arrive(&d1_empty[b]);
+        mbar_arrive(&a2_full[b]);
+      }
+      if (do_fin) {
+        mbar_wait(&d2_full[b], u & 1u);
+        tc_fence_after();
+        if (warp == 0 && lane == 0) trace_ev(a.trace, i, 4);
+        const bool has_next = i + NBUF < n_my;
+        const ConvTile tnext = has_next ? a.tiles[blockIdx.x + (i + NBUF) * gridDim.x] : tile;
+#pragma unroll 1
+        for (int blk = grp; blk < NBLK && !(a.dbg & 4); blk += NEPI / 4) {
+          float4 pre[8];
+          if (has_next) fin_issue(tnext, blk, pre);
+          fin_out(tile, blk, b);
+          if (has_next) fin_store(tnext, blk, b, pre);
+        }
+        if (has_next) tmem_st_wait();
+        tc_fence_before();
+        if (warp == 0 && lane == 0) trace_ev(a.trace, i, 5);
+        if (has_next) mbar_arrive(&d2i_full[b]);
+        // combined mode: the staging lives in the A2 tile; nobody may start mid(i+1) before everyone left fin(i)
+        if (kCombined) asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+template <int C, int NBUF, int W_ST, int NEPI, int NPROD, int EM, typename ActT>
+int launch_pair_em(const ConvArgs& a, const PairArgs& p, uint32_t idesc, int grid, cudaStream_t st) {
+  constexpr int CB = C / 64;
+  using PC = PairCfg<C, NBUF, NEPI, NPROD>;
+  constexpr int smem = NBUF * CB * (kPairRA1 + kPairRA2) * 128 + W_ST * C * 128 + (8 * NBUF + 2 * W_ST) * 8 + 16 + 5 * C * 4 +
+                       (PC::kCombined ? 0 : NEPI * 32 * kStageLd * 4);
+  static_assert(smem <= 232448, "shared memory budget exceeded");
+  static_assert(!PC::kCombined || NEPI * 32 * kStageLd * 4 <= CB * kPairRA2 * 128, "fin staging must fit the A2 tile");
+  static bool configured = false;
+  if (!configured) {
+    VT_CUDA_OK(cudaFuncSetAttribute(k_pair_tc<C, NBUF, W_ST, NEPI, NPROD, EM, ActT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  k_pair_tc<C, NBUF, W_ST, NEPI, NPROD, EM, ActT><<<grid, PC::WARPS * 32, smem, st>>>(a, p, idesc);
+  VT_LAUNCHED();
+  return VT_OK;
+}
+
+template <int C, int NBUF, int W_ST, int NEPI, int NPROD, typename ActT>
+int launch_pair_c(const ConvArgs& a, const PairArgs& p, uint32_t idesc, int grid, cudaStream_t st) {
+  VT_REQUIRE(a.out && a.res1 && !a.act[1].dst && !a.act[2].dst, "pair_tc: needs an fp32 output and the residual stream");
+  const bool oact = a.act[0].dst && a.act[0].kind == ACT_LRELU && a.act_from_out;
+  VT_REQUIRE(oact || !a.act[0].dst, "pair_tc: only a leaky-ReLU output copy is supported");
+  if (a.res2) {
+    VT_REQUIRE(!oact && !a.out_accum && a.out_scale == 1.0f, "pair_tc: unsupported epilogue with two residuals");
+    return launch_pair_em<C, NBUF, W_ST, NEPI, NPROD, EM_RES1 | EM_RES2 | EM_OUT, ActT>(a, p, idesc, grid, st);
+  }
+  if (oact) return launch_pair_em<C, NBUF, W_ST, NEPI, NPROD, EM_RES1 | EM_OUT | EM_ACCUM | EM_OACT, ActT>(a, p, idesc, grid, st);
+  if (a.out_accum || a.out_scale != 1.0f)
+    return launch_pair_em<C, NBUF, W_ST, NEPI, NPROD, EM_RES1 | EM_OUT | EM_ACCUM, ActT>(a, p, idesc, grid, st);
+  return launch_pair_em<C, NBUF, W_ST, NEPI, NPROD, EM_RES1 | EM_OUT, ActT>(a, p, idesc, grid, st);
+}
+
+}  // namespace tc
+
+bool pair_tc_supported(const ConvLayer& c1, const ConvLayer& c2) {
+  return c1.w_tc && c2.w_tc && c1.cin == c1.cout && c2.cin == c2.cout && c1.cin == c2.cin && (c1.cin == 64 || c1.cin == 128) &&
+         c1.k == c2.k && (c1.k & 1) && c2.dil == 1 && (c1.k - 1) * c1.dil <= tc::kPairRA1 - 256 - 6 && c1.k - 1 <= 10 &&
+         c1.stride == 1 && c2.stride == 1 && c1.out_mul == 1 && c2.out_mul == 1;
+}
+
+int pair_tc_tile_rows(int k) { return 256 - (k - 1); }
+
+// `a` describes the fin epilogue (bias = conv2 bias, res1 = the pair's input stream, out, tiles of
+// pair_tc_tile_rows(k) output steps); alpha1 / alpha2 are the Snake parameters before conv1 / conv2.
+int launch_pair_tc(const ConvArgs& a_in, const ConvLayer& c1, const ConvLayer& c2, const float* alpha1, const float* alpha2,
+                   int act_elem, cudaStream_t st) {
+  VT_REQUIRE(pair_tc_supported(c1, c2) && (act_elem == ELEM_F16 || act_elem == ELEM_BF16), "pair_tc: layers %s / %s cannot be fused",
+             c1.name.c_str(), c2.name.c_str());
+  if (a_in.n_tiles == 0) return VT_OK;
+  ConvArgs a = a_in;
+  static const int dbg = getenv("VT_TC_DBG") ? atoi(getenv("VT_TC_DBG")) : 0;
+  a.dbg = dbg;
+  a.bias = c2.bias;
+  a.cout = c2.cout; a.phase_c = c2.cout; a.out_mul = 1; a.out_shift = 0; a.dup_row2 = 0;
+  PairArgs p{};
+  p.x_in = a.res1;
+  p.alpha1 = alpha1; p.alpha2 = alpha2; p.bias1 = c1.bias;
+  p.w1 = reinterpret_cast<const uint8_t*>(c1.w_tc);
+  p.w2 = reinterpret_cast<const uint8_t*>(c2.w_tc);
+  p.k = c1.k; p.dil = c1.dil;
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    VT_CUDA_OK(cudaGetDevice(&dev));
+    VT_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int C = c1.cin;
+  const int grid = a.n_tiles < sm_count ? a.n_tiles : sm_count;
+  // debug timeline: VT_TC_TRACE=<conv1 layer name> dumps CTA 0's per-tile role timestamps to stderr
+  static const char* trace_name = getenv("VT_TC_TRACE");
+  static long long* d_trace = nullptr;
+  const bool tracing = trace_name && c1.name == trace_name;
+  if (tracing) {
+    if (!d_trace) VT_CUDA_OK(cudaMalloc(&d_trace, tc::kTraceTiles * tc::kTraceEvents * 8));
+    VT_CUDA_OK(cudaMemsetAsync(d_trace, 0, tc::kTraceTiles * tc::kTraceEvents * 8, st));
+    a.trace = d_trace;
+  }
+  const uint32_t fmt = act_elem == ELEM_F16 ? 0u : 1u;
+  const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(C >> 3) << 17) | ((128u >> 4) << 24);
+  int rc;
+  if (act_elem == ELEM_F16)
+    rc = C == 64 ? tc::launch_pair_c<64, 2, 4, 8, 6, __half>(a, p, idesc, grid, st)
+                 : tc::launch_pair_c<128, 1, 4, 8, 8, __half>(a, p, idesc, grid, st);
+  else
+    rc = C == 64 ? tc::launch_pair_c<64, 2, 4, 8, 6, __nv_bfloat16>(a, p, idesc, grid, st)
+                 : tc::launch_pair_c<128, 1, 4, 8, 8, __nv_bfloat16>(a, p, idesc, grid, st);
+  if (tracing && rc == VT_OK) {
+    std::vector<long long> h(tc::kTraceTiles * tc::kTraceEvents);
+    VT_CUDA_OK(cudaStreamSynchronize(st));
+    VT_CUDA_OK(cudaMemcpy(h.data(), d_trace, h.size() * 8, cudaMemcpyDeviceToHost));
+    long long t0 = 0;
+    for (long long v : h) if (v && (!t0 || v < t0)) t0 = v;
+    fprintf(stderr, "[vt trace] pair %s k=%d dil=%d tiles=%d grid=%d (cycles; PROD start end | MID start end | FIN start end | "
+            "C1 start issued | C2 start issued)\n", c1.name.c_str(), c1.k, c1.dil, a.n_tiles, grid);
+    for (int it = 0; it < tc::kTraceTiles; ++it) {
+      if (!h[it * tc::kTraceEvents + 0]) break;
+      fprintf(stderr, "[vt trace] %2d", it);
+      for (int e = 0; e < 10; ++e) fprintf(stderr, " %7lld", h[it * tc::kTraceEvents + e] ? h[it * tc::kTraceEvents + e] - t0 : -1);
+      fprintf(stderr, "\n");
+    }
+  }
+  return rc;
+}
+
+}  // namespace vt

@@ -242,7 +242,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const ConvTile&
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (4 * i < nvalid) {
+        if (4 * i < nvalid && !(a.dbg & 32)) {
           const long long idx = idx0 + i * istride;
           if constexpr ((EM & EM_RES1) != 0) q = __ldg(reinterpret_cast<const float4*>(a.res1 + idx));
           if constexpr ((EM & EM_RES2) != 0) {
@@ -276,7 +276,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const ConvTile&
       }
       if constexpr ((EM & EM_OUT) != 0) {
         float4 o = make_float4(x[0] * a.out_scale, x[1] * a.out_scale, x[2] * a.out_scale, x[3] * a.out_scale);
-        *reinterpret_cast<float4*>(a.out + idx) = o;
+        if (!(a.dbg & 64)) *reinterpret_cast<float4*>(a.out + idx) = o;
         if (a.dup_row2 && step == 2)                      // reflection pad (1, 0): padded[0] = unpadded[1]
           *reinterpret_cast<float4*>(a.out + tile.out_row0 * ld + co) = o;
         if constexpr ((EM & EM_OACT) != 0) {
