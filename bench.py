@@ -286,7 +286,7 @@ def run_ours(args, rank, world, local_rank):
                 "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "ResBlock convolutions (72 launches per forward)",
+        "roofline": {"bound": "tensor", "kernel": f"ResBlock convolutions ({prof['resblock_launches'] // args.steps} launches per forward: fused pairs at C=64/128, single convs at C=256)",
                      "achieved": rb_tflops, "peak": tf, "unit": "TFLOP/s", "frac": rb_tflops / tf, "traffic": None,
                      "peak_source": how, "kernel_ms_per_step": rb_ms, "forward_ms_per_step": fwd_ms,
                      "kernel_share_of_step": rb_ms / ms if ms > 0 else None,

@@ -90,6 +90,48 @@ def test_fp32_path_matches_oracle_layer_by_layer(torch, weights, vocoders, kind)
         assert H.snr_db(ref, got) >= 80.0, (kind, b, H.snr_db(ref, got))
 
 
+def test_tensor_core_path_layer_by_layer(torch, weights, vocoders):
+    """The tcgen05 path (K-blocked layers, fused ResBlock pairs at C = 64 / 128, activation-resident convs at
+    C = 256) against the oracle, tap by tap: fp16 operands bound every intermediate to ~1e-3 of its range.
+    Lengths cross the fused kernel's 246/250/254-step tiles and include sequences shorter than one halo."""
+    Ts = [37, 50, 8, 1, 3]
+    mels, f0s, pvs, nzs = _inputs(torch, Ts, seed=13)
+    voc = vocoders("unit", "fp16")
+    wavs = voc.inference(mels, f0=f0s, phase_vec=pvs, noise=nzs)
+    W = H.fold_weight_norm(weights["unit"])
+    for b, T in enumerate(Ts):
+        taps = {}
+        ref = _oracle(torch, W, mels[b], f0s[b], pvs[b], nzs[b], taps)
+        for name in ("conv_pre", "ups0", "x0", "stage0", "ups1", "x1", "stage1", "ups2", "x2", "stage2", "conv_post"):
+            got = voc.read_tap(name, b, TAP_CH[name]).cpu()
+            want = taps[name][0].t().contiguous()
+            assert got.shape == want.shape, (name, b, got.shape, want.shape)
+            assert torch.isfinite(got).all(), (name, b)
+            assert _rel_err(want, got) < 3e-3, (name, b, _rel_err(want, got))
+        got = wavs[b].cpu()
+        assert got.numel() == 480 * T == ref.numel()
+        assert float((got - ref).abs().max()) <= MAX_ABS and H.snr_db(ref, got) >= MIN_SNR_DB, (b, H.snr_db(ref, got))
+
+
+def test_fused_pairs_agree_with_unfused_convs(torch, weights, monkeypatch):
+    """VT_NO_FUSE=1 runs every ResBlock conv as its own launch (operand copies in HBM); the fused pair kernel
+    must agree with it well inside the parity bar (same arithmetic, but the fp32 residual add order differs, which
+    moves individual fp16 operand roundings downstream)."""
+    from vocalie_tts_b200.hift import HiFTVocoder
+    Ts = [123, 40]
+    mels, f0s, pvs, nzs = _inputs(torch, Ts, seed=17)
+    fused = HiFTVocoder(weights["unit"], operand="fp16")
+    monkeypatch.setenv("VT_NO_FUSE", "1")
+    plain = HiFTVocoder(weights["unit"], operand="fp16")
+    monkeypatch.delenv("VT_NO_FUSE")
+    a = [w.clone().cpu() for w in fused.inference(mels, f0=f0s, phase_vec=pvs, noise=nzs)]
+    n_fused = fused.last_launches
+    b = [w.clone().cpu() for w in plain.inference(mels, f0=f0s, phase_vec=pvs, noise=nzs)]
+    assert n_fused < plain.last_launches
+    for x, y in zip(a, b):
+        assert H.snr_db(y, x) >= 66.0, H.snr_db(y, x)
+
+
 @pytest.mark.parametrize("kind", ["init", "unit"])
 @pytest.mark.parametrize("operand", ["fp32", "fp16"])
 def test_waveform_parity_cfg1(torch, weights, vocoders, kind, operand):

@@ -717,7 +717,7 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
       const double steps = (double)kLevelMul[i] * (double)total_T + (i == 2 ? B : 0);
       const double c = (double)(kBase >> (i + 1));
       h->rb_flops += steps * 2.0 * c * c * 6.0 * (kSrcRbKernels[i] + kRbKernels[0] + kRbKernels[1] + kRbKernels[2]);
-      h->rb_launches += 24;
+      h->rb_launches += h->fuse[i] ? 12 : 24;
     }
     if (h->fuse[i]) {
       // fused pairs: fp32 stream in, fp32 stream out, no operand copies in HBM

@@ -70,10 +70,10 @@ struct PairCfg {
   static constexpr bool kCombined = NBUF == 1;
   static constexpr int W_MID = kCombined ? 0 : NEPI;
   static constexpr int W_MMA = kCombined ? NEPI : 2 * NEPI;
-  static constexpr int WARPS = W_MMA + 2 + NPROD;
+  static constexpr int WARPS = W_MMA + 3 + NPROD;      // + MMA, weight producer, x loader
 };
 
-template <int C, int NBUF, int W_ST, int NEPI, int NPROD, int EM, typename ActT>
+template <int C, int NBUF, int NA1, int NA2, int W_ST, int NEPI, int NPROD, int NSLAB, int EM, typename ActT>
 __global__ void __launch_bounds__(PairCfg<C, NBUF, NEPI, NPROD>::WARPS * 32, 1)
 k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
   using PC = PairCfg<C, NBUF, NEPI, NPROD>;
@@ -84,18 +84,23 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
   constexpr int A1_BYTES = CB * kPairRA1 * 128, A2_BYTES = CB * kPairRA2 * 128, W_BYTES = C * 128;
   constexpr int ACC_COLS = 2 * C;                        // two 128-row M blocks
   constexpr int SKEW = NBUF - 1;
-  constexpr int W_MID = PC::W_MID, W_MMA = PC::W_MMA, W_WP = W_MMA + 1, W_AP = W_MMA + 2;
-  static_assert(4 * C * NBUF <= 512 && NEPI % 4 == 0 && kProdT % (C / 8) == 0, "bad configuration");
+  constexpr int W_MID = PC::W_MID, W_MMA = PC::W_MMA, W_WP = W_MMA + 1, W_XP = W_MMA + 2, W_AP = W_MMA + 3;
+  // fp32 stream slabs of the x ring: kSlabBytes of whole rows each (rows are contiguous in HBM -> one 1-D bulk copy)
+  constexpr int kSlabBytes = 8192, SLAB_ROWS = kSlabBytes / (C * 4);
+  static_assert(4 * C * NBUF <= 512 && NEPI % 4 == 0 && kProdT % (C / 4) == 0, "bad configuration");
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA1 = smem;
-  uint8_t* sA2 = sA1 + NBUF * A1_BYTES;
-  uint8_t* sW = sA2 + NBUF * A2_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + W_ST * W_BYTES);
+  uint8_t* sA2 = sA1 + NA1 * A1_BYTES;
+  uint8_t* sW = sA2 + NA2 * A2_BYTES;
+  uint8_t* sX = sW + W_ST * W_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sX + NSLAB * kSlabBytes);
   uint64_t* a1_full = bars;
-  uint64_t* a1_empty = a1_full + NBUF;
-  uint64_t* a2_full = a1_empty + NBUF;
-  uint64_t* a2_empty = a2_full + NBUF;
-  uint64_t* d1_full = a2_empty + NBUF;
+  uint64_t* a1_empty = a1_full + NA1;
+  uint64_t* x_full = a1_empty + NA1;
+  uint64_t* x_empty = x_full + NSLAB;
+  uint64_t* a2_full = x_empty + NSLAB;
+  uint64_t* a2_empty = a2_full + NA2;
+  uint64_t* d1_full = a2_empty + NA2;
   uint64_t* d1_empty = d1_full + NBUF;
   uint64_t* d2_full = d1_empty + NBUF;
   uint64_t* d2i_full = d2_full + NBUF;   // D2 free AND preloaded with the residual terms
@@ -108,9 +113,10 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
+    for (int i = 0; i < NA1; ++i) { mbar_init(&a1_full[i], kProdT); mbar_init(&a1_empty[i], 1); }
+    for (int i = 0; i < NA2; ++i) { mbar_init(&a2_full[i], NMID * 32); mbar_init(&a2_empty[i], 1); }
+    for (int i = 0; i < NSLAB; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], kProdT); }
     for (int i = 0; i < NBUF; ++i) {
-      mbar_init(&a1_full[i], kProdT); mbar_init(&a1_empty[i], 1);
-      mbar_init(&a2_full[i], NMID * 32); mbar_init(&a2_empty[i], 1);
       mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], NMID * 32);
       mbar_init(&d2_full[i], 1); mbar_init(&d2i_full[i], kFin * 32);
     }
@@ -138,65 +144,82 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
   const int nchunks = p.k * CB;
 
   if (warp >= W_AP) {
-    // ---------------- producers: fp32 stream rows -> Snake1 -> fp16 A1 tile.  One task = one 16-byte operand
-    // chunk (8 channels) of one row; a thread keeps the same 8 channels for every task (128 % (C/8) == 0).
-    constexpr int CPR = C / 8, RSTEP = kProdT / CPR, U = 4;
+    // ---------------- producers: fp32 slabs of the x ring -> Snake1 -> fp16 A1 tile (SWIZZLE_128B).  All global
+    // latency is taken by the bulk-copy engine; this loop is shared-memory to shared-memory.  A thread owns the
+    // channels [4*ch, 4*ch+4) and [C/2 + 4*ch, +4) (two conflict-free 16-byte reads per row) for every row it
+    // touches, so its Snake parameters stay in registers.
+    constexpr int QPR = C / 8;                     // threads per row
+    constexpr int RPP = kProdT / QPR;              // rows per pass of all producer threads
     const int pt = threadIdx.x - W_AP * 32;
-    const int ch = pt % CPR, r_first = pt / CPR;
-    float al[8], ia[8];
+    const int ch = pt % QPR, r_in = pt / QPR;
+    const int cA = 4 * ch, cB = C / 2 + 4 * ch;    // first channel of the two pieces
+    float alA[4], iaA[4], alB[4], iaB[4];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { al[e] = prm[ch * 8 + e]; ia[e] = prm[C + ch * 8 + e]; }
+    for (int e = 0; e < 4; ++e) {
+      alA[e] = prm[cA + e]; iaA[e] = prm[C + cA + e];
+      alB[e] = prm[cB + e]; iaB[e] = prm[C + cB + e];
+    }
     const int R1 = 256 + 2 * H1;
-    const uint32_t col_off = (uint32_t)(ch >> 3) * (uint32_t)(kPairRA1 * 128);
-    // Rolling prefetch: inside a tile every register slot q re-issues its next row's 32-byte load right after it
-    // is consumed; the first round of the NEXT tile is issued after this tile's arrive (the proxy fence before the
-    // arrive is a full membar - it must not find global loads in flight) and flies during the a1_empty wait.
-    auto tile_src = [&](int i) {
-      const ConvTile tl = a.tiles[blockIdx.x + i * gridDim.x];
-      return p.x_in + (tl.in_row0 + tl.q0 - H1 - H2) * (long long)C + ch * 8;
-    };
-    float4 lo[U], hi[U];
-    const bool loads_on = !(a.dbg & 2);
-    auto first_round = [&](const float* src) {
-#pragma unroll
-      for (int q = 0; q < U; ++q) {
-        const int r = r_first + q * RSTEP;
-        lo[q] = hi[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < R1 && loads_on) { lo[q] = ldg_f4(src + (long long)r * C); hi[q] = ldg_f4(src + (long long)r * C + 4); }
-      }
-    };
-    const float* src = n_my > 0 ? tile_src(0) : p.x_in;
-    if (n_my > 0) first_round(src);
+    const int n_slab = (R1 + SLAB_ROWS - 1) / SLAB_ROWS;
+    // byte offsets of the two pieces inside an A1 row block: 64-channel block, 16-byte chunk, 8-byte half
+    const uint32_t blkA = (uint32_t)(cA >> 6) * (uint32_t)(kPairRA1 * 128), blkB = (uint32_t)(cB >> 6) * (uint32_t)(kPairRA1 * 128);
+    const uint32_t chkA = (uint32_t)((cA & 63) >> 3), chkB = (uint32_t)((cB & 63) >> 3);
+    const uint32_t halfA = (uint32_t)((cA & 7) >> 2) * 8u, halfB = (uint32_t)((cB & 7) >> 2) * 8u;
+    const uint32_t a1_base = smem_u32(sA1);
+    uint32_t xs = 0, xph = 0;
     for (int i = 0; i < n_my; ++i) {
-      const int b = i % NBUF;
-      const uint32_t u = (uint32_t)(i / NBUF);
-      mbar_wait(&a1_empty[b], (u & 1u) ^ 1u);
+      const int b1 = i % NA1;
+      mbar_wait(&a1_empty[b1], ((uint32_t)(i / NA1) & 1u) ^ 1u);
       if (pt == 0) trace_ev(a.trace, i, 0);
-      const uint32_t dst = smem_u32(sA1 + b * A1_BYTES) + col_off;
-      for (int r0 = r_first; r0 < R1; r0 += RSTEP * U) {
+      const uint32_t a1 = a1_base + (uint32_t)(b1 * A1_BYTES);
+      for (int sl = 0; sl < n_slab; ++sl) {
+        mbar_wait(&x_full[xs], xph);
+        const uint32_t xsrc = smem_u32(sX + xs * kSlabBytes);
 #pragma unroll
-        for (int q = 0; q < U; ++q) {
-          const int r = r0 + q * RSTEP;
+        for (int rr = r_in; rr < SLAB_ROWS; rr += RPP) {
+          const int r = sl * SLAB_ROWS + rr;
           if (r < R1) {
-            float y[8];
-            y[0] = snake_f(lo[q].x, al[0], ia[0]); y[1] = snake_f(lo[q].y, al[1], ia[1]);
-            y[2] = snake_f(lo[q].z, al[2], ia[2]); y[3] = snake_f(lo[q].w, al[3], ia[3]);
-            y[4] = snake_f(hi[q].x, al[4], ia[4]); y[5] = snake_f(hi[q].y, al[5], ia[5]);
-            y[6] = snake_f(hi[q].z, al[6], ia[6]); y[7] = snake_f(hi[q].w, al[7], ia[7]);
-            const uint4 pk = Pack8<ActT>::pack(y);
-            const uint32_t addr = dst + (uint32_t)r * 128u + (uint32_t)(((ch & 7) ^ (r & 7)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk.x), "r"(pk.y), "r"(pk.z), "r"(pk.w) : "memory");
-            const int rn = r + RSTEP * U;
-            if (rn < R1 && loads_on) { lo[q] = ldg_f4(src + (long long)rn * C); hi[q] = ldg_f4(src + (long long)rn * C + 4); }
+            float4 va, vb;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(va.x), "=f"(va.y), "=f"(va.z), "=f"(va.w)
+                         : "r"(xsrc + (uint32_t)(rr * C * 4 + cA * 4)));
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(vb.x), "=f"(vb.y), "=f"(vb.z), "=f"(vb.w)
+                         : "r"(xsrc + (uint32_t)(rr * C * 4 + cB * 4)));
+            float ya[4] = {snake_f(va.x, alA[0], iaA[0]), snake_f(va.y, alA[1], iaA[1]), snake_f(va.z, alA[2], iaA[2]),
+                           snake_f(va.w, alA[3], iaA[3])};
+            float yb[4] = {snake_f(vb.x, alB[0], iaB[0]), snake_f(vb.y, alB[1], iaB[1]), snake_f(vb.z, alB[2], iaB[2]),
+                           snake_f(vb.w, alB[3], iaB[3])};
+            const uint2 pa = Pack4<ActT>::pack(ya), pb = Pack4<ActT>::pack(yb);
+            const uint32_t rowb = a1 + (uint32_t)r * 128u;
+            const uint32_t swz = (uint32_t)(r & 7);
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(rowb + blkA + ((chkA ^ swz) << 4) + halfA), "r"(pa.x), "r"(pa.y) : "memory");
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(rowb + blkB + ((chkB ^ swz) << 4) + halfB), "r"(pb.x), "r"(pb.y) : "memory");
           }
         }
+        mbar_arrive(&x_empty[xs]);                  // the slab has been read: the loader may refill it
+        if (++xs == (uint32_t)NSLAB) { xs = 0; xph ^= 1u; }
       }
       fence_proxy_async();
       if (pt == 0) trace_ev(a.trace, i, 1);
-      mbar_arrive(&a1_full[b]);
-      if (i + 1 < n_my) {
-        src = tile_src(i + 1);
-        first_round(src);
+      mbar_arrive(&a1_full[b1]);
+    }
+  } else if (warp == W_XP) {
+    // ---------------- x loader: streams the tiles' fp32 rows (with halo) into the ring, slab by slab
+    if (lane == 0) {
+      const int R1 = 256 + 2 * H1;
+      uint32_t xs = 0, xph = 0;
+      for (int i = 0; i < n_my; ++i) {
+        const ConvTile tl = a.tiles[blockIdx.x + i * gridDim.x];
+        const float* src = p.x_in + (tl.in_row0 + tl.q0 - H1 - H2) * (long long)C;
+        for (int r0 = 0; r0 < R1; r0 += SLAB_ROWS) {
+          const int rows = R1 - r0 < SLAB_ROWS ? R1 - r0 : SLAB_ROWS;
+          mbar_wait(&x_empty[xs], xph ^ 1u);
+          if (a.dbg & 2) mbar_arrive(&x_full[xs]);
+          else {
+            mbar_arrive_expect_tx(&x_full[xs], (uint32_t)(rows * C * 4));
+            bulk_g2s(sX + xs * kSlabBytes, src + (long long)r0 * C, (uint32_t)(rows * C * 4), &x_full[xs]);
+          }
+          if (++xs == (uint32_t)NSLAB) { xs = 0; xph ^= 1u; }
+        }
       }
     }
   } else if (warp == W_WP) {
@@ -232,17 +255,19 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
         const int i = pass == 0 ? s : s - SKEW;
         const int b = i % NBUF;
         const uint32_t u = (uint32_t)(i / NBUF);
-        uint64_t* src_full = pass == 0 ? &a1_full[b] : &a2_full[b];
-        uint64_t* src_empty = pass == 0 ? &a1_empty[b] : &a2_empty[b];
+        const int bs = pass == 0 ? i % NA1 : i % NA2;                         // shared-memory operand buffer
+        const uint32_t us = (uint32_t)(pass == 0 ? i / NA1 : i / NA2);
+        uint64_t* src_full = pass == 0 ? &a1_full[bs] : &a2_full[bs];
+        uint64_t* src_empty = pass == 0 ? &a1_empty[bs] : &a2_empty[bs];
         uint64_t* dst_full = pass == 0 ? &d1_full[b] : &d2_full[b];
         // conv1 needs D1 drained by the mid epilogue; conv2 needs D2 preloaded by the fin warps (x + b2 + ...)
         if (pass == 0) mbar_wait(&d1_empty[b], (u & 1u) ^ 1u);
         else mbar_wait(&d2i_full[b], u & 1u);
-        mbar_wait(src_full, u & 1u);
+        mbar_wait(src_full, us & 1u);
         tc_fence_after();
         if (lane == 0) trace_ev(a.trace, i, 6 + 2 * pass);
         const uint32_t d0 = tmem_base + (uint32_t)((pass * NBUF + b) * ACC_COLS);
-        const uint32_t a_tile = pass == 0 ? a1_lo0 + (uint32_t)b * (uint32_t)(A1_BYTES >> 4) : a2_lo0 + (uint32_t)b * (uint32_t)(A2_BYTES >> 4);
+        const uint32_t a_tile = pass == 0 ? a1_lo0 + (uint32_t)bs * (uint32_t)(A1_BYTES >> 4) : a2_lo0 + (uint32_t)bs * (uint32_t)(A2_BYTES >> 4);
         const uint32_t blk16 = (uint32_t)(pass == 0 ? kPairRA1 : kPairRA2) * 8u;   // 64-channel block stride, 16-byte units
         const uint32_t tap16 = (uint32_t)(pass == 0 ? p.dil : 1) * 8u;              // one tap = dil rows of 128 B
         uint32_t acc = pass == 0 ? 0u : 1u;
@@ -397,11 +422,12 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
       const uint32_t u = (uint32_t)(i / NBUF);
       const ConvTile tile = a.tiles[blockIdx.x + i * gridDim.x];
       if (do_mid) {
+        const int b2 = i % NA2;
         mbar_wait(&d1_full[b], u & 1u);
-        mbar_wait(&a2_empty[b], (u & 1u) ^ 1u);
+        mbar_wait(&a2_empty[b2], ((uint32_t)(i / NA2) & 1u) ^ 1u);
         tc_fence_after();
         if (ew == 0 && lane == 0 && (kCombined || warp == W_MID)) trace_ev(a.trace, i, 2);
-        const uint32_t dst0 = smem_u32(sA2 + b * A2_BYTES);
+        const uint32_t dst0 = smem_u32(sA2 + b2 * A2_BYTES);
 #pragma unroll 1
         for (int blk = grp; blk < NBLK && !(a.dbg & 4); blk += NMID / 4) {
           const int mb = blk / (C / 32), c0 = (blk - mb * (C / 32)) * 32;
@@ -436,7 +462,7 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
         fence_proxy_async();
         if (ew == 0 && lane == 0) trace_ev(a.trace, i, 3);
         mbar_arrive(&d1_empty[b]);
-        mbar_arrive(&a2_full[b]);
+        mbar_arrive(&a2_full[b2]);
       }
       if (do_fin) {
         mbar_wait(&d2_full[b], u & 1u);
@@ -469,37 +495,38 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
   }
 }
 
-template <int C, int NBUF, int W_ST, int NEPI, int NPROD, int EM, typename ActT>
+template <int C, int NBUF, int NA1, int NA2, int W_ST, int NEPI, int NPROD, int NSLAB, int EM, typename ActT>
 int launch_pair_em(const ConvArgs& a, const PairArgs& p, uint32_t idesc, int grid, cudaStream_t st) {
   constexpr int CB = C / 64;
   using PC = PairCfg<C, NBUF, NEPI, NPROD>;
-  constexpr int smem = NBUF * CB * (kPairRA1 + kPairRA2) * 128 + W_ST * C * 128 + (8 * NBUF + 2 * W_ST) * 8 + 16 + 5 * C * 4 +
+  constexpr int smem = CB * (NA1 * kPairRA1 + NA2 * kPairRA2) * 128 + W_ST * C * 128 + NSLAB * 8192 +
+                       (2 * NA1 + 2 * NA2 + 2 * NSLAB + 4 * NBUF + 2 * W_ST) * 8 + 16 + 5 * C * 4 +
                        (PC::kCombined ? 0 : NEPI * 32 * kStageLd * 4);
   static_assert(smem <= 232448, "shared memory budget exceeded");
   static_assert(!PC::kCombined || NEPI * 32 * kStageLd * 4 <= CB * kPairRA2 * 128, "fin staging must fit the A2 tile");
   static bool configured = false;
   if (!configured) {
-    VT_CUDA_OK(cudaFuncSetAttribute(k_pair_tc<C, NBUF, W_ST, NEPI, NPROD, EM, ActT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    VT_CUDA_OK(cudaFuncSetAttribute(k_pair_tc<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, ActT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  k_pair_tc<C, NBUF, W_ST, NEPI, NPROD, EM, ActT><<<grid, PC::WARPS * 32, smem, st>>>(a, p, idesc);
+  k_pair_tc<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, ActT><<<grid, PC::WARPS * 32, smem, st>>>(a, p, idesc);
   VT_LAUNCHED();
   return VT_OK;
 }
 
-template <int C, int NBUF, int W_ST, int NEPI, int NPROD, typename ActT>
+template <int C, int NBUF, int NA1, int NA2, int W_ST, int NEPI, int NPROD, int NSLAB, typename ActT>
 int launch_pair_c(const ConvArgs& a, const PairArgs& p, uint32_t idesc, int grid, cudaStream_t st) {
   VT_REQUIRE(a.out && a.res1 && !a.act[1].dst && !a.act[2].dst, "pair_tc: needs an fp32 output and the residual stream");
   const bool oact = a.act[0].dst && a.act[0].kind == ACT_LRELU && a.act_from_out;
   VT_REQUIRE(oact || !a.act[0].dst, "pair_tc: only a leaky-ReLU output copy is supported");
   if (a.res2) {
     VT_REQUIRE(!oact && !a.out_accum && a.out_scale == 1.0f, "pair_tc: unsupported epilogue with two residuals");
-    return launch_pair_em<C, NBUF, W_ST, NEPI, NPROD, EM_RES1 | EM_RES2 | EM_OUT, ActT>(a, p, idesc, grid, st);
+    return launch_pair_em<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM_RES1 | EM_RES2 | EM_OUT, ActT>(a, p, idesc, grid, st);
   }
-  if (oact) return launch_pair_em<C, NBUF, W_ST, NEPI, NPROD, EM_RES1 | EM_OUT | EM_ACCUM | EM_OACT, ActT>(a, p, idesc, grid, st);
+  if (oact) return launch_pair_em<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM_RES1 | EM_OUT | EM_ACCUM | EM_OACT, ActT>(a, p, idesc, grid, st);
   if (a.out_accum || a.out_scale != 1.0f)
-    return launch_pair_em<C, NBUF, W_ST, NEPI, NPROD, EM_RES1 | EM_OUT | EM_ACCUM, ActT>(a, p, idesc, grid, st);
-  return launch_pair_em<C, NBUF, W_ST, NEPI, NPROD, EM_RES1 | EM_OUT, ActT>(a, p, idesc, grid, st);
+    return launch_pair_em<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM_RES1 | EM_OUT | EM_ACCUM, ActT>(a, p, idesc, grid, st);
+  return launch_pair_em<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM_RES1 | EM_OUT, ActT>(a, p, idesc, grid, st);
 }
 
 }  // namespace tc
@@ -551,11 +578,11 @@ int launch_pair_tc(const ConvArgs& a_in, const ConvLayer& c1, const ConvLayer& c
   const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(C >> 3) << 17) | ((128u >> 4) << 24);
   int rc;
   if (act_elem == ELEM_F16)
-    rc = C == 64 ? tc::launch_pair_c<64, 2, 4, 8, 6, __half>(a, p, idesc, grid, st)
-                 : tc::launch_pair_c<128, 1, 4, 8, 8, __half>(a, p, idesc, grid, st);
+    rc = C == 64 ? tc::launch_pair_c<64, 2, 2, 1, 4, 8, 4, 5, __half>(a, p, idesc, grid, st)
+                 : tc::launch_pair_c<128, 1, 1, 1, 3, 8, 4, 3, __half>(a, p, idesc, grid, st);
   else
-    rc = C == 64 ? tc::launch_pair_c<64, 2, 4, 8, 6, __nv_bfloat16>(a, p, idesc, grid, st)
-                 : tc::launch_pair_c<128, 1, 4, 8, 8, __nv_bfloat16>(a, p, idesc, grid, st);
+    rc = C == 64 ? tc::launch_pair_c<64, 2, 2, 1, 4, 8, 4, 5, __nv_bfloat16>(a, p, idesc, grid, st)
+                 : tc::launch_pair_c<128, 1, 1, 1, 3, 8, 4, 3, __nv_bfloat16>(a, p, idesc, grid, st);
   if (tracing && rc == VT_OK) {
     std::vector<long long> h(tc::kTraceTiles * tc::kTraceEvents);
     VT_CUDA_OK(cudaStreamSynchronize(st));
