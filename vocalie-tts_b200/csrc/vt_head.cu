@@ -13,11 +13,18 @@ namespace vt {
 constexpr int kHeadSamples = 512;                       // output samples per block
 constexpr int kHeadFrames = kHeadSamples / kHop + 4;    // frames touching them (132)
 
+// Three phases per block of 512 output samples:
+//   1. (frame, bin) -> re, im   = clip(exp(x_m), 100) * (cos, sin)(sin(x_p))           [shared memory]
+//   2. frame -> 16 windowed time samples: real inverse DFT with compile-time twiddles (one thread per frame;
+//      a data-dependent twiddle index would serialise the constant cache), times hann / 16      [shared memory]
+//   3. sample -> overlap-add of its <= 4 frames, divide by the overlap-added squared window, clamp, trim_fade
 __global__ void __launch_bounds__(256)
 k_istft_head(const float* __restrict__ post, const int* __restrict__ mel_off, const int* __restrict__ T,
              const long long* __restrict__ off2, const float* __restrict__ trim_fade, float* __restrict__ wav) {
   __shared__ float sh_re[kHeadFrames][10];
   __shared__ float sh_im[kHeadFrames][10];
+  __shared__ float sh_y[kHeadFrames][17];
+  __shared__ float sh_w2[16];
   const int b = blockIdx.y;
   const long long L = (long long)T[b] * kSPF;
   const long long frames = L / kHop + 1;
@@ -27,6 +34,7 @@ k_istft_head(const float* __restrict__ post, const int* __restrict__ mel_off, co
   long long f0 = (p0 + 8 - 15 + 3) / 4;   // ceil((p0 - 7) / 4) for p0 >= 0 (p0 multiple of 512)
   if (f0 < 0) f0 = 0;
   const float* src = post + (off2[b] + f0) * kSpecCh;
+  if (threadIdx.x < 16) sh_w2[threadIdx.x] = c_hann16[threadIdx.x] * c_hann16[threadIdx.x];
   for (int i = threadIdx.x; i < kHeadFrames * 9; i += blockDim.x) {
     const int fl = i / 9, m = i - fl * 9;
     float re = 0.0f, im = 0.0f;
@@ -44,6 +52,32 @@ k_istft_head(const float* __restrict__ post, const int* __restrict__ mel_off, co
     sh_im[fl][m] = im;
   }
   __syncthreads();
+  if (threadIdx.x < kHeadFrames) {
+    const int fl = threadIdx.x;
+    float re[9], im[9];
+#pragma unroll
+    for (int m = 0; m < 9; ++m) { re[m] = sh_re[fl][m]; im[m] = sh_im[fl][m]; }
+    constexpr float kCos[16] = {1.0f, 0.9238795325112867f, 0.7071067811865476f, 0.3826834323650898f, 0.0f,
+                                -0.3826834323650898f, -0.7071067811865476f, -0.9238795325112867f, -1.0f,
+                                -0.9238795325112867f, -0.7071067811865476f, -0.3826834323650898f, 0.0f,
+                                0.3826834323650898f, 0.7071067811865476f, 0.9238795325112867f};
+    constexpr float kHann[16] = {0.0f, 0.03806023374435663f, 0.14644660940672627f, 0.3086582838174551f, 0.5f,
+                                 0.6913417161825449f, 0.8535533905932737f, 0.9619397662556434f, 1.0f,
+                                 0.9619397662556434f, 0.8535533905932737f, 0.6913417161825449f, 0.5f,
+                                 0.3086582838174551f, 0.14644660940672627f, 0.03806023374435663f};
+#pragma unroll
+    for (int n = 0; n < 16; ++n) {
+      float acc = re[0] + ((n & 1) ? -re[8] : re[8]);
+#pragma unroll
+      for (int m = 1; m < 8; ++m) {
+        const int ph = (m * n) & 15;
+        acc = fmaf(2.0f * re[m], kCos[ph], acc);
+        acc = fmaf(-2.0f * im[m], kCos[(ph + 12) & 15], acc);   // sin(t) = cos(t - pi/2)
+      }
+      sh_y[fl][n] = acc * (1.0f / 16.0f) * kHann[n];
+    }
+  }
+  __syncthreads();
   for (int l = threadIdx.x; l < kHeadSamples; l += blockDim.x) {
     const long long p = p0 + l;
     if (p >= L) break;
@@ -55,17 +89,8 @@ k_istft_head(const float* __restrict__ post, const int* __restrict__ mel_off, co
     float num = 0.0f, den = 0.0f;
     for (long long f = fa; f <= fb; ++f) {
       const int n = (int)(P - 4 * f);          // 0..15
-      const int fl = (int)(f - f0);
-      float acc = sh_re[fl][0] + ((n & 1) ? -sh_re[fl][8] : sh_re[fl][8]);
-#pragma unroll
-      for (int m = 1; m < 8; ++m) {
-        const int ph = (m * n) & 15;
-        acc = fmaf(2.0f * sh_re[fl][m], c_cos16[ph], acc);
-        acc = fmaf(-2.0f * sh_im[fl][m], c_sin16[ph], acc);
-      }
-      const float w = c_hann16[n];
-      num = fmaf(acc * (1.0f / 16.0f), w, num);
-      den = fmaf(w, w, den);
+      num += sh_y[(int)(f - f0)][n];
+      den += sh_w2[n];
     }
     float y = num / den;
     y = fminf(fmaxf(y, -0.99f), 0.99f);

@@ -659,7 +659,7 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
   rc = launch_sine_source(f0, P.d_mel_off, P.d_T, B, total_T, phase_vec, noise, seed, h->lin_w, h->lin_b,
                           w.phase_base, w.s, st);
   if (rc) return rc;
-  rc = launch_stft(w.s, P.d_mel_off, P.d_T, P.d_off[2], B, total_T, w.spec, h->use_tc ? w.spec_op : nullptr, ae, st);
+  rc = launch_stft(w.s, P.d_mel_off, P.d_T, P.d_off[2], B, total_T, h->use_tc ? nullptr : w.spec, h->use_tc ? w.spec_op : nullptr, ae, st);
   if (rc) return rc;
   mark(h, "source_stft", st);
   // ---- conv_pre
@@ -895,7 +895,11 @@ int64_t vt_hift_read_tap(vt_hift* h, const char* tap, int seq, float* out, int64
   };
   if (name == "f0") { src = w.f0; row0 = P.h_mel_off[seq]; rows = T; ld = ch = 1; }
   else if (name == "s") { src = w.s; row0 = (long long)P.h_mel_off[seq] * kSPF; rows = (long long)T * kSPF; ld = ch = 1; }
-  else if (name == "s_stft") { src = w.spec; row0 = P.h_off[2][seq]; rows = 120LL * T + 1; ld = kSpecCh; ch = kNfft + 2; }
+  else if (name == "s_stft") {
+    // tensor-core modes keep only the operand-typed rows (kSpecOp wide)
+    src = h->use_tc ? w.spec_op : (const void*)w.spec; row0 = P.h_off[2][seq]; rows = 120LL * T + 1;
+    ld = h->use_tc ? kSpecOp : kSpecCh; ch = kNfft + 2; elem = h->use_tc ? h->act_elem : (int)ELEM_F32;
+  }
   else if (name == "conv_post") { src = w.post; row0 = P.h_off[2][seq]; rows = 120LL * T + 1; ld = kSpecCh; ch = kNfft + 2; }
   else if (name == "conv_pre") { src = w.xpre; row0 = P.h_offM[seq]; rows = T; ld = ch = kBase; }
   else if (name.size() == 4 && name.compare(0, 3, "ups") == 0) level(name[3] - '0', w.U[name[3] - '0'], ELEM_F32);

@@ -59,6 +59,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // Warp roles: [0, NEPI) fin epilogue; then (NBUF == 2) NEPI mid-epilogue warps, or (NBUF == 1, "combined") the
@@ -70,7 +76,7 @@ struct PairCfg {
   static constexpr bool kCombined = NBUF == 1;
   static constexpr int W_MID = kCombined ? 0 : NEPI;
   static constexpr int W_MMA = kCombined ? NEPI : 2 * NEPI;
-  static constexpr int WARPS = W_MMA + 3 + NPROD;      // + MMA, weight producer, x loader
+  static constexpr int WARPS = W_MMA + 2 + NPROD;      // + MMA warp, loader warp (weights and x ring)
 };
 
 template <int C, int NBUF, int NA1, int NA2, int W_ST, int NEPI, int NPROD, int NSLAB, int EM, typename ActT>
@@ -84,10 +90,10 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
   constexpr int A1_BYTES = CB * kPairRA1 * 128, A2_BYTES = CB * kPairRA2 * 128, W_BYTES = C * 128;
   constexpr int ACC_COLS = 2 * C;                        // two 128-row M blocks
   constexpr int SKEW = NBUF - 1;
-  constexpr int W_MID = PC::W_MID, W_MMA = PC::W_MMA, W_WP = W_MMA + 1, W_XP = W_MMA + 2, W_AP = W_MMA + 3;
+  constexpr int W_MID = PC::W_MID, W_MMA = PC::W_MMA, W_WP = W_MMA + 1, W_AP = W_MMA + 2;
   // fp32 stream slabs of the x ring: kSlabBytes of whole rows each (rows are contiguous in HBM -> one 1-D bulk copy)
   constexpr int kSlabBytes = 8192, SLAB_ROWS = kSlabBytes / (C * 4);
-  static_assert(4 * C * NBUF <= 512 && NEPI % 4 == 0 && kProdT % (C / 4) == 0, "bad configuration");
+  static_assert(4 * C * NBUF <= 512 && NEPI % 4 == 0 && kProdT % (C / 8) == 0 && SLAB_ROWS % (kProdT / (C / 8)) == 0, "bad configuration");
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA1 = smem;
   uint8_t* sA2 = sA1 + NA1 * A1_BYTES;
@@ -151,7 +157,10 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
     constexpr int QPR = C / 8;                     // threads per row
     constexpr int RPP = kProdT / QPR;              // rows per pass of all producer threads
     const int pt = threadIdx.x - W_AP * 32;
-    const int ch = pt % QPR, r_in = pt / QPR;
+    const int ch = pt % QPR, r_raw = pt / QPR;
+    // swap bits 1 and 2 of the row index: the 4 rows of a warp (C = 64) then cover both (row & 4) halves of the
+    // swizzle pattern and the 8-byte stores spread over all 32 banks
+    const int r_in = (r_raw & ~6) | ((r_raw & 2) << 1) | ((r_raw & 4) >> 1);
     const int cA = 4 * ch, cB = C / 2 + 4 * ch;    // first channel of the two pieces
     float alA[4], iaA[4], alB[4], iaB[4];
 #pragma unroll
@@ -175,19 +184,26 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
       for (int sl = 0; sl < n_slab; ++sl) {
         mbar_wait(&x_full[xs], xph);
         const uint32_t xsrc = smem_u32(sX + xs * kSlabBytes);
+        // all shared-memory reads of this slab first (the volatile asm statements keep program order, so
+        // interleaving loads and stores task by task would serialise the tasks), then convert and store
+        constexpr int TPS = SLAB_ROWS / RPP;          // tasks per thread per slab
+        float4 va[TPS], vb[TPS];
 #pragma unroll
-        for (int rr = r_in; rr < SLAB_ROWS; rr += RPP) {
-          const int r = sl * SLAB_ROWS + rr;
+        for (int t = 0; t < TPS; ++t) {
+          const int rr = r_in + t * RPP;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(va[t].x), "=f"(va[t].y), "=f"(va[t].z), "=f"(va[t].w)
+                       : "r"(xsrc + (uint32_t)(rr * C * 4 + cA * 4)));
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(vb[t].x), "=f"(vb[t].y), "=f"(vb[t].z), "=f"(vb[t].w)
+                       : "r"(xsrc + (uint32_t)(rr * C * 4 + cB * 4)));
+        }
+#pragma unroll
+        for (int t = 0; t < TPS; ++t) {
+          const int r = sl * SLAB_ROWS + r_in + t * RPP;
           if (r < R1) {
-            float4 va, vb;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(va.x), "=f"(va.y), "=f"(va.z), "=f"(va.w)
-                         : "r"(xsrc + (uint32_t)(rr * C * 4 + cA * 4)));
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(vb.x), "=f"(vb.y), "=f"(vb.z), "=f"(vb.w)
-                         : "r"(xsrc + (uint32_t)(rr * C * 4 + cB * 4)));
-            float ya[4] = {snake_f(va.x, alA[0], iaA[0]), snake_f(va.y, alA[1], iaA[1]), snake_f(va.z, alA[2], iaA[2]),
-                           snake_f(va.w, alA[3], iaA[3])};
-            float yb[4] = {snake_f(vb.x, alB[0], iaB[0]), snake_f(vb.y, alB[1], iaB[1]), snake_f(vb.z, alB[2], iaB[2]),
-                           snake_f(vb.w, alB[3], iaB[3])};
+            float ya[4] = {snake_f(va[t].x, alA[0], iaA[0]), snake_f(va[t].y, alA[1], iaA[1]), snake_f(va[t].z, alA[2], iaA[2]),
+                           snake_f(va[t].w, alA[3], iaA[3])};
+            float yb[4] = {snake_f(vb[t].x, alB[0], iaB[0]), snake_f(vb[t].y, alB[1], iaB[1]), snake_f(vb[t].z, alB[2], iaB[2]),
+                           snake_f(vb[t].w, alB[3], iaB[3])};
             const uint2 pa = Pack4<ActT>::pack(ya), pb = Pack4<ActT>::pack(yb);
             const uint32_t rowb = a1 + (uint32_t)r * 128u;
             const uint32_t swz = (uint32_t)(r & 7);
@@ -202,44 +218,75 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
       if (pt == 0) trace_ev(a.trace, i, 1);
       mbar_arrive(&a1_full[b1]);
     }
-  } else if (warp == W_XP) {
-    // ---------------- x loader: streams the tiles' fp32 rows (with halo) into the ring, slab by slab
+  } else if (warp == W_WP) {
+    // ---------------- loader: ONE thread feeds both rings by polling (non-blocking test_wait), so neither ring
+    // can stall the other.  Weights: chunk order mirrors the MMA issue order.  x: the tiles' fp32 rows (with
+    // halo), slab by slab (whole rows are contiguous in HBM -> 1-D bulk copies).
     if (lane == 0) {
+      auto test = [](uint64_t* bar, uint32_t parity) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        return done != 0;
+      };
       const int R1 = 256 + 2 * H1;
+      // weight ring state: step s, pass, chunk c
+      uint32_t ws = 0, wph = 0;
+      int w_s = 0, w_pass = 0, w_c = 0;
+      auto w_skip = [&]() {            // advance (w_s, w_pass) to the next existing conv of the issue order
+        while (w_s < n_my + SKEW && (w_pass == 0 ? w_s >= n_my : w_s < SKEW)) {
+          if (++w_pass == 2) { w_pass = 0; ++w_s; }
+        }
+      };
+      w_skip();
+      // x ring state: tile xi, first row xr of the next slab
       uint32_t xs = 0, xph = 0;
-      for (int i = 0; i < n_my; ++i) {
-        const ConvTile tl = a.tiles[blockIdx.x + i * gridDim.x];
-        const float* src = p.x_in + (tl.in_row0 + tl.q0 - H1 - H2) * (long long)C;
-        for (int r0 = 0; r0 < R1; r0 += SLAB_ROWS) {
-          const int rows = R1 - r0 < SLAB_ROWS ? R1 - r0 : SLAB_ROWS;
-          mbar_wait(&x_empty[xs], xph ^ 1u);
+      int xi = 0, xr = 0;
+      const float* xsrc = nullptr;
+      const long long t0 = clock64();
+      while (w_s < n_my + SKEW || xi < n_my) {
+        bool progress = false;
+        if (w_s < n_my + SKEW && test(&w_empty[ws], wph ^ 1u)) {
+          const uint8_t* wsrc = w_pass == 0 ? p.w1 : p.w2;
+          if (a.dbg & 1) mbar_arrive(&w_full[ws]);
+          else {
+            mbar_arrive_expect_tx(&w_full[ws], W_BYTES);
+            bulk_g2s(sW + ws * W_BYTES, wsrc + (size_t)w_c * W_BYTES, W_BYTES, &w_full[ws]);
+          }
+          if (++ws == (uint32_t)W_ST) { ws = 0; wph ^= 1u; }
+          if (++w_c == nchunks) {
+            w_c = 0;
+            if (++w_pass == 2) { w_pass = 0; ++w_s; }
+            w_skip();
+          }
+          progress = true;
+        }
+        if (xi < n_my && test(&x_empty[xs], xph ^ 1u)) {
+          if (xr == 0) {
+            const ConvTile tl = a.tiles[blockIdx.x + xi * gridDim.x];
+            xsrc = p.x_in + (tl.in_row0 + tl.q0 - H1 - H2) * (long long)C;
+          }
+          const int rows = R1 - xr < SLAB_ROWS ? R1 - xr : SLAB_ROWS;
           if (a.dbg & 2) mbar_arrive(&x_full[xs]);
           else {
             mbar_arrive_expect_tx(&x_full[xs], (uint32_t)(rows * C * 4));
-            bulk_g2s(sX + xs * kSlabBytes, src + (long long)r0 * C, (uint32_t)(rows * C * 4), &x_full[xs]);
+            bulk_g2s(sX + xs * kSlabBytes, xsrc + (long long)xr * C, (uint32_t)(rows * C * 4), &x_full[xs]);
           }
           if (++xs == (uint32_t)NSLAB) { xs = 0; xph ^= 1u; }
+          xr += SLAB_ROWS;
+          if (xr >= R1) { xr = 0; ++xi; }
+          progress = true;
+        }
+        if (!progress) {
+          __nanosleep(32);
+          if (clock64() - t0 > 8000000000LL) __trap();     // a protocol bug must fault the launch, not hang
         }
       }
-    }
-  } else if (warp == W_WP) {
-    // ---------------- weight producer: the chunk order mirrors the MMA issue order
-    if (lane == 0) {
-      uint32_t ws = 0, ph = 0;
-      for (int s = 0; s < n_my + SKEW; ++s)
-        for (int pass = 0; pass < 2; ++pass) {
-          if (pass == 0 ? s >= n_my : s < SKEW) continue;
-          const uint8_t* wsrc = pass == 0 ? p.w1 : p.w2;
-          for (int c = 0; c < nchunks; ++c) {
-            mbar_wait(&w_empty[ws], ph ^ 1u);
-            if (a.dbg & 1) mbar_arrive(&w_full[ws]);
-            else {
-              mbar_arrive_expect_tx(&w_full[ws], W_BYTES);
-              bulk_g2s(sW + ws * W_BYTES, wsrc + (size_t)c * W_BYTES, W_BYTES, &w_full[ws]);
-            }
-            if (++ws == (uint32_t)W_ST) { ws = 0; ph ^= 1u; }
-          }
-        }
     }
   } else if (warp == W_MMA) {
     // ---------------- MMA issuer: conv1(s) then conv2(s - SKEW)
@@ -371,15 +418,15 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
     auto fin_out = [&](const ConvTile& tl, int blk, int b) {
       int mb, c0, nvalid; long long idx0;
       blk_geom(tl, blk, mb, c0, idx0, nvalid);
-      // two 16-column loads: the prefetched residual registers of fin_issue are live across this function
+      // 8-column loads: the prefetched residual registers of fin_issue are live across this function
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        uint32_t v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((NBUF + b) * ACC_COLS + mb * C + c0 + hh * 16), v);
+      for (int hh = 0; hh < 4; ++hh) {
+        uint32_t v[8];
+        tmem_ld8(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((NBUF + b) * ACC_COLS + mb * C + c0 + hh * 8), v);
         tmem_ld_wait();
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
-          *reinterpret_cast<float4*>(stage + lane * kStageLd + hh * 16 + g * 4) =
+        for (int g = 0; g < 2; ++g)
+          *reinterpret_cast<float4*>(stage + lane * kStageLd + hh * 8 + g * 4) =
               make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]),
                           __uint_as_float(v[4 * g + 3]));
       }
@@ -578,10 +625,10 @@ int launch_pair_tc(const ConvArgs& a_in, const ConvLayer& c1, const ConvLayer& c
   const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(C >> 3) << 17) | ((128u >> 4) << 24);
   int rc;
   if (act_elem == ELEM_F16)
-    rc = C == 64 ? tc::launch_pair_c<64, 2, 2, 1, 4, 8, 4, 5, __half>(a, p, idesc, grid, st)
+    rc = C == 64 ? tc::launch_pair_c<64, 2, 2, 1, 4, 8, 2, 5, __half>(a, p, idesc, grid, st)
                  : tc::launch_pair_c<128, 1, 1, 1, 3, 8, 4, 3, __half>(a, p, idesc, grid, st);
   else
-    rc = C == 64 ? tc::launch_pair_c<64, 2, 2, 1, 4, 8, 4, 5, __nv_bfloat16>(a, p, idesc, grid, st)
+    rc = C == 64 ? tc::launch_pair_c<64, 2, 2, 1, 4, 8, 2, 5, __nv_bfloat16>(a, p, idesc, grid, st)
                  : tc::launch_pair_c<128, 1, 1, 1, 3, 8, 4, 3, __nv_bfloat16>(a, p, idesc, grid, st);
   if (tracing && rc == VT_OK) {
     std::vector<long long> h(tc::kTraceTiles * tc::kTraceEvents);

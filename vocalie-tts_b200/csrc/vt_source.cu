@@ -81,6 +81,13 @@ __device__ __forceinline__ float2 box_muller(unsigned a, unsigned b) {
   return make_float2(r * c, r * s);
 }
 
+// sin(t) for t in [-pi, 3pi]: one explicit reduction to [-pi, pi], then the SFU sine (absolute error
+// ~5e-7 there: three orders below the fp16 operand rounding of everything the source feeds).
+__device__ __forceinline__ float sin_2pi_range(float t) {
+  t = fmaf(-6.283185307179586f, rintf(t * 0.15915494309189535f), t);
+  return __sinf(t);
+}
+
 // One thread per output sample: 9 harmonics, noise mix, Linear(9->1), tanh.
 __global__ void __launch_bounds__(256)
 k_sine_source(const float* __restrict__ f0, const int* __restrict__ mel_off, const int* __restrict__ T, int B,
@@ -137,7 +144,7 @@ k_sine_source(const float* __restrict__ f0, const int* __restrict__ mel_off, con
       const float c = __double2float_rn(c64);
       const float frac = c - truncf(c);                       // torch `% 1` on a non-negative value
       const float theta = __fmul_rn(frac, 6.283185307179586f);  // 2*pi as an fp32 scalar
-      const float sine = __fmul_rn(0.1f, sinf(theta + pv[h]));
+      const float sine = __fmul_rn(0.1f, sin_2pi_range(theta + pv[h]));
       const float v = __fadd_rn(__fmul_rn(sine, uv), __fmul_rn(namp, z[h]));
       acc = fmaf(v, lw[h], acc);
     }
@@ -194,7 +201,6 @@ k_stft(const float* __restrict__ s, const int* __restrict__ mel_off, const int* 
       if (i >= L) i = 2 * (L - 1) - i;
       x[n] = sb[i] * c_hann16[n];
     }
-    float* dst = spec + (off2[b] + f) * kSpecCh;
     float outv[kSpecCh];
 #pragma unroll
     for (int m = 0; m <= kNfft / 2; ++m) {
@@ -210,9 +216,12 @@ k_stft(const float* __restrict__ s, const int* __restrict__ mel_off, const int* 
     }
 #pragma unroll
     for (int c = kNfft + 2; c < kSpecCh; ++c) outv[c] = 0.0f;
+    if (spec) {
+      float* dst = spec + (off2[b] + f) * kSpecCh;
 #pragma unroll
-    for (int c = 0; c < kSpecCh; c += 4)
-      *reinterpret_cast<float4*>(dst + c) = make_float4(outv[c], outv[c + 1], outv[c + 2], outv[c + 3]);
+      for (int c = 0; c < kSpecCh; c += 4)
+        *reinterpret_cast<float4*>(dst + c) = make_float4(outv[c], outv[c + 1], outv[c + 2], outv[c + 3]);
+    }
     if (spec_op) {
       uint4* od = reinterpret_cast<uint4*>(spec_op + (off2[b] + f) * kSpecOp);
 #pragma unroll
