@@ -34,6 +34,14 @@ struct PairArgs {
 
 namespace tc {
 
+// Residual handling of the fin epilogue.  1: the fin warps preload D2 with x + b2 (+ extras) for the tile that
+// uses the buffer next (tcgen05.st; conv2 accumulates on top): no load latency in the epilogue, but two more
+// shared-memory transposition passes per block.  0: the residual rows are prefetched into registers two blocks
+// ahead and added in the coalesced phase of the output pass: half the shared-memory traffic of the epilogue -
+// the L1/shared data pipe is the saturated unit of this kernel.
+// Measured (B200, 64 x 500 frames): preload wins wherever the tile is long (k >= 7, C = 128: the weight stream
+// makes epilogue load latency very long), register prefetch wins for the short k = 3 tiles at C = 64.
+
 constexpr int kPairRA1 = 312;   // A1 rows: 256 + (k-1)*dil <= 306, multiple of 8
 constexpr int kPairRA2 = 272;   // A2 rows: 256 + (k-1) <= 266, multiple of 8
 
@@ -79,7 +87,7 @@ struct PairCfg {
   static constexpr int WARPS = W_MMA + 2 + NPROD;      // + MMA warp, loader warp (weights and x ring)
 };
 
-template <int C, int NBUF, int NA1, int NA2, int W_ST, int NEPI, int NPROD, int NSLAB, int EM, typename ActT>
+template <int C, int NBUF, int NA1, int NA2, int W_ST, int NEPI, int NPROD, int NSLAB, int EM, bool kPreload, typename ActT>
 __global__ void __launch_bounds__(PairCfg<C, NBUF, NEPI, NPROD>::WARPS * 32, 1)
 k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
   using PC = PairCfg<C, NBUF, NEPI, NPROD>;
@@ -309,7 +317,8 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
         uint64_t* dst_full = pass == 0 ? &d1_full[b] : &d2_full[b];
         // conv1 needs D1 drained by the mid epilogue; conv2 needs D2 preloaded by the fin warps (x + b2 + ...)
         if (pass == 0) mbar_wait(&d1_empty[b], (u & 1u) ^ 1u);
-        else mbar_wait(&d2i_full[b], u & 1u);
+        else if (kPreload) mbar_wait(&d2i_full[b], u & 1u);
+        else mbar_wait(&d2i_full[b], (u & 1u) ^ 1u);       // plain "D2 drained" barrier in register-prefetch mode
         mbar_wait(src_full, us & 1u);
         tc_fence_after();
         if (lane == 0) trace_ev(a.trace, i, 6 + 2 * pass);
@@ -317,7 +326,7 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
         const uint32_t a_tile = pass == 0 ? a1_lo0 + (uint32_t)bs * (uint32_t)(A1_BYTES >> 4) : a2_lo0 + (uint32_t)bs * (uint32_t)(A2_BYTES >> 4);
         const uint32_t blk16 = (uint32_t)(pass == 0 ? kPairRA1 : kPairRA2) * 8u;   // 64-channel block stride, 16-byte units
         const uint32_t tap16 = (uint32_t)(pass == 0 ? p.dil : 1) * 8u;              // one tap = dil rows of 128 B
-        uint32_t acc = pass == 0 ? 0u : 1u;
+        uint32_t acc = (pass == 1 && kPreload) ? 1u : 0u;
         for (int j = 0; j < p.k; ++j) {
           uint32_t a_chunk = a_tile + (uint32_t)j * tap16;
 #pragma unroll 1
@@ -449,8 +458,75 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
       }
       __syncwarp();
     };
+    // ---- register-prefetch mode: block sequence n = tile * BPW + k of this warp; residual rows of block n + PF are
+    // requested right after block n has been consumed
+    constexpr int BPW = NBLK / (NEPI / 4), PF = C == 64 ? 1 : 2;    // 96 registers at C = 64 hold one block in flight
+    static_assert(BPW % PF == 0, "prefetch slots must divide the blocks per warp");
+    auto pf_issue = [&](int n, float4 (&pr)[8]) {
+      const int ti = n / BPW;
+      if (ti >= n_my) return;
+      const ConvTile tl = a.tiles[blockIdx.x + ti * gridDim.x];
+      int mb, c0, nvalid; long long idx0;
+      blk_geom(tl, grp + (n - ti * BPW) * (NEPI / 4), mb, c0, idx0, nvalid);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        pr[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (4 * q < nvalid && !(a.dbg & 32)) pr[q] = ldg_f4(a.res1 + idx0 + (long long)q * 4 * C);
+      }
+    };
+    auto fin_out_res = [&](const ConvTile& tl, int blk, int b, float4 (&pr)[8]) {
+      int mb, c0, nvalid; long long idx0;
+      blk_geom(tl, blk, mb, c0, idx0, nvalid);
+#pragma unroll
+      for (int hh = 0; hh < 4; ++hh) {
+        uint32_t v[8];
+        tmem_ld8(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((NBUF + b) * ACC_COLS + mb * C + c0 + hh * 8), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+          *reinterpret_cast<float4*>(stage + lane * kStageLd + hh * 8 + g * 4) =
+              make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]),
+                          __uint_as_float(v[4 * g + 3]));
+      }
+      __syncwarp();
+      if (!(a.dbg & 8)) {
+        const float4 bias = *reinterpret_cast<const float4*>(a.bias + c0 + sub * 4);
+        const bool accum = kAccum && a.out_accum;
+        const float inv = 1.0f / a.out_scale;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (4 * q >= nvalid) continue;
+          const long long idx = idx0 + (long long)q * 4 * C;
+          const float4 acc = *reinterpret_cast<const float4*>(stage + (q * 4 + rsub) * kStageLd + sub * 4);
+          float4 t = make_float4(acc.x + bias.x + pr[q].x, acc.y + bias.y + pr[q].y, acc.z + bias.z + pr[q].z,
+                                 acc.w + bias.w + pr[q].w);
+          if constexpr (kRes2) {
+            const float4 r2 = ldg_f4(a.res2 + idx);
+            t.x += r2.x; t.y += r2.y; t.z += r2.z; t.w += r2.w;
+          }
+          if (accum) {
+            const float4 pv = *reinterpret_cast<const float4*>(a.out + idx);
+            t.x = fmaf(pv.x, inv, t.x); t.y = fmaf(pv.y, inv, t.y); t.z = fmaf(pv.z, inv, t.z); t.w = fmaf(pv.w, inv, t.w);
+          }
+          const float4 o = make_float4(t.x * a.out_scale, t.y * a.out_scale, t.z * a.out_scale, t.w * a.out_scale);
+          if (!(a.dbg & 64)) *reinterpret_cast<float4*>(a.out + idx) = o;
+          if constexpr ((EM & EM_OACT) != 0) {
+            const float sl = a.act[0].slope;
+            float y[4] = {o.x > 0.f ? o.x : o.x * sl, o.y > 0.f ? o.y : o.y * sl, o.z > 0.f ? o.z : o.z * sl,
+                          o.w > 0.f ? o.w : o.w * sl};
+            *reinterpret_cast<uint2*>(reinterpret_cast<ActT*>(a.act[0].dst) + idx) = Pack4<ActT>::pack(y);
+          }
+        }
+      }
+      __syncwarp();
+    };
+    float4 pfr[PF][8];
+    if (do_fin && !kPreload) {
+#pragma unroll
+      for (int k = 0; k < PF; ++k) pf_issue(k, pfr[k]);
+    }
     // prologue: preload D2 for the first NBUF tiles
-    if (do_fin) {
+    if (do_fin && kPreload) {
       for (int j = 0; j < NBUF && j < n_my; ++j) {
         const ConvTile tl = a.tiles[blockIdx.x + j * gridDim.x];
 #pragma unroll 1
@@ -515,19 +591,30 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
         mbar_wait(&d2_full[b], u & 1u);
         tc_fence_after();
         if (warp == 0 && lane == 0) trace_ev(a.trace, i, 4);
-        const bool has_next = i + NBUF < n_my;
-        const ConvTile tnext = has_next ? a.tiles[blockIdx.x + (i + NBUF) * gridDim.x] : tile;
+        if constexpr (kPreload) {
+          const bool has_next = i + NBUF < n_my;
+          const ConvTile tnext = has_next ? a.tiles[blockIdx.x + (i + NBUF) * gridDim.x] : tile;
 #pragma unroll 1
-        for (int blk = grp; blk < NBLK && !(a.dbg & 4); blk += NEPI / 4) {
-          float4 pre[8];
-          if (has_next) fin_issue(tnext, blk, pre);
-          fin_out(tile, blk, b);
-          if (has_next) fin_store(tnext, blk, b, pre);
+          for (int blk = grp; blk < NBLK && !(a.dbg & 4); blk += NEPI / 4) {
+            float4 pre[8];
+            if (has_next) fin_issue(tnext, blk, pre);
+            fin_out(tile, blk, b);
+            if (has_next) fin_store(tnext, blk, b, pre);
+          }
+          if (has_next) tmem_st_wait();
+          tc_fence_before();
+          if (warp == 0 && lane == 0) trace_ev(a.trace, i, 5);
+          if (has_next) mbar_arrive(&d2i_full[b]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < BPW; ++k) {
+            if (!(a.dbg & 4)) fin_out_res(tile, grp + k * (NEPI / 4), b, pfr[k % PF]);
+            pf_issue(i * BPW + k + PF, pfr[k % PF]);
+          }
+          tc_fence_before();
+          if (warp == 0 && lane == 0) trace_ev(a.trace, i, 5);
+          mbar_arrive(&d2i_full[b]);
         }
-        if (has_next) tmem_st_wait();
-        tc_fence_before();
-        if (warp == 0 && lane == 0) trace_ev(a.trace, i, 5);
-        if (has_next) mbar_arrive(&d2i_full[b]);
         // combined mode: the staging lives in the A2 tile; nobody may start mid(i+1) before everyone left fin(i)
         if (kCombined) asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");
       }
@@ -542,7 +629,7 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
   }
 }
 
-template <int C, int NBUF, int NA1, int NA2, int W_ST, int NEPI, int NPROD, int NSLAB, int EM, typename ActT>
+template <int C, int NBUF, int NA1, int NA2, int W_ST, int NEPI, int NPROD, int NSLAB, int EM, bool kPreload, typename ActT>
 int launch_pair_em(const ConvArgs& a, const PairArgs& p, uint32_t idesc, int grid, cudaStream_t st) {
   constexpr int CB = C / 64;
   using PC = PairCfg<C, NBUF, NEPI, NPROD>;
@@ -553,12 +640,19 @@ int launch_pair_em(const ConvArgs& a, const PairArgs& p, uint32_t idesc, int gri
   static_assert(!PC::kCombined || NEPI * 32 * kStageLd * 4 <= CB * kPairRA2 * 128, "fin staging must fit the A2 tile");
   static bool configured = false;
   if (!configured) {
-    VT_CUDA_OK(cudaFuncSetAttribute(k_pair_tc<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, ActT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    VT_CUDA_OK(cudaFuncSetAttribute(k_pair_tc<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, kPreload, ActT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  k_pair_tc<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, ActT><<<grid, PC::WARPS * 32, smem, st>>>(a, p, idesc);
+  k_pair_tc<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, kPreload, ActT><<<grid, PC::WARPS * 32, smem, st>>>(a, p, idesc);
   VT_LAUNCHED();
   return VT_OK;
+}
+
+template <int C, int NBUF, int NA1, int NA2, int W_ST, int NEPI, int NPROD, int NSLAB, int EM, typename ActT>
+int launch_pair_pre(const ConvArgs& a, const PairArgs& p, uint32_t idesc, int grid, cudaStream_t st) {
+  if (C == 64 && p.k == 3)
+    return launch_pair_em<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, false, ActT>(a, p, idesc, grid, st);
+  return launch_pair_em<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, true, ActT>(a, p, idesc, grid, st);
 }
 
 template <int C, int NBUF, int NA1, int NA2, int W_ST, int NEPI, int NPROD, int NSLAB, typename ActT>
@@ -568,12 +662,12 @@ int launch_pair_c(const ConvArgs& a, const PairArgs& p, uint32_t idesc, int grid
   VT_REQUIRE(oact || !a.act[0].dst, "pair_tc: only a leaky-ReLU output copy is supported");
   if (a.res2) {
     VT_REQUIRE(!oact && !a.out_accum && a.out_scale == 1.0f, "pair_tc: unsupported epilogue with two residuals");
-    return launch_pair_em<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM_RES1 | EM_RES2 | EM_OUT, ActT>(a, p, idesc, grid, st);
+    return launch_pair_pre<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM_RES1 | EM_RES2 | EM_OUT, ActT>(a, p, idesc, grid, st);
   }
-  if (oact) return launch_pair_em<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM_RES1 | EM_OUT | EM_ACCUM | EM_OACT, ActT>(a, p, idesc, grid, st);
+  if (oact) return launch_pair_pre<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM_RES1 | EM_OUT | EM_ACCUM | EM_OACT, ActT>(a, p, idesc, grid, st);
   if (a.out_accum || a.out_scale != 1.0f)
-    return launch_pair_em<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM_RES1 | EM_OUT | EM_ACCUM, ActT>(a, p, idesc, grid, st);
-  return launch_pair_em<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM_RES1 | EM_OUT, ActT>(a, p, idesc, grid, st);
+    return launch_pair_pre<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM_RES1 | EM_OUT | EM_ACCUM, ActT>(a, p, idesc, grid, st);
+  return launch_pair_pre<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM_RES1 | EM_OUT, ActT>(a, p, idesc, grid, st);
 }
 
 }  // namespace tc
