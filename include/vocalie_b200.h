@@ -130,6 +130,14 @@ int vt_post_process(const float* audio, const int64_t* seg_off, int n_seg, int64
 int vt_pcm16_encode(const float* in, int16_t* out, int64_t n, void* stream);
 int vt_pcm16_decode(const int16_t* in, float* out, int64_t n, void* stream);
 
+/* RMS helper the reference uses to validate clips (tts_backends/cosyvoice_backend.py:103,
+ * tests/test_qwen3_runner.py:58): rms_out[i] = sqrt(mean(float64(x)^2)) over segment i, 0 for an empty
+ * segment.  float64 accumulation in a fixed reduction order (deterministic; equal to numpy's pairwise
+ * sum to ~1e-15 relative).  workspace >= VT_RMS_PARTIALS * n_seg doubles. */
+#define VT_RMS_PARTIALS 64
+int vt_rms(const float* audio, const int64_t* seg_off, int n_seg, double* rms_out, void* workspace,
+           int64_t workspace_bytes, void* stream);
+
 /* ---- HiFT vocoder: upstream chatterbox/models/s3gen/hifigan.py ------------------------- */
 
 typedef struct vt_hift vt_hift;   /* opaque handle: packed weights + layer plan */

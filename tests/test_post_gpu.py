@@ -174,6 +174,25 @@ def test_batched_segments_vs_oracle(vt):
     assert pos == r.total
 
 
+def test_rms_helper_matches_reference_definition(vt):
+    """sqrt(mean(float64(x)^2)) - the reference's clip-validation helper (tts_backends/cosyvoice_backend.py:103,
+    tests/test_qwen3_runner.py:58).  float64 accumulation in another order than numpy's pairwise sum: equal to
+    1e-13 relative (stated tolerance; the reduction itself is deterministic, checked by running it twice)."""
+    rng = np.random.default_rng(23)
+    lens = [0, 1, 3, 4, 5, 1023, 24000, 100001, 7, 480000]
+    chunks = [(rng.standard_normal(n) * 0.3).astype(np.float32) for n in lens]
+    seg_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    flat = np.concatenate(chunks)
+    got = vt.rms_segments(flat, seg_off)
+    again = vt.rms_segments(flat, seg_off)
+    assert np.array_equal(got.view(np.uint64), again.view(np.uint64))
+    for i, c in enumerate(chunks):
+        want = po.rms(c)
+        assert abs(got[i] - want) <= 1e-13 * max(want, 1e-30), (i, got[i], want)
+    assert vt.rms(np.zeros(0, np.float32)) == 0.0
+    assert vt.rms(np.full(1000, 0.5, np.float32)) == 0.5        # reference test value: a constant clip
+
+
 def test_full_size_properties(vt):
     """cfg3-sized stitch (512 chunks x 10 s, gap 250 ms): size-independent properties -
     exact length, gaps are zero, interior samples untouched, idempotent trim."""

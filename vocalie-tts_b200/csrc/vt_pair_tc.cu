@@ -650,8 +650,9 @@ int launch_pair_em(const ConvArgs& a, const PairArgs& p, uint32_t idesc, int gri
 
 template <int C, int NBUF, int NA1, int NA2, int W_ST, int NEPI, int NPROD, int NSLAB, int EM, typename ActT>
 int launch_pair_pre(const ConvArgs& a, const PairArgs& p, uint32_t idesc, int grid, cudaStream_t st) {
-  if (C == 64 && p.k == 3)
-    return launch_pair_em<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, false, ActT>(a, p, idesc, grid, st);
+  if constexpr (C == 64) {
+    if (p.k == 3) return launch_pair_em<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, false, ActT>(a, p, idesc, grid, st);
+  }
   return launch_pair_em<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, true, ActT>(a, p, idesc, grid, st);
 }
 

@@ -526,6 +526,50 @@ static int grid_x_for(int n_seg, int64_t max_len, int tile) {
 
 using namespace vt;
 
+// ---- RMS helper: sqrt(mean(float64(x)^2)) per segment, fixed reduction order ---------------------------
+// block (p, seg) sums the 128-bit-aligned tiles p, p + P, p + 2P, ... of the segment in float64; thread
+// partials are combined by a fixed shuffle tree, block partials by k_rms_final in index order.
+namespace vt {
+__global__ void __launch_bounds__(kThreads)
+k_rms_partial(const float* __restrict__ audio, const int64_t* __restrict__ seg_off, double* __restrict__ partial) {
+  __shared__ double sh[kThreads / 32];
+  const int seg = blockIdx.y;
+  const long long a = seg_off[seg], b = seg_off[seg + 1];
+  double acc = 0.0;
+  const long long A = a & ~3LL;                               // float4-aligned start
+  const long long n4 = (b - A + 3) / 4;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n4; i += (long long)gridDim.x * kThreads) {
+    const long long idx = A + i * 4;
+    if (idx >= a && idx + 4 <= b) {
+      const float4 v = ldg_stream4(audio + idx);
+      acc += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+    } else {
+      for (int e = 0; e < 4; ++e)
+        if (idx + e >= a && idx + e < b) { const double x = audio[idx + e]; acc += x * x; }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < kThreads / 32; ++w) t += sh[w];
+    partial[(long long)seg * gridDim.x + blockIdx.x] = t;
+  }
+}
+
+__global__ void k_rms_final(const int64_t* __restrict__ seg_off, int n_seg, const double* __restrict__ partial,
+                            double* __restrict__ out) {
+  const int seg = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (seg >= n_seg || (threadIdx.x & 31) != 0) return;
+  double t = 0.0;
+  for (int p = 0; p < VT_RMS_PARTIALS; ++p) t += partial[(long long)seg * VT_RMS_PARTIALS + p];
+  const long long n = seg_off[seg + 1] - seg_off[seg];
+  out[seg] = n > 0 ? sqrt(t / (double)n) : 0.0;
+}
+}  // namespace vt
+
 extern "C" {
 
 int64_t vt_post_workspace_bytes(int n_seg, int64_t n_samples) {
@@ -655,6 +699,20 @@ int vt_snap_zero_crossing(const float* audio, const int64_t* seg_off, int n_seg,
   launch_counter() = 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
   k_snap_only<<<n_seg, kThreads, 0, st>>>(audio, seg_off, idx_in, radius_samples, idx_out);
+  VT_LAUNCHED();
+  return VT_OK;
+}
+
+int vt_rms(const float* audio, const int64_t* seg_off, int n_seg, double* rms_out, void* workspace, int64_t workspace_bytes,
+           void* stream_v) {
+  VT_REQUIRE(n_seg >= 0 && n_seg <= 65535, "vt_rms: n_seg must be in [0, 65535]");
+  if (n_seg == 0) return VT_OK;
+  VT_REQUIRE(audio && seg_off && rms_out && workspace, "vt_rms: NULL argument");
+  VT_REQUIRE(workspace_bytes >= (int64_t)n_seg * VT_RMS_PARTIALS * 8, "vt_rms: workspace too small");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
+  k_rms_partial<<<dim3(VT_RMS_PARTIALS, n_seg), kThreads, 0, st>>>(audio, seg_off, reinterpret_cast<double*>(workspace));
+  VT_LAUNCHED();
+  k_rms_final<<<(n_seg + 7) / 8, 256, 0, st>>>(seg_off, n_seg, reinterpret_cast<const double*>(workspace), rms_out);
   VT_LAUNCHED();
   return VT_OK;
 }

@@ -332,3 +332,26 @@ def pcm16_encode(audio: np.ndarray) -> np.ndarray:
     q = torch.empty(x.size, dtype=torch.int16, device="cuda")
     check(lib.vt_pcm16_encode(_ptr(xd), _ptr(q), x.size, _stream(torch)), "vt_pcm16_encode")
     return q.cpu().numpy()
+
+
+def rms(audio: np.ndarray) -> float:
+    """``sqrt(mean(x.astype(float64) ** 2))`` on the GPU - the helper the reference uses to validate
+    clips (tts_backends/cosyvoice_backend.py:103, tests/test_qwen3_runner.py:58); 0.0 for an empty array."""
+    return float(rms_segments(audio, [0, int(np.asarray(audio).size)])[0])
+
+
+def rms_segments(audio: np.ndarray, seg_off: Sequence[int]) -> np.ndarray:
+    """Per-segment RMS (float64) of a flat float32 buffer; segment ``i`` is ``audio[seg_off[i]:seg_off[i+1]]``."""
+    torch = _torch()
+    lib = _lib.load_library()
+    x = _as_f32(audio)
+    off = np.asarray(seg_off, dtype=np.int64)
+    n_seg = off.size - 1
+    if n_seg <= 0:
+        return np.zeros(0, np.float64)
+    xd = torch.from_numpy(np.ascontiguousarray(x)).cuda() if x.size else torch.zeros(4, dtype=torch.float32, device="cuda")
+    od = torch.from_numpy(off).cuda()
+    out = torch.empty(n_seg, dtype=torch.float64, device="cuda")
+    ws = torch.empty(n_seg * 64, dtype=torch.float64, device="cuda")
+    check(lib.vt_rms(_ptr(xd), _ptr(od), n_seg, _ptr(out), _ptr(ws), ws.numel() * 8, _stream(torch)), "vt_rms")
+    return out.cpu().numpy()
