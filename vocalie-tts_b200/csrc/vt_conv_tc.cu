@@ -51,8 +51,8 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
   uint8_t* sW = sA + A_ST * K::A_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sW + W_ST * K::W_BYTES);
   uint64_t* a_full = bars;
-  uint64_t* a_empty = a_full + A_ST;
-  uint64_t* w_full = a_empty + A_ST;
+  uint64_t* a_empty = a_full + A_ST * CB;        // one (full, empty) pair per 64-channel block of an A stage
+  uint64_t* w_full = a_empty + A_ST * CB;
   uint64_t* w_empty = w_full + W_ST;
   uint64_t* acc_full = w_empty + W_ST;
   uint64_t* acc_empty = acc_full + 2;
@@ -61,7 +61,7 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < A_ST; ++i) { mbar_init(&a_full[i], kProd); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < A_ST * CB; ++i) { mbar_init(&a_full[i], kProd); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < W_ST; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], NEPI * 32); }
     fence_barrier_init();
@@ -91,22 +91,32 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
       const int ab = it % A_ST;
       const uint32_t ph = (uint32_t)(it / A_ST) & 1u;
-      mbar_wait(&a_empty[ab], ph ^ 1u);
-      if (pt == 0) trace_ev(a.trace, it, 0);
       const ConvTile tile = a.tiles[t / n_nt];
       const ActT* src = in + (tile.in_row0 + tile.q0 - a.pad) * (long long)CIN;
       const uint32_t dst = smem_u32(sA + ab * K::A_BYTES);
-      for (int p = pt; p < pieces && !(a.dbg & 2); p += kProd) {
-        const int r = p / K::KC, c = p - r * K::KC;
-        const uint32_t off = kSwz ? (uint32_t)((c >> 3) * K::RA + r) * 128u + (uint32_t)(((c & 7) ^ (r & 7)) << 4)
-                                  : (uint32_t)(c * K::RA + r) * 16u;
-        cp_async16(dst + off, src + (long long)r * CIN + c * 8);
+      // one 64-channel block at a time: the MMA warp walks the blocks in the same order (block outer, taps
+      // inner) and releases each block as soon as its taps are issued, so the refill of block 0 for the next
+      // tile overlaps the MMAs of this tile's later blocks even with a single A stage
+      constexpr int KCB = (kSwz && A_ST == 1) ? 8 : K::KC;      // 16-byte chunks per row of a block
+      constexpr int NB = (kSwz && A_ST == 1) ? CB : 1;          // with two A stages whole tiles already overlap
+      const int bpieces = r_need * KCB;
+      for (int cb = 0; cb < NB; ++cb) {
+        mbar_wait(&a_empty[ab * CB + cb], ph ^ 1u);
+        if (NB == 1) for (int x = 1; x < CB; ++x) mbar_wait(&a_empty[ab * CB + x], ph ^ 1u);
+        if (pt == 0 && cb == 0) trace_ev(a.trace, it, 0);
+        for (int p = pt; p < bpieces && !(a.dbg & 2); p += kProd) {
+          const int r = p / KCB, c = cb * KCB + (p - r * KCB);
+          const uint32_t off = kSwz ? (uint32_t)((c >> 3) * K::RA + r) * 128u + (uint32_t)(((c & 7) ^ (r & 7)) << 4)
+                                    : (uint32_t)(c * K::RA + r) * 16u;
+          cp_async16(dst + off, src + (long long)r * CIN + c * 8);
+        }
+        if (pt == 0 && cb == NB - 1) trace_ev(a.trace, it, 1);
+        cp_async_wait_all();
+        fence_proxy_async();
+        if (pt == 0 && cb == NB - 1) trace_ev(a.trace, it, 2);
+        mbar_arrive(&a_full[ab * CB + cb]);
+        if (NB == 1) for (int x = 1; x < CB; ++x) mbar_arrive(&a_full[ab * CB + x]);
       }
-      if (pt == 0) trace_ev(a.trace, it, 1);
-      cp_async_wait_all();
-      fence_proxy_async();
-      if (pt == 0) trace_ev(a.trace, it, 2);
-      mbar_arrive(&a_full[ab]);
     }
   } else if (warp == W_WP) {
     // ---------------- weight producer: one bulk copy per (tap, 64-channel block) of this tile's column tile
@@ -115,7 +125,10 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const int nt = t % n_nt;
         const uint8_t* wsrc = wtc + (size_t)nt * nchunks * K::W_BYTES;
-        for (int c = 0; c < nchunks; ++c, ws = (ws + 1 == (uint32_t)W_ST ? 0u : ws + 1), ph ^= (ws == 0 ? 1u : 0u)) {
+        // issue order of the MMA warp: channel block outer, taps inner; the packed image is (tap, block)
+        for (int q = 0; q < nchunks; ++q, ws = (ws + 1 == (uint32_t)W_ST ? 0u : ws + 1), ph ^= (ws == 0 ? 1u : 0u)) {
+          const int cb = q / a.k, j = q - cb * a.k;
+          const int c = j * CB + cb;
           mbar_wait(&w_empty[ws], ph ^ 1u);
           if (a.dbg & 1) { mbar_arrive(&w_full[ws]); continue; }
           mbar_arrive_expect_tx(&w_full[ws], K::W_BYTES);
@@ -141,16 +154,17 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
       const uint32_t asph = (uint32_t)(it >> 1) & 1u;
       mbar_wait(&acc_empty[as], asph ^ 1u);
       if (lane == 0) trace_ev(a.trace, it, 3);
-      mbar_wait(&a_full[ab], aph);
-      if (lane == 0) trace_ev(a.trace, it, 4);
       tc_fence_after();
       const uint32_t d0 = tmem_base + (uint32_t)(as * K::ACC_COLS);
       const uint32_t a_tile = a_lo0 + (uint32_t)ab * (uint32_t)(K::A_BYTES >> 4);
       uint32_t acc = 0;
-      for (int j = 0; j < a.k; ++j) {
-        uint32_t a_chunk = a_tile + (uint32_t)j * tap16;
 #pragma unroll 1
-        for (int cb = 0; cb < CB; ++cb, a_chunk += (uint32_t)K::RA * 8u) {
+      for (int cb = 0; cb < CB; ++cb) {
+        mbar_wait(&a_full[ab * CB + cb], aph);
+        if (lane == 0 && cb == 0) trace_ev(a.trace, it, 4);
+        tc_fence_after();
+        uint32_t a_chunk = a_tile + (uint32_t)cb * (uint32_t)K::RA * 8u;
+        for (int j = 0; j < a.k; ++j, a_chunk += tap16) {
           mbar_wait(&w_full[ws], wph);
           tc_fence_after();
           if (elect_one()) {
@@ -169,11 +183,10 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
           acc = 1u;
           if (++ws == (uint32_t)W_ST) { ws = 0; wph ^= 1u; }
         }
+        if (elect_one()) umma_commit(&a_empty[ab * CB + cb]);     // this block's taps are issued: it may be refilled
+        __syncwarp();
       }
-      if (elect_one()) {
-        umma_commit(&a_empty[ab]);
-        umma_commit(&acc_full[as]);
-      }
+      if (elect_one()) umma_commit(&acc_full[as]);
       __syncwarp();
       if (lane == 0) trace_ev(a.trace, it, 5);
     }
@@ -211,7 +224,7 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
 template <int CIN, int NT, int MB, int A_ST, int W_ST, int NEPI, int HALO>
 constexpr int smem_bytes() {
   return A_ST * Cfg<CIN, NT, MB, HALO>::A_BYTES + W_ST * Cfg<CIN, NT, MB, HALO>::W_BYTES +
-         (2 * A_ST + 2 * W_ST + 4) * 8 + 16 + NEPI * 32 * kStageLd * 4;
+         (2 * A_ST * (CIN / 64) + 2 * W_ST + 4) * 8 + 16 + NEPI * 32 * kStageLd * 4;
 }
 
 template <int CIN, int NT, int MB, int A_ST, int W_ST, int NEPI, int HALO, int EM, typename ActT>
