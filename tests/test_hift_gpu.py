@@ -223,3 +223,40 @@ def test_bad_arguments_raise_backend_error(torch, weights):
         HiFTVocoder(sd, operand="fp32")
     with pytest.raises(ValueError):
         HiFTVocoder(weights["init"], operand="int8")
+
+
+def test_full_size_batch_cfg2_properties(torch, weights, vocoders):
+    """BASELINE.json configs[1] at full size (64 chunks x 500 frames, fp16 operands): size-independent properties
+    for every chunk, oracle parity for one chunk drawn from the middle of the packed batch, and bit equality of
+    another chunk with the same chunk run alone (tiling / packing independence)."""
+    B, T = 64, 500
+    L = 480 * T
+    voc = vocoders("unit", "fp16")
+    mels = [H.synth_mel(T, 1001, b) for b in range(B)]
+    mel, Ts = voc.pack_mels(mels)
+    f0 = torch.cat([H.synth_f0(T, 1001, b).reshape(-1) for b in range(B)]).cuda().contiguous()
+    g = torch.Generator(device="cuda").manual_seed(2001)
+    pv = (torch.rand(B, 9, generator=g, device="cuda") * 2 - 1) * math.pi
+    pv[:, 0] = 0
+    noise = torch.randn(B * 9 * L, generator=g, device="cuda")
+    wav = voc.forward_packed(mel, Ts, f0=f0, phase_vec=pv.contiguous(), noise=noise).clone()
+    torch.cuda.synchronize()
+    assert wav.numel() == B * L and bool(torch.isfinite(wav).all())
+    w = wav.view(B, L)
+    assert float(w.abs().max()) <= 0.99 + 1e-7
+    assert float(w[:, :480].abs().max()) == 0.0                      # trim_fade zeroes the first 20 ms of every chunk
+    assert float(w[:, 960:].abs().amax(dim=1).min()) > 1e-3          # every chunk carries signal
+    # determinism
+    again = voc.forward_packed(mel, Ts, f0=f0, phase_vec=pv.contiguous(), noise=noise)
+    assert torch.equal(wav, again)
+    # one chunk against the oracle
+    b = 37
+    nz_b = noise[b * 9 * L:(b + 1) * 9 * L].view(9, L).cpu()
+    ref = _oracle(torch, H.fold_weight_norm(weights["unit"]), mels[b], f0[b * T:(b + 1) * T].cpu(), pv[b].cpu(), nz_b)
+    got = w[b].cpu()
+    assert float((got - ref).abs().max()) <= MAX_ABS and H.snr_db(ref, got) >= MIN_SNR_DB, H.snr_db(ref, got)
+    # one chunk alone == the same chunk inside the batch
+    b = 5
+    solo = voc.forward_packed(mel[b * T:(b + 1) * T].contiguous(), Ts[b:b + 1], f0=f0[b * T:(b + 1) * T].contiguous(),
+                              phase_vec=pv[b:b + 1].contiguous(), noise=noise[b * 9 * L:(b + 1) * 9 * L].contiguous())
+    assert torch.equal(solo, w[b])

@@ -198,10 +198,14 @@ int launch_gemm_nt(const ConvArgs& a, const ConvLayer& L, uint32_t idesc, int gr
     return launch_gemm_em<NT, 2, 4, 4, EM_ELU | EM_OUT, ActT>(a, L, idesc, grid, st);
   if (a.out && a.act[0].dst && a.act[0].kind == ACT_LRELU && a.act_from_out && !a.act[1].dst)
     return launch_gemm_em<NT, 2, 4, 4, EM_OUT | EM_OACT, ActT>(a, L, idesc, grid, st);
+  // layers with few K blocks (the source_downs) are bound by their epilogue: 8 epilogue warps, 3 stages
+  const bool epi_heavy = L.n_kb <= 12;
   if (a.out && a.act[0].dst && a.act[0].kind == ACT_SNAKE && !a.act[1].dst)
-    return launch_gemm_em<NT, 2, 4, 4, EM_OUT | EM_ACT1, ActT>(a, L, idesc, grid, st);
+    return epi_heavy ? launch_gemm_em<NT, 2, 3, 8, EM_OUT | EM_ACT1, ActT>(a, L, idesc, grid, st)
+                     : launch_gemm_em<NT, 2, 4, 4, EM_OUT | EM_ACT1, ActT>(a, L, idesc, grid, st);
   if (a.out && !a.act[0].dst && a.act[0].kind == ACT_NONE && !a.act[1].dst)
-    return launch_gemm_em<NT, 2, 4, 4, EM_OUT, ActT>(a, L, idesc, grid, st);
+    return epi_heavy ? launch_gemm_em<NT, 2, 3, 8, EM_OUT, ActT>(a, L, idesc, grid, st)
+                     : launch_gemm_em<NT, 2, 4, 4, EM_OUT, ActT>(a, L, idesc, grid, st);
   VT_REQUIRE(false, "gemm_tc: no compiled epilogue for layer %s", L.name.c_str());
   return VT_OK;
 }
