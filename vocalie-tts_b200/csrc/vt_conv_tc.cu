@@ -126,13 +126,17 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
         const int nt = t % n_nt;
         const uint8_t* wsrc = wtc + (size_t)nt * nchunks * K::W_BYTES;
         // issue order of the MMA warp: channel block outer, taps inner; the packed image is (tap, block)
-        for (int q = 0; q < nchunks; ++q, ws = (ws + 1 == (uint32_t)W_ST ? 0u : ws + 1), ph ^= (ws == 0 ? 1u : 0u)) {
+        for (int q = 0; q < nchunks; ++q) {
           const int cb = q / a.k, j = q - cb * a.k;
           const int c = j * CB + cb;
+          if ((a.tap_skip >> (4 * nt + j)) & 1ull) continue;   // all-zero tap of this column tile: not loaded, not issued
           mbar_wait(&w_empty[ws], ph ^ 1u);
-          if (a.dbg & 1) { mbar_arrive(&w_full[ws]); continue; }
-          mbar_arrive_expect_tx(&w_full[ws], K::W_BYTES);
-          bulk_g2s(sW + ws * K::W_BYTES, wsrc + (size_t)c * K::W_BYTES, K::W_BYTES, &w_full[ws]);
+          if (a.dbg & 1) mbar_arrive(&w_full[ws]);
+          else {
+            mbar_arrive_expect_tx(&w_full[ws], K::W_BYTES);
+            bulk_g2s(sW + ws * K::W_BYTES, wsrc + (size_t)c * K::W_BYTES, K::W_BYTES, &w_full[ws]);
+          }
+          if (++ws == (uint32_t)W_ST) { ws = 0; ph ^= 1u; }
         }
       }
     }
@@ -165,6 +169,7 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
         tc_fence_after();
         uint32_t a_chunk = a_tile + (uint32_t)cb * (uint32_t)K::RA * 8u;
         for (int j = 0; j < a.k; ++j, a_chunk += tap16) {
+          if ((a.tap_skip >> (4 * (t % n_nt) + j)) & 1ull) continue;
           mbar_wait(&w_full[ws], wph);
           tc_fence_after();
           if (elect_one()) {
@@ -357,6 +362,20 @@ int pack_conv_tc(ConvLayer& L, const std::vector<float>& w, int act_elem, std::v
               dst[pos] = to_bits(v);
             }
       }
+  // phase-decomposed transposed convs: a tap whose weights are all zero for a whole column tile is skipped
+  L.tap_skip = 0;
+  if (L.out_mul > 1 && N / NT <= 16 && k <= 4) {
+    for (int nt = 0; nt < N / NT; ++nt)
+      for (int j = 0; j < k; ++j) {
+        bool zero = true;
+        for (int ci = 0; ci < CIN && zero; ++ci)
+          for (int co = 0; co < NT; ++co)
+            if (w[((size_t)j * CIN + ci) * N + nt * NT + co] != 0.0f) { zero = false; break; }
+        if (zero) L.tap_skip |= 1ull << (4 * nt + j);
+      }
+    for (int nt = 0; nt < N / NT; ++nt)
+      VT_REQUIRE(((L.tap_skip >> (4 * nt)) & 15ull) != ((1ull << k) - 1), "conv_tc: layer %s has an all-zero column tile", L.name.c_str());
+  }
   void* p = nullptr;
   VT_CUDA_OK(cudaMalloc(&p, n * 2));
   allocs.push_back(p);
@@ -389,6 +408,7 @@ int launch_conv_tc(const ConvArgs& a_in, const ConvLayer& L, int act_elem, const
   const int NT = tc_nt(inst);
   VT_REQUIRE(inst != 0 && tile_rows == conv_tc_tile_rows(L), "conv_tc: tile table does not match layer %s", L.name.c_str());
   ConvArgs a = a_in;
+  a.tap_skip = L.tap_skip;
   a.tiles = reinterpret_cast<const ConvTile*>(tc_tiles);
   a.n_tiles = n_tc_tiles;
   static int sm_count = 0;

@@ -385,17 +385,23 @@ Workspace carve_ws(const vt_hift* h, int B, long long total_T, void* base) {
   return w;
 }
 
-// Zero the gap rows of the activation copies (read through TMA by the tensor-core kernels).
-__global__ void k_zero_gaps(void* buf, int row_bytes, const long long* off, const int* T, int B, int mul, int plus,
-                            long long rows_total) {
-  // gap g (0..B): rows [start_g, start_g + kGap)
-  const int g = blockIdx.x;
+// Zero the gap rows of every buffer the tensor-core kernels read with a halo: ONE launch over a table.
+struct GapBuf { void* p; int row_bytes; int level; };      // level 0..2, 3 = gapped mel rate
+constexpr int kMaxGapBufs = 40;
+struct GapTable {
+  GapBuf b[kMaxGapBufs];
+  const long long* off[4];
+  int mul[4], plus[4];
+};
+__global__ void k_zero_gaps(const GapTable t, const int* T) {
+  // gap g (0..B) of buffer blockIdx.y: rows [start_g, start_g + kGap)
+  const GapBuf gb = t.b[blockIdx.y];
+  const int g = blockIdx.x, l = gb.level;
   long long start = 0;
-  if (g > 0) start = off[g - 1] + (long long)mul * T[g - 1] + plus;
-  const long long bytes = (long long)kGap * row_bytes;
-  uint4* p = reinterpret_cast<uint4*>((char*)buf + start * row_bytes);
+  if (g > 0) start = t.off[l][g - 1] + (long long)t.mul[l] * T[g - 1] + t.plus[l];
+  const long long bytes = (long long)kGap * gb.row_bytes;
+  uint4* p = reinterpret_cast<uint4*>((char*)gb.p + start * gb.row_bytes);
   for (long long i = threadIdx.x; i < bytes / 16; i += blockDim.x) p[i] = make_uint4(0, 0, 0, 0);
-  (void)rows_total;
 }
 
 }  // namespace
@@ -588,30 +594,32 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
   }
 
   if (h->use_tc) {
-    for (int l = 0; l < 3; ++l)
-      for (int i = 0; i < 5; ++i) {
-        k_zero_gaps<<<B + 1, 256, 0, st>>>(i < 4 ? w.A[l][i] : w.Yact[l], (kBase >> (l + 1)) * (int)elem_size(ae), P.d_off[l],
-                                           P.d_T, B, kLevelMul[l], l == 2 ? 1 : 0, P.rows[l]);
-        VT_LAUNCHED();
-      }
-    k_zero_gaps<<<B + 1, 256, 0, st>>>(w.xpre_act, kBase * (int)elem_size(ae), P.d_offM, P.d_T, B, 1, 0, P.rowsM);
-    VT_LAUNCHED();
-    // fused pairs read the fp32 streams with their halo: the gap rows of those buffers must be zero
+    GapTable gt{};
+    int nb = 0;
+    auto add = [&](void* p, int row_bytes, int level) { gt.b[nb++] = GapBuf{p, row_bytes, level}; };
     for (int l = 0; l < 3; ++l) {
-      if (!h->fuse[l]) continue;
-      float* fb[5] = {w.S[l], w.S2[l], w.X[l], w.XR[l], w.XR2[l]};
-      for (int i = 0; i < 5; ++i) {
-        k_zero_gaps<<<B + 1, 256, 0, st>>>(fb[i], (kBase >> (l + 1)) * 4, P.d_off[l], P.d_T, B, kLevelMul[l], l == 2 ? 1 : 0, P.rows[l]);
-        VT_LAUNCHED();
+      const int C = kBase >> (l + 1);
+      gt.off[l] = P.d_off[l]; gt.mul[l] = kLevelMul[l]; gt.plus[l] = l == 2 ? 1 : 0;
+      add(w.Yact[l], C * (int)elem_size(ae), l);
+      if (h->fuse[l]) {
+        // fused pairs read the fp32 streams with their halo
+        float* fb[5] = {w.S[l], w.S2[l], w.X[l], w.XR[l], w.XR2[l]};
+        for (int i = 0; i < 5; ++i) add(fb[i], C * 4, l);
+      } else {
+        for (int i = 0; i < 4; ++i) add(w.A[l][i], C * (int)elem_size(ae), l);
       }
     }
+    gt.off[3] = P.d_offM; gt.mul[3] = 1; gt.plus[3] = 0;
+    add(w.xpre_act, kBase * (int)elem_size(ae), 3);
     // operands of the K-blocked layers: mel split, F0 trunk ping-pong, STFT rows
-    void* mbufs[6] = {w.mel_hi, w.mel_lo, w.fx[0][0], w.fx[0][1], w.fx[1][0], w.fx[1][1]};
-    for (int i = 0; i < (f0_in ? 2 : 6); ++i) {
-      k_zero_gaps<<<B + 1, 256, 0, st>>>(mbufs[i], (i < 2 ? kMelOp : kF0Ch) * 2, P.d_offM, P.d_T, B, 1, 0, P.rowsM);
-      VT_LAUNCHED();
-    }
-    k_zero_gaps<<<B + 1, 256, 0, st>>>(w.spec_op, kSpecOp * 2, P.d_off[2], P.d_T, B, kLevelMul[2], 1, P.rows[2]);
+    add(w.mel_hi, kMelOp * 2, 3);
+    add(w.mel_lo, kMelOp * 2, 3);
+    if (!f0_in)
+      for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j) add(w.fx[i][j], kF0Ch * 2, 3);
+    add(w.spec_op, kSpecOp * 2, 2);
+    VT_REQUIRE(nb <= kMaxGapBufs, "gap table overflow");
+    k_zero_gaps<<<dim3(B + 1, nb), 256, 0, st>>>(gt, P.d_T);
     VT_LAUNCHED();
     rc = launch_pack_mel(mel, P.d_mel_off, P.d_T, P.d_offM, B, total_T, w.mel_hi, w.mel_lo, st);
     if (rc) return rc;

@@ -78,6 +78,7 @@ struct ConvArgs {
   int out_mul, out_shift, phase_c, dup_row2;
   const ConvTile* tiles;
   int n_tiles;
+  unsigned long long tap_skip;   // activation-resident conv: bit (4*column_tile + tap) set = that tap's weights are all zero
   int dbg;              // debug: timing-ablation bits (VT_TC_DBG), 0 normally
   long long* trace;     // debug: per-tile role timestamps of CTA 0 (VT_TC_TRACE=<layer>), nullptr normally
 };
@@ -97,6 +98,7 @@ struct ConvLayer {
   float* w = nullptr;               // device [k][cin][cout] fp32
   float* bias = nullptr;            // device [cout]
   void* w_tc = nullptr;             // device, tensor-core operand packing (vt_conv_tc.cu)
+  unsigned long long tap_skip = 0;  // all-zero (column tile, tap) pairs of a phase-decomposed transposed conv
   void* w_gemm = nullptr;           // device, K-blocked tensor-core packing (vt_gemm_tc.cu)
   void* d_kb = nullptr;             // device KBlock table
   int n_kb = 0, gemm_nt = 0, gemm_elem = 0;
