@@ -40,6 +40,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   if (!mbar_try(addr, parity)) mbar_wait_slow(addr, parity);
 }
+// Relaxed wait for roles whose waits are long (epilogues, producers): back off between probes so that waiting
+// warps do not compete for issue slots (and power) with the roles that are working.
+static __device__ __noinline__ void mbar_wait_relaxed_slow(uint32_t addr, uint32_t parity) {
+  const long long t0 = clock64();
+  while (!mbar_try(addr, parity)) {
+    __nanosleep(96);
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  if (!mbar_try(addr, parity)) mbar_wait_relaxed_slow(addr, parity);
+}
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
