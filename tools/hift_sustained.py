@@ -1,4 +1,6 @@
-"""Sustained (power-capped) forward time: 30 back-to-back forwards at bench size after 6 warm-ups, with the SM clock\nand board power sampled while the queue is still busy.  B200 boards reach the 1 kW cap on this workload, so the\nfirst forwards of a process run ~12 % faster than the steady state bench.py reports.  Honors VT_TC_DBG."""
+"""Sustained (power-capped) forward time: 30 back-to-back forwards at bench size after 6 warm-ups, with the SM clock
+and board power sampled while the queue is still busy.  B200 boards reach the 1 kW cap on this workload, so the
+first forwards of a process run ~12 % faster than the steady state bench.py reports.  Honors VT_TC_DBG."""
 import sys, os, subprocess
 from pathlib import Path
 import torch
