@@ -162,6 +162,7 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
       const uint32_t d0 = tmem_base + (uint32_t)(as * K::ACC_COLS);
       const uint32_t a_tile = a_lo0 + (uint32_t)ab * (uint32_t)(K::A_BYTES >> 4);
       uint32_t acc = 0;
+      long long w_wait = 0;
 #pragma unroll 1
       for (int cb = 0; cb < CB; ++cb) {
         mbar_wait(&a_full[ab * CB + cb], aph);
@@ -170,7 +171,13 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
         uint32_t a_chunk = a_tile + (uint32_t)cb * (uint32_t)K::RA * 8u;
         for (int j = 0; j < a.k; ++j, a_chunk += tap16) {
           if ((a.tap_skip >> (4 * (t % n_nt) + j)) & 1ull) continue;
-          mbar_wait(&w_full[ws], wph);
+          if (a.trace) {
+            const long long tw = clock64();
+            mbar_wait(&w_full[ws], wph);
+            w_wait += clock64() - tw;
+          } else {
+            mbar_wait(&w_full[ws], wph);
+          }
           tc_fence_after();
           if (elect_one()) {
             const uint32_t b_lo = w_lo0 + ws * (uint32_t)(K::W_BYTES >> 4);
@@ -194,6 +201,7 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
       if (elect_one()) umma_commit(&acc_full[as]);
       __syncwarp();
       if (lane == 0) trace_ev(a.trace, it, 5);
+      if (lane == 0 && a.trace && blockIdx.x == 0 && it < kTraceTiles) a.trace[it * kTraceEvents + 8] = w_wait;
     }
   } else {
     // ---------------- epilogue warps 0..NEPI-1.  Warp w may touch TMEM lanes 32*(w%4)..+31; the NEPI/4
@@ -443,7 +451,8 @@ int launch_conv_tc(const ConvArgs& a_in, const ConvLayer& L, int act_elem, const
     VT_CUDA_OK(cudaStreamSynchronize(st));
     VT_CUDA_OK(cudaMemcpy(h.data(), d_trace, h.size() * 8, cudaMemcpyDeviceToHost));
     long long t0 = 0;
-    for (long long v : h) if (v && (!t0 || v < t0)) t0 = v;
+    for (size_t q = 0; q < h.size(); ++q)
+      if ((int)(q % tc::kTraceEvents) < 8 && h[q] && (!t0 || h[q] < t0)) t0 = h[q];
     fprintf(stderr, "[vt trace] layer %s k=%d dil=%d tiles=%lld grid=%d  (cycles since first event; "
             "A:wait_empty issued landed | MMA:acc_free a_full issued | EPI:acc_full done)\n", L.name.c_str(), L.k, L.dil, total, grid);
     for (int it = 0; it < tc::kTraceTiles; ++it) {

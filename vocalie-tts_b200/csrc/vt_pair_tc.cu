@@ -327,11 +327,18 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
         const uint32_t blk16 = (uint32_t)(pass == 0 ? kPairRA1 : kPairRA2) * 8u;   // 64-channel block stride, 16-byte units
         const uint32_t tap16 = (uint32_t)(pass == 0 ? p.dil : 1) * 8u;              // one tap = dil rows of 128 B
         uint32_t acc = (pass == 1 && kPreload) ? 1u : 0u;
+        long long w_wait = 0;
         for (int j = 0; j < p.k; ++j) {
           uint32_t a_chunk = a_tile + (uint32_t)j * tap16;
 #pragma unroll 1
           for (int cb = 0; cb < CB; ++cb, a_chunk += blk16) {
-            mbar_wait(&w_full[ws], wph);
+            if (a.trace) {
+              const long long tw = clock64();
+              mbar_wait(&w_full[ws], wph);
+              w_wait += clock64() - tw;
+            } else {
+              mbar_wait(&w_full[ws], wph);
+            }
             tc_fence_after();
             if (elect_one()) {
               const uint32_t b_lo = w_lo0 + ws * (uint32_t)(W_BYTES >> 4);
@@ -356,6 +363,7 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
         }
         __syncwarp();
         if (lane == 0) trace_ev(a.trace, i, 7 + 2 * pass);
+        if (lane == 0 && a.trace && blockIdx.x == 0 && i < kTraceTiles) a.trace[i * kTraceEvents + 10 + pass] = w_wait;
       }
   } else {
     // ---------------- epilogue warps.  mid: D1 + b1 -> Snake2 -> fp16 A2 rows (zero outside the sequence);
@@ -730,13 +738,15 @@ int launch_pair_tc(const ConvArgs& a_in, const ConvLayer& c1, const ConvLayer& c
     VT_CUDA_OK(cudaStreamSynchronize(st));
     VT_CUDA_OK(cudaMemcpy(h.data(), d_trace, h.size() * 8, cudaMemcpyDeviceToHost));
     long long t0 = 0;
-    for (long long v : h) if (v && (!t0 || v < t0)) t0 = v;
+    for (size_t q = 0; q < h.size(); ++q)
+      if ((int)(q % tc::kTraceEvents) < 10 && h[q] && (!t0 || h[q] < t0)) t0 = h[q];
     fprintf(stderr, "[vt trace] pair %s k=%d dil=%d tiles=%d grid=%d (cycles; PROD start end | MID start end | FIN start end | "
             "C1 start issued | C2 start issued)\n", c1.name.c_str(), c1.k, c1.dil, a.n_tiles, grid);
     for (int it = 0; it < tc::kTraceTiles; ++it) {
       if (!h[it * tc::kTraceEvents + 0]) break;
       fprintf(stderr, "[vt trace] %2d", it);
       for (int e = 0; e < 10; ++e) fprintf(stderr, " %7lld", h[it * tc::kTraceEvents + e] ? h[it * tc::kTraceEvents + e] - t0 : -1);
+      fprintf(stderr, "  w_wait c1=%lld c2=%lld", h[it * tc::kTraceEvents + 10], h[it * tc::kTraceEvents + 11]);
       fprintf(stderr, "\n");
     }
   }

@@ -184,7 +184,7 @@ __device__ __forceinline__ float snake_f(float v, float alpha, float inv_alpha) 
 }
 
 // Debug timeline (VT_TC_TRACE): CTA 0 records clock64 at role events of its first kTraceTiles tiles.
-constexpr int kTraceTiles = 48, kTraceEvents = 10;
+constexpr int kTraceTiles = 48, kTraceEvents = 12;
 __device__ __forceinline__ void trace_ev(long long* trace, int it, int ev) {
   if (trace && blockIdx.x == 0 && it < kTraceTiles) trace[it * kTraceEvents + ev] = clock64();
 }
