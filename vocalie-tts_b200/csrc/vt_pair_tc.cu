@@ -79,18 +79,31 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 // fin warps also run the mid epilogue - conv2(i) waits for mid(i) anyway, and the fin staging can then live in
 // the A2 tile, which is idle between conv2(i) and mid(i+1); then the MMA warp, the weight producer, NPROD
 // activation-producer warps.
-template <int C, int NBUF, int NEPI, int NPROD>
+// TR ("transposed"): the MMA computes D^T = W^T X^T - weights are the M = 128 operand, the 256 time steps of the
+// tile the N operand (one MMA per K step instead of one per 128-row block: the weight slab is fetched from shared
+// memory once per 256 rows, -25 % operand traffic at C = 128).  Accumulators come out as lane = channel, column =
+// time step, so a warp's lanes are 32 consecutive channels of ONE time step: the fin epilogue's global accesses
+// are coalesced 128-byte lines with no shared-memory transposition (no staging at all), the Snake parameters of
+// the mid epilogue are per-thread registers, and mid and fin can be separate warps again.
+template <int C, int NBUF, int NEPI, int NPROD, bool TR = false>
 struct PairCfg {
-  static constexpr bool kCombined = NBUF == 1;
+  static constexpr bool kCombined = NBUF == 1 && !TR;
   static constexpr int W_MID = kCombined ? 0 : NEPI;
   static constexpr int W_MMA = kCombined ? NEPI : 2 * NEPI;
   static constexpr int WARPS = W_MMA + 2 + NPROD;      // + MMA warp, loader warp (weights and x ring)
 };
 
-template <int C, int NBUF, int NA1, int NA2, int W_ST, int NEPI, int NPROD, int NSLAB, int EM, bool kPreload, typename ActT>
-__global__ void __launch_bounds__(PairCfg<C, NBUF, NEPI, NPROD>::WARPS * 32, 1)
+template <typename T> __device__ __forceinline__ unsigned short to_op_bits(float v);
+template <> __device__ __forceinline__ unsigned short to_op_bits<__half>(float v) { return __half_as_ushort(__float2half_rn(v)); }
+template <> __device__ __forceinline__ unsigned short to_op_bits<__nv_bfloat16>(float v) {
+  return __bfloat16_as_ushort(__float2bfloat16_rn(v));
+}
+
+template <int C, int NBUF, int NA1, int NA2, int W_ST, int NEPI, int NPROD, int NSLAB, int EM, bool kPreload, bool TR, typename ActT>
+__global__ void __launch_bounds__(PairCfg<C, NBUF, NEPI, NPROD, TR>::WARPS * 32, 1)
 k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
-  using PC = PairCfg<C, NBUF, NEPI, NPROD>;
+  using PC = PairCfg<C, NBUF, NEPI, NPROD, TR>;
+  static_assert(!TR || (C == 128 && NBUF == 1 && !kPreload && NEPI == 8), "the transposed variant is built for C = 128");
   constexpr bool kCombined = PC::kCombined;
   constexpr int NMID = NEPI, kFin = NEPI, kProdT = NPROD * 32;
   static_assert(kSwz, "the fused pair kernel assumes the SWIZZLE_128B operand layout");
@@ -343,12 +356,19 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
             if (elect_one()) {
               const uint32_t b_lo = w_lo0 + ws * (uint32_t)(W_BYTES >> 4);
               if (mma_on) {
-#pragma unroll
-                for (int mb = 0; mb < 2; ++mb)
+                if constexpr (TR) {
+                  // A operand = weight slab (M = C output channels), B operand = 256 rows of the activation tile
 #pragma unroll
                   for (int ks = 0; ks < 4; ++ks)
-                    umma_f16_lh(d0 + (uint32_t)(mb * C), a_chunk + (uint32_t)(mb * 1024 + ks * 2), b_lo + (uint32_t)(ks * 2), kDescHi,
-                                idesc, ks == 0 ? acc : 1u);
+                    umma_f16_lh(d0, b_lo + (uint32_t)(ks * 2), a_chunk + (uint32_t)(ks * 2), kDescHi, idesc, ks == 0 ? acc : 1u);
+                } else {
+#pragma unroll
+                  for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                      umma_f16_lh(d0 + (uint32_t)(mb * C), a_chunk + (uint32_t)(mb * 1024 + ks * 2), b_lo + (uint32_t)(ks * 2), kDescHi,
+                                  idesc, ks == 0 ? acc : 1u);
+                }
               }
               umma_commit(&w_empty[ws]);
             }
@@ -365,6 +385,125 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
         if (lane == 0) trace_ev(a.trace, i, 7 + 2 * pass);
         if (lane == 0 && a.trace && blockIdx.x == 0 && i < kTraceTiles) a.trace[i * kTraceEvents + 10 + pass] = w_wait;
       }
+  } else if constexpr (TR) {
+    // ---------------- transposed epilogues: lane = output channel (TMEM lane), TMEM column = time step of the tile.
+    // Warps [0, NEPI) fin, [NEPI, 2 NEPI) mid; warp & 3 = channel quarter, the two warps of a quarter split the
+    // 256 time steps in halves.
+    const bool is_fin = warp < W_MID;
+    const int ew = is_fin ? warp : warp - W_MID;
+    const int quarter = warp & 3, half = ew >> 2;
+    const int c = quarter * 32 + lane;                                   // this thread's channel
+    const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
+    if (!is_fin) {
+      const float b1 = prm[2 * C + c], al2 = prm[3 * C + c], ia2 = prm[4 * C + c];
+      // A2 element (row r, channel c): 64-channel block, 16-byte chunk XOR-swizzled by the row, 2 bytes inside
+      const uint32_t coff = (uint32_t)(c >> 6) * (uint32_t)(kPairRA2 * 128) + (uint32_t)((c & 7) * 2);
+      const uint32_t chunk = (uint32_t)((c & 63) >> 3);
+      for (int i = 0; i < n_my; ++i) {
+        const ConvTile tile = a.tiles[blockIdx.x + i * gridDim.x];
+        mbar_wait_relaxed(&d1_full[0], (uint32_t)i & 1u);
+        mbar_wait_relaxed(&a2_empty[0], ((uint32_t)i & 1u) ^ 1u);
+        tc_fence_after();
+        if (ew == 0 && lane == 0) trace_ev(a.trace, i, 2);
+        const uint32_t dst0 = smem_u32(sA2) + coff;
+#pragma unroll 1
+        for (int cc = 0; cc < 4 && !(a.dbg & 4); ++cc) {
+          const int col0 = half * 128 + cc * 32;
+          uint32_t v[32];
+          tmem_ld32(tmem_base + lane_sel + (uint32_t)col0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int t = 0; t < 32; ++t) {
+            const int row = col0 + t;                                      // conv1 output row of the tile = A2 row
+            const int pseq = tile.q0 - H2 + row;
+            const bool valid = pseq >= 0 && pseq < tile.out_len;          // warp-uniform
+            const float y = valid ? snake_f(__uint_as_float(v[t]) + b1, al2, ia2) : 0.0f;
+            const uint32_t addr = dst0 + (uint32_t)row * 128u + ((chunk ^ (uint32_t)(row & 7)) << 4);
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(to_op_bits<ActT>(y)) : "memory");
+          }
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        if (ew == 0 && lane == 0) trace_ev(a.trace, i, 3);
+        mbar_arrive(&d1_empty[0]);
+        mbar_arrive(&a2_full[0]);
+      }
+    } else {
+      constexpr bool kRes2 = (EM & EM_RES2) != 0, kAccum = (EM & EM_ACCUM) != 0;
+      const float b2 = a.bias[c];
+      const bool accum = kAccum && a.out_accum;
+      const float inv = 1.0f / a.out_scale;
+      const uint32_t d2 = tmem_base + lane_sel + (uint32_t)ACC_COLS;
+      // Residual rows are prefetched into registers one 32-step block ahead (the first block of a tile before the
+      // d2_full wait): 32 coalesced 128-byte requests in flight per warp, lane = channel on both sides, so neither
+      // the loads nor the stores need a transposition.  Unconditional loads from clamped rows (a branch per load
+      // would serialise them).
+      float x[32];
+      // only (first element of this thread's column, rows) of a tile are kept in registers
+      auto tile_base = [&](int i, int& n) {
+        const ConvTile tl = a.tiles[blockIdx.x + i * gridDim.x];
+        n = tl.n;
+        return (tl.out_row0 + tl.q0) * (long long)C + c;
+      };
+      auto issue = [&](long long base, int n, int cc) {
+        const float* xr = a.res1 + base;
+        const int col0 = half * 128 + cc * 32, last = n - 1;
+#pragma unroll
+        for (int t = 0; t < 32; ++t) x[t] = (a.dbg & 32) ? 0.0f : __ldg(xr + (long long)(col0 + t < last ? col0 + t : last) * C);
+      };
+      int n_cur = 1;
+      long long obase = n_my > 0 ? tile_base(0, n_cur) : 0;
+      if (n_my > 0) issue(obase, n_cur, 0);
+      for (int i = 0; i < n_my; ++i) {
+        mbar_wait_relaxed(&d2_full[0], (uint32_t)i & 1u);
+        tc_fence_after();
+        if (warp == 0 && lane == 0) trace_ev(a.trace, i, 4);
+        struct { int n; } tile{n_cur};
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+          const int col0 = half * 128 + cc * 32, last = tile.n - 1;
+          if (!(a.dbg & 4)) {
+            if constexpr (kRes2) {
+#pragma unroll
+              for (int t = 0; t < 32; ++t) x[t] += __ldg(a.res2 + obase + (long long)(col0 + t < last ? col0 + t : last) * C);
+            }
+            if (accum) {
+#pragma unroll
+              for (int t = 0; t < 32; ++t)
+                x[t] = fmaf(__ldg(a.out + obase + (long long)(col0 + t < last ? col0 + t : last) * C), inv, x[t]);
+            }
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {                 // 16 accumulator columns at a time: x[32] stays live
+              uint32_t v[16];
+              tmem_ld16(d2 + (uint32_t)(col0 + hh * 16), v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int t = 0; t < 16; ++t) {
+                const int row = col0 + hh * 16 + t;
+                if (row < tile.n) {
+                  const float o = (__uint_as_float(v[t]) + b2 + x[hh * 16 + t]) * a.out_scale;
+                  const long long idx = obase + (long long)row * C;
+                  if (!(a.dbg & 64)) a.out[idx] = o;
+                  if constexpr ((EM & EM_OACT) != 0) {
+                    const float sl = a.act[0].slope;
+                    reinterpret_cast<unsigned short*>(a.act[0].dst)[idx] = to_op_bits<ActT>(o > 0.f ? o : o * sl);
+                  }
+                }
+              }
+            }
+          }
+          // next block of this tile, or the first block of the next one (in flight during the d2_full wait)
+          if (cc < 3) issue(obase, n_cur, cc + 1);
+          else if (i + 1 < n_my) {
+            obase = tile_base(i + 1, n_cur);
+            issue(obase, n_cur, 0);
+          }
+        }
+        tc_fence_before();
+        if (warp == 0 && lane == 0) trace_ev(a.trace, i, 5);
+        mbar_arrive(&d2i_full[0]);
+      }
+    }
   } else {
     // ---------------- epilogue warps.  mid: D1 + b1 -> Snake2 -> fp16 A2 rows (zero outside the sequence);
     // fin: D2 -> fp32 stream, then the residual terms of the tile that uses D2 next are preloaded into it.
@@ -637,21 +776,21 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
   }
 }
 
-template <int C, int NBUF, int NA1, int NA2, int W_ST, int NEPI, int NPROD, int NSLAB, int EM, bool kPreload, typename ActT>
+template <int C, int NBUF, int NA1, int NA2, int W_ST, int NEPI, int NPROD, int NSLAB, int EM, bool kPreload, bool TR, typename ActT>
 int launch_pair_em(const ConvArgs& a, const PairArgs& p, uint32_t idesc, int grid, cudaStream_t st) {
   constexpr int CB = C / 64;
-  using PC = PairCfg<C, NBUF, NEPI, NPROD>;
+  using PC = PairCfg<C, NBUF, NEPI, NPROD, TR>;
   constexpr int smem = CB * (NA1 * kPairRA1 + NA2 * kPairRA2) * 128 + W_ST * C * 128 + NSLAB * 8192 +
                        (2 * NA1 + 2 * NA2 + 2 * NSLAB + 4 * NBUF + 2 * W_ST) * 8 + 16 + 5 * C * 4 +
-                       (PC::kCombined ? 0 : NEPI * 32 * kStageLd * 4);
+                       ((PC::kCombined || TR) ? 0 : NEPI * 32 * kStageLd * 4);
   static_assert(smem <= 232448, "shared memory budget exceeded");
   static_assert(!PC::kCombined || NEPI * 32 * kStageLd * 4 <= CB * kPairRA2 * 128, "fin staging must fit the A2 tile");
   static bool configured = false;
   if (!configured) {
-    VT_CUDA_OK(cudaFuncSetAttribute(k_pair_tc<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, kPreload, ActT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    VT_CUDA_OK(cudaFuncSetAttribute(k_pair_tc<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, kPreload, TR, ActT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  k_pair_tc<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, kPreload, ActT><<<grid, PC::WARPS * 32, smem, st>>>(a, p, idesc);
+  k_pair_tc<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, kPreload, TR, ActT><<<grid, PC::WARPS * 32, smem, st>>>(a, p, idesc);
   VT_LAUNCHED();
   return VT_OK;
 }
@@ -659,9 +798,18 @@ int launch_pair_em(const ConvArgs& a, const PairArgs& p, uint32_t idesc, int gri
 template <int C, int NBUF, int NA1, int NA2, int W_ST, int NEPI, int NPROD, int NSLAB, int EM, typename ActT>
 int launch_pair_pre(const ConvArgs& a, const PairArgs& p, uint32_t idesc, int grid, cudaStream_t st) {
   if constexpr (C == 64) {
-    if (p.k == 3) return launch_pair_em<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, false, ActT>(a, p, idesc, grid, st);
+    if (p.k == 3) return launch_pair_em<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, false, false, ActT>(a, p, idesc, grid, st);
+    return launch_pair_em<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, true, false, ActT>(a, p, idesc, grid, st);
+  } else {
+    static const bool tr = !(getenv("VT_PAIR_TR") && getenv("VT_PAIR_TR")[0] == '0');
+    if (tr && p.k <= 7) {
+      // transposed MMA: M = 128 output channels, N = 256 time steps (k = 11 tiles keep the TMEM-preload kernel: under
+      // their weight stream the residual loads of a register-prefetch epilogue take several microseconds)
+      const uint32_t idesc_t = (idesc & ~((0x3Fu << 17) | (0x1Fu << 24))) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+      return launch_pair_em<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, false, true, ActT>(a, p, idesc_t, grid, st);
+    }
+    return launch_pair_em<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, true, false, ActT>(a, p, idesc, grid, st);
   }
-  return launch_pair_em<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, true, ActT>(a, p, idesc, grid, st);
 }
 
 template <int C, int NBUF, int NA1, int NA2, int W_ST, int NEPI, int NPROD, int NSLAB, typename ActT>
