@@ -291,7 +291,7 @@ def run_ours(args, rank, world, local_rank):
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the top kernel (k_pair_tc<64>, k=7,
                      # 3.84 M steps) from the ncu --set full capture summarised in profiles/r01_pair_c64_ncu.txt;
                      # algorithmic = 512 B per step = 1.966e9 B
-                     "traffic": 1.918e9 if (n_chunks, T) == (CHUNKS_PER_RANK, T_FRAMES) else None,
+                     "traffic": 1.916e9 if (n_chunks, T) == (CHUNKS_PER_RANK, T_FRAMES) else None,
                      "peak_source": how, "kernel_ms_per_step": rb_ms, "forward_ms_per_step": fwd_ms,
                      "kernel_share_of_step": rb_ms / ms if ms > 0 else None,
                      "path_tflops": algorithmic_flops_per_frame() * n_chunks * T / (ms * 1e-3) / 1e12},
