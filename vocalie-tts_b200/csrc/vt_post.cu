@@ -20,7 +20,7 @@ namespace vt {
 
 constexpr int kThreads = 256;
 constexpr int kScanTile = 1024;    // samples per warp iteration of the scan pass (8 x float4 per lane)
-constexpr int kWriteTile = 2048;   // output samples per block iteration (8 per thread)
+constexpr int kWriteTile = 4096;   // output samples per block iteration (16 per thread)
 
 struct __align__(16) SegPlan {
   long long first;       // first active sample (segment-relative); LLONG_MAX if none
@@ -107,16 +107,43 @@ __global__ void k_post_init(SegPlan* plan, PostHeader* hdr, const int64_t* seg_o
   }
 }
 
-// Exclusive scan of per-segment tile counts (tiny; one thread).
+// Block-wide exclusive scan of one long long per thread (blockDim.x a multiple of 32, <= 1024); `carry` is a
+// shared running total carried across calls.  Returns this thread's exclusive prefix including the carry.
+__device__ __forceinline__ long long block_excl_scan(long long v, long long* sh_warp, long long* sh_carry) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  long long incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const long long t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) sh_warp[wid] = incl;
+  __syncthreads();
+  long long woff = 0;
+  for (int w = 0; w < wid; ++w) woff += sh_warp[w];
+  const long long carry = *sh_carry;
+  __syncthreads();
+  if (threadIdx.x == blockDim.x - 1) *sh_carry = carry + woff + incl;
+  __syncthreads();
+  return carry + woff + incl - v;
+}
+
+// Exclusive scan of per-segment tile counts (one block).
 __global__ void k_tile_bases(SegPlan* plan, const int64_t* seg_off, int n_seg) {
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    long long acc = 0;
-    for (int i = 0; i < n_seg; ++i) {
-      plan[i].tile_base = acc;
+  __shared__ long long sh_warp[32];
+  __shared__ long long sh_carry;
+  if (threadIdx.x == 0) sh_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n_seg; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    long long v = 0;
+    if (i < n_seg) {
       const long long a = seg_off[i], b = seg_off[i + 1];
       const long long A = a & ~3LL;
-      acc += (b - A + kScanTile - 1) / kScanTile;
+      v = (b - A + kScanTile - 1) / kScanTile;
     }
+    const long long ex = block_excl_scan(v, sh_warp, &sh_carry);
+    if (i < n_seg) plan[i].tile_base = ex;
   }
 }
 
@@ -158,23 +185,39 @@ k_scan(const float* __restrict__ audio, const int64_t* __restrict__ seg_off, int
     }
     float m = 0.0f;
     const bool inside = (t0 >= a) && (t0 + kScanTile <= b);
+    // bit (4u + e) of `act`: element e of this lane's u-th float4 is inside the segment and above the threshold.
+    // Two or three instructions per sample on the common path; the 64-bit index arithmetic runs once per tile.
+    unsigned act = 0u;
+    if (inside) {
 #pragma unroll
-    for (int u = 0; u < kScanTile / 128; ++u) {
-      const long long p = t0 + (u * 32 + lane) * 4;
-      const float v[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+      for (int u = 0; u < kScanTile / 128; ++u) {
+        const float v[4] = {fabsf(q[u].x), fabsf(q[u].y), fabsf(q[u].z), fabsf(q[u].w)};
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const long long idx = p + e;
-        if (inside || (idx >= a && idx < b)) {
-          const float av = fabsf(v[e]);
-          m = fmaxf(m, av);
-          if (av > thr) {
-            const long long r = idx - a;
-            lo = r < lo ? r : lo;
-            hi = r > hi ? r : hi;
+        for (int e = 0; e < 4; ++e) {
+          m = fmaxf(m, v[e]);
+          act |= (v[e] > thr ? 1u : 0u) << (4 * u + e);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < kScanTile / 128; ++u) {
+        const long long p = t0 + (u * 32 + lane) * 4;
+        const float v[4] = {fabsf(q[u].x), fabsf(q[u].y), fabsf(q[u].z), fabsf(q[u].w)};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (p + e >= a && p + e < b) {
+            m = fmaxf(m, v[e]);
+            act |= (v[e] > thr ? 1u : 0u) << (4 * u + e);
           }
         }
       }
+    }
+    if (act) {
+      const int bl = __ffs(act) - 1, bh = 31 - __clz(act);
+      const long long rl = t0 + ((bl >> 2) * 32 + lane) * 4 + (bl & 3) - a;
+      const long long rh = t0 + ((bh >> 2) * 32 + lane) * 4 + (bh & 3) - a;
+      lo = rl < lo ? rl : lo;
+      hi = rh > hi ? rh : hi;
     }
     m = warp_max(m);
     if (lane == 0) tile_max[tbase + tile] = m;
@@ -327,14 +370,23 @@ k_peak(const float* __restrict__ audio, const int64_t* __restrict__ seg_off, int
   for (long long t = (long long)blockIdx.x * kThreads + threadIdx.x; t < n_tiles;
        t += (long long)gridDim.x * kThreads) {
     const long long t0 = A + t * kScanTile, t1 = t0 + kScanTile;
-    if (t1 <= ra || t0 >= rb) continue;  // outside the trimmed range
-    if (t0 >= ia && t1 <= ib) {          // untouched interior tile (lies inside [a, b) too)
-      m = fmaxf(m, tile_max[p.tile_base + t]);
-    } else {                             // boundary tile: at most a handful per segment
-      const long long lo = t0 > ra ? t0 : ra, hi = t1 < rb ? t1 : rb;
-      for (long long idx = lo; idx < hi; ++idx)
-        m = fmaxf(m, fabsf(apply_fades(audio[idx], idx - ra, len, p.fi, p.fo, out_first)));
-    }
+    // untouched interior tile (inside the trim range, outside both fades, inside [a, b)): reuse k_scan's maximum
+    if (t0 >= ia && t1 <= ib) m = fmaxf(m, tile_max[p.tile_base + t]);
+  }
+  // The samples of every other tile that overlaps [ra, rb) - the two boundary zones cut by the trim range or a
+  // fade, a few tiles at most - are re-read by the whole block 0 of the segment with coalesced strided loads
+  // (one thread walking a 1024-sample tile alone made this kernel as slow as the full-bandwidth passes).
+  if (blockIdx.x == 0) {
+    // first interior tile boundary at or after ia, last interior tile boundary at or before ib
+    long long hi_a = A + ((ia - A + kScanTile - 1) / kScanTile) * kScanTile;   // head zone [ra, hi_a)
+    long long lo_b = A + ((ib - A) / kScanTile) * kScanTile;                   // tail zone [lo_b, rb)
+    if (hi_a > rb) hi_a = rb;
+    if (lo_b < hi_a) lo_b = hi_a;                                              // zones meet: one pass over [ra, rb)
+    if (ia >= ib) { hi_a = rb; lo_b = rb; }                                    // fades overlap: no interior at all
+    for (long long idx = ra + threadIdx.x; idx < hi_a; idx += kThreads)
+      m = fmaxf(m, fabsf(apply_fades(audio[idx], idx - ra, len, p.fi, p.fo, out_first)));
+    for (long long idx = lo_b + threadIdx.x; idx < rb; idx += kThreads)
+      m = fmaxf(m, fabsf(apply_fades(audio[idx], idx - ra, len, p.fi, p.fo, out_first)));
   }
   const float bm = block_max(m, sh_f);
   if (threadIdx.x == 0 && bm > 0.0f) {
@@ -373,16 +425,22 @@ __global__ void k_plan(SegPlan* plan, PostHeader* hdr, const int64_t* seg_off, i
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    long long acc = 0;
-    for (int i = 0; i < n_seg; ++i) {
-      SegPlan& p = plan[i];
-      p.dst = concat ? acc : (long long)seg_off[i];
-      acc += p.out_len + p.gap_after;
-      if (results) results[(size_t)i * VT_POST_RESULT_STRIDE + 4] = (double)p.dst;
+  // exclusive scan of (out_len + gap_after) over the segments, one chunk of blockDim.x segments at a time
+  __shared__ long long sh_warp[32];
+  __shared__ long long sh_carry;
+  if (threadIdx.x == 0) sh_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n_seg; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const long long v = i < n_seg ? plan[i].out_len + plan[i].gap_after : 0;
+    const long long ex = block_excl_scan(v, sh_warp, &sh_carry);
+    if (i < n_seg) {
+      const long long dst = concat ? ex : (long long)seg_off[i];
+      plan[i].dst = dst;
+      if (results) results[(size_t)i * VT_POST_RESULT_STRIDE + 4] = (double)dst;
     }
-    hdr->total_out = concat ? acc : (long long)seg_off[n_seg];
   }
+  if (threadIdx.x == 0) hdr->total_out = concat ? sh_carry : (long long)seg_off[n_seg];
 }
 
 __global__ void k_total_out(const PostHeader* hdr, int64_t* total_out) {
@@ -437,6 +495,23 @@ k_write(const float* __restrict__ audio, const int64_t* __restrict__ seg_off, in
       *reinterpret_cast<float4*>(&sh_in[4 * v]) = r;
     }
     __syncthreads();
+    // interior tile (no fade, no gap, no edge of the segment or of the output buffer in it - all but a handful
+    // of tiles per segment): gain and clip only, no per-sample index arithmetic
+    if (j0 >= p.fi && j0 + kWriteTile <= p.out_len - p.fo && d0 + kWriteTile <= out_capacity) {
+#pragma unroll
+      for (int u = 0; u < kWriteTile / (4 * kThreads); ++u) {
+        const int l = (u * kThreads + threadIdx.x) * 4;
+        float y[4] = {sh_in[shift + l], sh_in[shift + l + 1], sh_in[shift + l + 2], sh_in[shift + l + 3]};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (p.apply_scale) y[e] = __fmul_rn(y[e], p.scale);
+          if (clip) y[e] = fminf(fmaxf(y[e], -1.0f), 1.0f);
+        }
+        if (PCM16) *reinterpret_cast<short4*>(out_s + d0 + l) = make_short4(to_pcm16(y[0]), to_pcm16(y[1]), to_pcm16(y[2]), to_pcm16(y[3]));
+        else *reinterpret_cast<float4*>(out_f + d0 + l) = make_float4(y[0], y[1], y[2], y[3]);
+      }
+      continue;
+    }
 #pragma unroll
     for (int u = 0; u < kWriteTile / (4 * kThreads); ++u) {
       const int l = (u * kThreads + threadIdx.x) * 4;  // local output index (multiple of 4)
@@ -598,7 +673,7 @@ int vt_post_analyze(const float* audio, const int64_t* seg_off, int n_seg, int64
   const int out_first = prm->stitch ? 1 : 0;
   k_post_init<<<(n_seg + 255) / 256, 256, 0, st>>>(w.plan, w.hdr, seg_off, n_seg, range_override);
   VT_LAUNCHED();
-  k_tile_bases<<<1, 32, 0, st>>>(w.plan, seg_off, n_seg);
+  k_tile_bases<<<1, 256, 0, st>>>(w.plan, seg_off, n_seg);
   VT_LAUNCHED();
   const bool need_scan = (prm->trim && !range_override) || prm->normalize;
   if (need_scan) {
@@ -680,7 +755,7 @@ int vt_find_active_range(const float* audio, const int64_t* seg_off, int n_seg, 
   PostWs w = carve(workspace, n_seg, n_samples);
   k_post_init<<<(n_seg + 255) / 256, 256, 0, st>>>(w.plan, w.hdr, seg_off, n_seg, nullptr);
   VT_LAUNCHED();
-  k_tile_bases<<<1, 32, 0, st>>>(w.plan, seg_off, n_seg);
+  k_tile_bases<<<1, 256, 0, st>>>(w.plan, seg_off, n_seg);
   VT_LAUNCHED();
   dim3 g(grid_x_for(n_seg, max_seg_len, kScanTile * (kThreads / 32)), n_seg);
   k_scan<<<g, kThreads, 0, st>>>(audio, seg_off, n_seg, threshold, 1, w.plan, w.tile_max);
