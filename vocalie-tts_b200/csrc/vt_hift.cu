@@ -16,6 +16,8 @@ int launch_conv_tc(const ConvArgs& a, const ConvLayer& L, int act_elem, const vo
 int pack_conv_tc(ConvLayer& L, const std::vector<float>& w_kcico, int act_elem, std::vector<void*>& allocs);
 bool conv_tc_supported(const ConvLayer& L);
 int conv_tc_tile_rows(const ConvLayer& L);
+bool convT_tc_supported(const ConvLayer& L);
+int launch_convT_tc(const ConvArgs& a, const ConvLayer& L, int act_elem, const void* tiles, int n_tiles, cudaStream_t st);
 bool pair_tc_supported(const ConvLayer& c1, const ConvLayer& c2);
 int pair_tc_tile_rows(int k);
 int launch_pair_tc(const ConvArgs& a, const ConvLayer& c1, const ConvLayer& c2, const float* alpha1, const float* alpha2,
@@ -434,6 +436,11 @@ static ConvArgs base_args(const ConvLayer& L, const Plan& P, const Plan::Seg& se
 }
 
 static int run_conv(vt_hift* h, const ConvArgs& a, const ConvLayer& L, int level, cudaStream_t st) {
+  if (h->use_tc && L.w_tc && level >= 0 && convT_tc_supported(L)) {
+    // C = 256: transposed formulation on 256-step tiles (weights streamed once per 256 steps)
+    const Plan::Seg& seg = h->plan.tc[level][1];
+    return launch_convT_tc(a, L, h->act_elem, h->plan.d_tiles + seg.off, seg.n, st);
+  }
   if (h->use_tc && L.w_tc && level >= 0) {
     const int rows = conv_tc_tile_rows(L);
     const Plan::Seg& seg = h->plan.tc[level][rows == 256 ? 1 : 0];
