@@ -31,20 +31,22 @@ template <> __device__ __forceinline__ unsigned short op_bits<__nv_bfloat16>(flo
   return __bfloat16_as_ushort(__float2bfloat16_rn(v));
 }
 
-template <int EM, typename ActT>
+// C = 256: two channel halves per tile (NH = 2), one activation stage.  C = 128: one half, the two TMEM buffers
+// alternate between tiles, two activation stages.
+template <int C, int EM, typename ActT>
 __global__ void __launch_bounds__((kTEpi + 2 + kProdWarps) * 32, 1)
 k_convT_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t idesc) {
-  constexpr int C = 256, CB = 4;
+  constexpr int CB = C / 64, NH = C / 128, NA = C == 128 ? 2 : 1;
   constexpr int A_BLK = kTRA * 128, A_BYTES = CB * A_BLK, W_BYTES = 128 * 128;
   constexpr int W_MMA = kTEpi, W_WP = kTEpi + 1, W_AP = kTEpi + 2;
   constexpr int NACT = (EM & EM_ACT3) ? 3 : ((EM & EM_ACT1) ? 1 : 0);
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
-  uint8_t* sW = sA + A_BYTES;
+  uint8_t* sW = sA + NA * A_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sW + kTWst * W_BYTES);
-  uint64_t* a_full = bars;
-  uint64_t* a_empty = a_full + CB;
-  uint64_t* w_full = a_empty + CB;
+  uint64_t* a_full = bars;                       // [stage][block]
+  uint64_t* a_empty = a_full + NA * CB;
+  uint64_t* w_full = a_empty + NA * CB;
   uint64_t* w_empty = w_full + kTWst;
   uint64_t* acc_full = w_empty + kTWst;
   uint64_t* acc_empty = acc_full + 2;
@@ -52,7 +54,7 @@ k_convT_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ide
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < CB; ++i) { mbar_init(&a_full[i], kProd); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < NA * CB; ++i) { mbar_init(&a_full[i], kProd); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < kTWst; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kTEpi * 32); }
     fence_barrier_init();
@@ -78,16 +80,18 @@ k_convT_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ide
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
       const ConvTile tile = a.tiles[t];
       const ActT* src = in + (tile.in_row0 + tile.q0 - a.pad) * (long long)C;
+      const int ab = it % NA;
+      const uint32_t aph = (uint32_t)(it / NA) & 1u;
       for (int cb = 0; cb < CB; ++cb) {
-        mbar_wait(&a_empty[cb], ((uint32_t)it & 1u) ^ 1u);
-        const uint32_t dst = smem_u32(sA + cb * A_BLK);
+        mbar_wait(&a_empty[ab * CB + cb], aph ^ 1u);
+        const uint32_t dst = smem_u32(sA + ab * A_BYTES + cb * A_BLK);
         for (int p = pt; p < bpieces && !(a.dbg & 2); p += kProd) {
           const int r = p >> 3, c = p & 7;
           cp_async16(dst + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4), src + (long long)r * C + cb * 64 + c * 8);
         }
         cp_async_wait_all();
         fence_proxy_async();
-        mbar_arrive(&a_full[cb]);
+        mbar_arrive(&a_full[ab * CB + cb]);
       }
     }
   } else if (warp == W_WP) {
@@ -96,14 +100,14 @@ k_convT_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ide
     if (lane == 0) {
       uint32_t ws = 0, ph = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x)
-        for (int h = 0; h < 2; ++h)
+        for (int h = 0; h < NH; ++h)
           for (int cb = 0; cb < CB; ++cb)
             for (int j = 0; j < a.k; ++j) {
               mbar_wait(&w_empty[ws], ph ^ 1u);
               if (a.dbg & 1) mbar_arrive(&w_full[ws]);
               else {
                 mbar_arrive_expect_tx(&w_full[ws], W_BYTES);
-                bulk_g2s(sW + ws * W_BYTES, wtc + ((size_t)(j * CB + cb) * 2 + h) * W_BYTES, W_BYTES, &w_full[ws]);
+                bulk_g2s(sW + ws * W_BYTES, wtc + ((size_t)(j * CB + cb) * NH + h) * W_BYTES, W_BYTES, &w_full[ws]);
               }
               if (++ws == (uint32_t)kTWst) { ws = 0; ph ^= 1u; }
             }
@@ -118,18 +122,21 @@ k_convT_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ide
     uint32_t ws = 0, wph = 0;
     int it = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-      for (int h = 0; h < 2; ++h) {
-        mbar_wait(&acc_empty[h], ((uint32_t)it & 1u) ^ 1u);
+      const int ab = it % NA;
+      const uint32_t aph = (uint32_t)(it / NA) & 1u;
+      for (int h = 0; h < NH; ++h) {
+        const int seq = it * NH + h, buf = seq & 1;
+        mbar_wait(&acc_empty[buf], ((uint32_t)(seq >> 1) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t d0 = tmem_base + (uint32_t)(h * kTRows);
+        const uint32_t d0 = tmem_base + (uint32_t)(buf * kTRows);
         uint32_t acc = 0;
 #pragma unroll 1
         for (int cb = 0; cb < CB; ++cb) {
           if (h == 0) {
-            mbar_wait(&a_full[cb], (uint32_t)it & 1u);
+            mbar_wait(&a_full[ab * CB + cb], aph);
             tc_fence_after();
           }
-          uint32_t x_lo = a_lo0 + (uint32_t)cb * (uint32_t)(A_BLK >> 4);
+          uint32_t x_lo = a_lo0 + (uint32_t)(ab * (A_BYTES >> 4)) + (uint32_t)cb * (uint32_t)(A_BLK >> 4);
           for (int j = 0; j < a.k; ++j, x_lo += tap16) {
             mbar_wait(&w_full[ws], wph);
             tc_fence_after();
@@ -146,12 +153,12 @@ k_convT_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ide
             acc = 1u;
             if (++ws == (uint32_t)kTWst) { ws = 0; wph ^= 1u; }
           }
-          if (h == 1) {                                   // both halves have read this block: it may be refilled
-            if (elect_one()) umma_commit(&a_empty[cb]);
+          if (h == NH - 1) {                              // every half has read this block: it may be refilled
+            if (elect_one()) umma_commit(&a_empty[ab * CB + cb]);
             __syncwarp();
           }
         }
-        if (elect_one()) umma_commit(&acc_full[h]);
+        if (elect_one()) umma_commit(&acc_full[buf]);
         __syncwarp();
       }
     }
@@ -162,9 +169,10 @@ k_convT_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ide
     int it = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
       const ConvTile tile = a.tiles[t];
-      const long long row_base = (tile.out_row0 + tile.q0) * (long long)C;
+      const long long row_base = (tile.out_row0 + tile.q0) * (long long)C;   // channel-last rows of C channels
       const int last = tile.n - 1;
-      for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < NH; ++h) {
+        const int seq = it * NH + h, buf = seq & 1;
         const int co = h * 128 + quarter * 32 + lane;
         const float bias = a.bias[co];
         float al[NACT > 0 ? NACT : 1], ia[NACT > 0 ? NACT : 1];
@@ -190,7 +198,7 @@ k_convT_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ide
           }
         };
         if constexpr (kLoads) issue(0);
-        mbar_wait_relaxed(&acc_full[h], (uint32_t)it & 1u);
+        mbar_wait_relaxed(&acc_full[buf], (uint32_t)(seq >> 1) & 1u);
         tc_fence_after();
 #pragma unroll 1
         for (int cc = 0; cc < 4; ++cc) {
@@ -213,7 +221,7 @@ k_convT_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ide
                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                : "r"(tmem_base + lane_sel + (uint32_t)(h * kTRows + col0 + hh * 16))
+                : "r"(tmem_base + lane_sel + (uint32_t)(buf * kTRows + col0 + hh * 16))
                 : "memory");
             tmem_ld_wait();
 #pragma unroll
@@ -242,7 +250,7 @@ k_convT_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ide
           }
         }
         tc_fence_before();
-        mbar_arrive(&acc_empty[h]);
+        mbar_arrive(&acc_empty[buf]);
       }
     }
   }
@@ -255,34 +263,35 @@ k_convT_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ide
   }
 }
 
-template <int EM, typename ActT>
+template <int C, int EM, typename ActT>
 int launch_convT_em(const ConvArgs& a, const void* wtc, uint32_t idesc, int grid, cudaStream_t st) {
-  constexpr int smem = 4 * kTRA * 128 + kTWst * 128 * 128 + (2 * 4 + 2 * kTWst + 4) * 8 + 16;
+  constexpr int NA = C == 128 ? 2 : 1;
+  constexpr int smem = NA * (C / 64) * kTRA * 128 + kTWst * 128 * 128 + (2 * NA * (C / 64) + 2 * kTWst + 4) * 8 + 16;
   static_assert(smem <= 232448, "shared memory budget exceeded");
   static bool configured = false;
   if (!configured) {
-    VT_CUDA_OK(cudaFuncSetAttribute(k_convT_tc<EM, ActT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    VT_CUDA_OK(cudaFuncSetAttribute(k_convT_tc<C, EM, ActT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  k_convT_tc<EM, ActT><<<grid, (kTEpi + 2 + kProdWarps) * 32, smem, st>>>(a, reinterpret_cast<const uint8_t*>(wtc), idesc);
+  k_convT_tc<C, EM, ActT><<<grid, (kTEpi + 2 + kProdWarps) * 32, smem, st>>>(a, reinterpret_cast<const uint8_t*>(wtc), idesc);
   VT_LAUNCHED();
   return VT_OK;
 }
 
-template <typename ActT>
+template <int C, typename ActT>
 int launch_convT_t(const ConvArgs& a, const void* wtc, uint32_t idesc, int grid, cudaStream_t st) {
   int nsnake = 0;
   while (nsnake < 3 && a.act[nsnake].dst && a.act[nsnake].kind == ACT_SNAKE) ++nsnake;
   const bool oact = nsnake == 0 && a.act[0].dst && a.act[0].kind == ACT_LRELU && a.act_from_out;
   for (int s = nsnake + (oact ? 1 : 0); s < 3; ++s) VT_REQUIRE(!a.act[s].dst, "convT_tc: unsupported activation-copy combination");
   const bool r1 = a.res1 != nullptr, r2 = a.res2 != nullptr, out = a.out != nullptr;
-  if (!r1 && !r2 && !out && nsnake == 1) return launch_convT_em<EM_ACT1, ActT>(a, wtc, idesc, grid, st);
-  if (r1 && !r2 && out && !a.out_accum && nsnake == 1) return launch_convT_em<EM_RES1 | EM_OUT | EM_ACT1, ActT>(a, wtc, idesc, grid, st);
+  if (!r1 && !r2 && !out && nsnake == 1) return launch_convT_em<C, EM_ACT1, ActT>(a, wtc, idesc, grid, st);
+  if (r1 && !r2 && out && !a.out_accum && nsnake == 1) return launch_convT_em<C, EM_RES1 | EM_OUT | EM_ACT1, ActT>(a, wtc, idesc, grid, st);
   if (r1 && r2 && out && !a.out_accum && nsnake == 3)
-    return launch_convT_em<EM_RES1 | EM_RES2 | EM_OUT | EM_ACT3, ActT>(a, wtc, idesc, grid, st);
-  if (r1 && !r2 && out && nsnake == 0 && !oact) return launch_convT_em<EM_RES1 | EM_OUT | EM_ACCUM, ActT>(a, wtc, idesc, grid, st);
+    return launch_convT_em<C, EM_RES1 | EM_RES2 | EM_OUT | EM_ACT3, ActT>(a, wtc, idesc, grid, st);
+  if (r1 && !r2 && out && nsnake == 0 && !oact) return launch_convT_em<C, EM_RES1 | EM_OUT | EM_ACCUM, ActT>(a, wtc, idesc, grid, st);
   if (r1 && !r2 && out && nsnake == 0 && oact)
-    return launch_convT_em<EM_RES1 | EM_OUT | EM_ACCUM | EM_OACT, ActT>(a, wtc, idesc, grid, st);
+    return launch_convT_em<C, EM_RES1 | EM_OUT | EM_ACCUM | EM_OACT, ActT>(a, wtc, idesc, grid, st);
   VT_REQUIRE(false, "convT_tc: no compiled epilogue for res1=%d res2=%d out=%d accum=%d snake=%d", (int)r1, (int)r2, (int)out,
              a.out_accum, nsnake);
   return VT_OK;
@@ -292,7 +301,7 @@ int launch_convT_t(const ConvArgs& a, const void* wtc, uint32_t idesc, int grid,
 
 bool convT_tc_supported(const ConvLayer& L) {
   static const bool on = !(getenv("VT_CONVT") && getenv("VT_CONVT")[0] == '0');
-  return on && L.w_tc && L.cin == 256 && L.cout == 256 && L.stride == 1 && L.out_mul == 1 && (L.k - 1) * L.dil <= 50 && L.pad <= kGap;
+  return on && L.w_tc && L.cin == L.cout && (L.cin == 256 || L.cin == 128) && L.stride == 1 && L.out_mul == 1 && (L.k - 1) * L.dil <= 50 && L.pad <= kGap;
 }
 
 // `tiles`: tiles of 256 output steps.  The weight image is the one pack_conv_tc builds for the 256-column instance.
@@ -315,8 +324,11 @@ int launch_convT_tc(const ConvArgs& a_in, const ConvLayer& L, int act_elem, cons
   const uint32_t fmt = act_elem == ELEM_F16 ? 0u : 1u;
   // M = 128 channels, N = 256 time steps
   const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
-  return act_elem == ELEM_F16 ? tc::launch_convT_t<__half>(a, L.w_tc, idesc, grid, st)
-                              : tc::launch_convT_t<__nv_bfloat16>(a, L.w_tc, idesc, grid, st);
+  if (L.cin == 256)
+    return act_elem == ELEM_F16 ? tc::launch_convT_t<256, __half>(a, L.w_tc, idesc, grid, st)
+                                : tc::launch_convT_t<256, __nv_bfloat16>(a, L.w_tc, idesc, grid, st);
+  return act_elem == ELEM_F16 ? tc::launch_convT_t<128, __half>(a, L.w_tc, idesc, grid, st)
+                              : tc::launch_convT_t<128, __nv_bfloat16>(a, L.w_tc, idesc, grid, st);
 }
 
 }  // namespace vt

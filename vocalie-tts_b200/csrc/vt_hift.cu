@@ -523,6 +523,11 @@ int vt_hift_create(const vt_tensor* tensors, int n_tensors, int operand_dtype, v
       ok = ok && pair_tc_supported(h->src_c1[i][j], h->src_c2[i][j]);
       for (int kk = 0; kk < 3; ++kk) ok = ok && pair_tc_supported(h->rb_c1[i * 3 + kk][j], h->rb_c2[i * 3 + kk][j]);
     }
+    // C = 128 can also run unfused on the transposed single-conv kernel (VT_FUSE_L1=0).  Measured: 8.6 ms against
+    // 7.8 ms fused for the level - unfused, a pair moves 2 KB of HBM per step and the k = 3 / 7 convs fall under the
+    // ridge again.
+    const char* fl1 = getenv("VT_FUSE_L1");
+    if (ok && (kBase >> (i + 1)) == 128 && fl1 && fl1[0] == '0' && convT_tc_supported(h->rb_c1[i * 3][0])) ok = false;
     h->fuse[i] = ok;
   }
   TRY(pack_conv(h, h->conv_post, tab, "conv_post", kBase >> 3, kNfft + 2, 7, 1, 1, 3, kBase >> 3, kSpecCh));
