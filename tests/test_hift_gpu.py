@@ -260,3 +260,53 @@ def test_full_size_batch_cfg2_properties(torch, weights, vocoders):
     solo = voc.forward_packed(mel[b * T:(b + 1) * T].contiguous(), Ts[b:b + 1], f0=f0[b * T:(b + 1) * T].contiguous(),
                               phase_vec=pv[b:b + 1].contiguous(), noise=noise[b * 9 * L:(b + 1) * 9 * L].contiguous())
     assert torch.equal(solo, w[b])
+
+
+def test_bf16_operand_mode_runs_at_its_documented_accuracy(torch, weights):
+    """VT_OPERAND_BF16 is kept as a measured, NOT parity-green mode (an 8-bit mantissa cannot hold
+    60 dB through 72 sequential convs).  The test pins what it does deliver so that the bf16 template instances stay
+    exercised: finite output of the right length at >= 40 dB."""
+    from vocalie_tts_b200.hift import HiFTVocoder
+    Ts = [64, 9]
+    mels, f0s, pvs, nzs = _inputs(torch, Ts, seed=21)
+    voc = HiFTVocoder(weights["unit"], operand="bf16")
+    wavs = voc.inference(mels, f0=f0s, phase_vec=pvs, noise=nzs)
+    W = H.fold_weight_norm(weights["unit"])
+    for b, T in enumerate(Ts):
+        ref = _oracle(torch, W, mels[b], f0s[b], pvs[b], nzs[b])
+        got = wavs[b].cpu()
+        assert got.numel() == 480 * T and bool(torch.isfinite(got).all())
+        assert H.snr_db(ref, got) >= 40.0, (b, H.snr_db(ref, got))
+
+
+def test_fallback_kernels_meet_the_parity_bar():
+    """The kernel selections that are read from the environment once per process (VT_CONVT=0: activation-resident conv
+    at C = 256, VT_PAIR_TR=0: untransposed pair kernel at C = 128) are alternative implementations of the same
+    arithmetic; run them in a fresh process and hold them to the same waveform bar."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import torch\n"
+        "from oracle import hift_oracle as H\n"
+        "from vocalie_tts_b200.hift import HiFTVocoder\n"
+        "sd = H.make_state_dict(0, 'unit'); W = H.fold_weight_norm(sd)\n"
+        "voc = HiFTVocoder(sd, operand='fp16')\n"
+        "Ts = [70, 11]\n"
+        "mels = [H.synth_mel(T, 5, b) for b, T in enumerate(Ts)]\n"
+        "f0s = [H.synth_f0(T, 5, b) for b, T in enumerate(Ts)]\n"
+        "pn = [H.synth_noise(T, 5, b) for b, T in enumerate(Ts)]\n"
+        "w = voc.inference(mels, f0=f0s, phase_vec=[p for p, _ in pn], noise=[n for _, n in pn])\n"
+        "for b in range(len(Ts)):\n"
+        "    ref = H.hift_inference(mels[b], W, f0=f0s[b], phase_vec=pn[b][0], noise=pn[b][1])\n"
+        "    got = w[b].cpu()\n"
+        "    assert got.numel() == ref.numel()\n"
+        "    assert float((got - ref).abs().max()) <= 1e-3 and H.snr_db(ref, got) >= 60.0, H.snr_db(ref, got)\n"
+        "print('fallback-ok')\n"
+    ) % str(root)
+    env = dict(os.environ, VT_CONVT="0", VT_PAIR_TR="0")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "fallback-ok" in r.stdout, r.stdout + r.stderr
