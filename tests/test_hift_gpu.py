@@ -279,10 +279,18 @@ def test_bf16_operand_mode_runs_at_its_documented_accuracy(torch, weights):
         assert H.snr_db(ref, got) >= 40.0, (b, H.snr_db(ref, got))
 
 
-def test_fallback_kernels_meet_the_parity_bar():
+@pytest.mark.parametrize("env", [
+    {"VT_CONVT": "0", "VT_PAIR_TR": "0", "VT_PAIR64": "0"},
+    {"VT_PAIR64": "all"},
+    {"VT_PAIR64": "all", "VT_P64_NA1": "1"},
+    {"VT_PAIR_MC": "1"},
+], ids=["activation-major", "tap-paired-all", "tap-paired-single-a1", "weight-multicast"])
+def test_alternative_kernels_meet_the_parity_bar(env):
     """The kernel selections that are read from the environment once per process (VT_CONVT=0: activation-resident conv
-    at C = 256, VT_PAIR_TR=0: untransposed pair kernel at C = 128) are alternative implementations of the same
-    arithmetic; run them in a fresh process and hold them to the same waveform bar."""
+    at C = 256, VT_PAIR_TR=0: untransposed pair kernel at C = 128, VT_PAIR64=0 / all: tap-paired pair kernel at C = 64
+    for no / every pair, VT_P64_NA1=1: its single-A1 configuration, VT_PAIR_MC=1: weight ring multicast across a 2-CTA
+    cluster) are alternative implementations of the same arithmetic; run them in a fresh process and hold them to the
+    same waveform bar."""
     import os
     import subprocess
     import sys
@@ -307,6 +315,6 @@ def test_fallback_kernels_meet_the_parity_bar():
         "    assert float((got - ref).abs().max()) <= 1e-3 and H.snr_db(ref, got) >= 60.0, H.snr_db(ref, got)\n"
         "print('fallback-ok')\n"
     ) % str(root)
-    env = dict(os.environ, VT_CONVT="0", VT_PAIR_TR="0")
+    env = dict(os.environ, **env)
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "fallback-ok" in r.stdout, r.stdout + r.stderr

@@ -20,6 +20,11 @@ bool convT_tc_supported(const ConvLayer& L);
 int launch_convT_tc(const ConvArgs& a, const ConvLayer& L, int act_elem, const void* tiles, int n_tiles, cudaStream_t st);
 bool pair_tc_supported(const ConvLayer& c1, const ConvLayer& c2);
 int pair_tc_tile_rows(int k);
+bool pair64_tc_supported(const ConvLayer& c1, const ConvLayer& c2);
+int pair64_tc_tile_rows(int k);
+int pack_pair64(ConvLayer& L, std::vector<void*>& allocs);
+int launch_pair64_tc(const ConvArgs& a, const ConvLayer& c1, const ConvLayer& c2, const float* alpha1, const float* alpha2,
+                     int act_elem, cudaStream_t st);
 int launch_pair_tc(const ConvArgs& a, const ConvLayer& c1, const ConvLayer& c2, const float* alpha1, const float* alpha2,
                    int act_elem, cudaStream_t st);
 
@@ -64,6 +69,7 @@ struct Plan {
   Seg tc[3][2];                             // tensor-core tiles per level, [0]: 128 rows, [1]: 256 rows
   Seg tcu[3];                               // tensor-core tiles of the transposed convs (128 input steps)
   Seg pair[3][3];                           // fused ResBlock-pair tiles per level and kernel size 3 / 7 / 11
+  Seg pair64[3];                            // ... of the tap-paired kernel (C = 64 level)
   Seg g_mel, g_melu, g_sd[3];               // 256-step tiles of the K-blocked kernel: gapped mel -> gapped mel,
                                             // gapped mel -> ungapped mel, level-2 STFT rows -> level l
   std::vector<long long> h_off[3], h_offM;
@@ -101,6 +107,8 @@ struct vt_hift {
   Plan plan;
   Workspace ws{};
   bool fuse[3] = {false, false, false};     // level runs its ResBlock pairs on the fused kernel (vt_pair_tc.cu)
+  bool pair64_last = false;                 // VT_PAIR64=all: also the last pair of each ResBlock
+  bool pair64[3] = {false, false, false};   // ... C = 64 level: kernel size index kk runs on the tap-paired kernel (vt_pair64_tc.cu)
   bool have_forward = false;
   // profiling (vt_hift_set_profiling): events around the whole forward and around each stage's
   // run of resblock convolutions (the dominant kernel class)
@@ -193,7 +201,11 @@ int pack_conv(vt_hift* h, ConvLayer& L, const std::map<std::string, HostTensor>&
   rc = dev_upload(h, b.data(), b.size() * 4, (void**)&L.bias);
   if (rc) return rc;
   if (h->use_tc && gemm_mode != GEMM_NONE) return pack_gemm(h, L, w, cin, cin_pad, gemm_mode, op_ld);
-  if (h->use_tc && conv_tc_supported(L)) return pack_conv_tc(L, w, h->act_elem, h->allocs);
+  if (h->use_tc && conv_tc_supported(L)) {
+    rc = pack_conv_tc(L, w, h->act_elem, h->allocs);
+    if (rc) return rc;
+    return pack_pair64(L, h->allocs);
+  }
   return VT_OK;
 }
 
@@ -311,9 +323,13 @@ int build_plan(vt_hift* h, const int32_t* T, int B, cudaStream_t st) {
     add_tiles(tiles, P.lvl[l], B, P.h_off[l].data(), len[l].data(), P.h_off[l].data(), len[l].data(), kTileQ);
     add_tiles(tiles, P.tc[l][0], B, P.h_off[l].data(), len[l].data(), P.h_off[l].data(), len[l].data(), 128);
     add_tiles(tiles, P.tc[l][1], B, P.h_off[l].data(), len[l].data(), P.h_off[l].data(), len[l].data(), 256);
-    for (int kk = 0; kk < 3; ++kk)
+    for (int kk = 0; kk < 3; ++kk) {
       add_tiles(tiles, P.pair[l][kk], B, P.h_off[l].data(), len[l].data(), P.h_off[l].data(), len[l].data(),
                 pair_tc_tile_rows(kRbKernels[kk]));
+      if ((kBase >> (l + 1)) == 64)
+        add_tiles(tiles, P.pair64[kk], B, P.h_off[l].data(), len[l].data(), P.h_off[l].data(), len[l].data(),
+                  pair64_tc_tile_rows(kRbKernels[kk]));
+    }
   }
   // one device block: T | mel_off | off[3] | tiles
   const size_t nI = align_up((size_t)B * 4, 256), nL = align_up((size_t)B * 8, 256);
@@ -529,6 +545,23 @@ int vt_hift_create(const vt_tensor* tensors, int n_tensors, int operand_dtype, v
     const char* fl1 = getenv("VT_FUSE_L1");
     if (ok && (kBase >> (i + 1)) == 128 && fl1 && fl1[0] == '0' && convT_tc_supported(h->rb_c1[i * 3][0])) ok = false;
     h->fuse[i] = ok;
+    if (ok && (kBase >> (i + 1)) == 64) {
+      // Tap-paired kernel per kernel size.  Measured per launch (ncu, us; plain pairs, tap-paired / activation-major):
+      // k = 11: 860-890 / 1010, k = 7: 760-785 / 770-777, k = 3: 717-721 / 593-594 - the paired MMAs halve the
+      // tensor-pipe time, but with it gone the tile period is bound by the CUDA-core work (two Snakes and two epilogues
+      // per step), so only the MMA-bound k = 11 pairs gain.  VT_PAIR64=0: never, VT_PAIR64=all: every kernel size and
+      // also the last pair of each ResBlock.
+      const char* e64 = getenv("VT_PAIR64");
+      h->pair64_last = e64 && e64[0] == 'a';
+      for (int kk = 0; kk < 3; ++kk) {
+        bool p64 = e64 ? (e64[0] == 'a') : kRbKernels[kk] == 11;
+        for (int j = 0; j < 3; ++j) {
+          p64 = p64 && pair64_tc_supported(h->rb_c1[i * 3 + kk][j], h->rb_c2[i * 3 + kk][j]);
+          if (kSrcRbKernels[i] == kRbKernels[kk]) p64 = p64 && pair64_tc_supported(h->src_c1[i][j], h->src_c2[i][j]);
+        }
+        h->pair64[kk] = p64;
+      }
+    }
   }
   TRY(pack_conv(h, h->conv_post, tab, "conv_post", kBase >> 3, kNfft + 2, 7, 1, 1, 3, kBase >> 3, kSpecCh));
   for (int i = 0; i < 5; ++i)
@@ -744,11 +777,15 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
       float* sbuf[2] = {w.S[i], w.S2[i]};
       const int ksrc = kSrcRbKernels[i] == 3 ? 0 : (kSrcRbKernels[i] == 7 ? 1 : 2);
       for (int j = 0; j < 3; ++j) {
-        ConvArgs c = base_args(h->src_c2[i][j], P, P.pair[i][ksrc]);
+        // the tap-paired kernel takes the plain pairs; the last pair of a ResBlock (second residual / running mean /
+        // operand copy: more streams in the fin epilogue) stays on the activation-major kernel - measured faster there
+        const bool p64 = i == 2 && h->pair64[ksrc] && (j < 2 || h->pair64_last);
+        ConvArgs c = base_args(h->src_c2[i][j], P, p64 ? P.pair64[ksrc] : P.pair[i][ksrc]);
         c.res1 = sbuf[j & 1];
         if (j < 2) c.out = sbuf[(j + 1) & 1];
         else { c.res2 = w.U[i]; c.out = w.X[i]; }
-        rc = launch_pair_tc(c, h->src_c1[i][j], h->src_c2[i][j], h->src_a1[i][j], h->src_a2[i][j], ae, st);
+        rc = p64 ? launch_pair64_tc(c, h->src_c1[i][j], h->src_c2[i][j], h->src_a1[i][j], h->src_a2[i][j], ae, st)
+                                   : launch_pair_tc(c, h->src_c1[i][j], h->src_c2[i][j], h->src_a1[i][j], h->src_a2[i][j], ae, st);
         if (rc) return rc;
       }
       mark(h, ("source_resblock" + sfx).c_str(), st);
@@ -756,7 +793,8 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
         const int R = i * 3 + r;
         float* xin[3] = {w.X[i], w.XR[i], w.XR2[i]};
         for (int j = 0; j < 3; ++j) {
-          ConvArgs c = base_args(h->rb_c2[R][j], P, P.pair[i][r]);
+          const bool p64 = i == 2 && h->pair64[r] && (j < 2 || h->pair64_last);
+          ConvArgs c = base_args(h->rb_c2[R][j], P, p64 ? P.pair64[r] : P.pair[i][r]);
           c.res1 = xin[j];
           if (j < 2) c.out = xin[j + 1];
           else {
@@ -768,7 +806,8 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
               c.act_from_out = 1;
             }
           }
-          rc = launch_pair_tc(c, h->rb_c1[R][j], h->rb_c2[R][j], h->rb_a1[R][j], h->rb_a2[R][j], ae, st);
+          rc = p64 ? launch_pair64_tc(c, h->rb_c1[R][j], h->rb_c2[R][j], h->rb_a1[R][j], h->rb_a2[R][j], ae, st)
+                                     : launch_pair_tc(c, h->rb_c1[R][j], h->rb_c2[R][j], h->rb_a1[R][j], h->rb_a2[R][j], ae, st);
           if (rc) return rc;
         }
       }

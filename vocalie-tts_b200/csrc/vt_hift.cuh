@@ -80,6 +80,7 @@ struct ConvArgs {
   int n_tiles;
   unsigned long long tap_skip;   // activation-resident conv: bit (4*column_tile + tap) set = that tap's weights are all zero
   int dbg;              // debug: timing-ablation bits (VT_TC_DBG), 0 normally
+  int mc;               // pair kernel: weight ring multicast across a 2-CTA cluster
   long long* trace;     // debug: per-tile role timestamps of CTA 0 (VT_TC_TRACE=<layer>), nullptr normally
 };
 
@@ -97,6 +98,7 @@ struct ConvLayer {
   int out_mul = 1, phase_c = 0;     // transposed convs run as a k'=3 conv with cout = s*C_out
   float* w = nullptr;               // device [k][cin][cout] fp32
   float* bias = nullptr;            // device [cout]
+  void* w_tp = nullptr;             // device, tap-pair image for the C = 64 pair kernel (vt_pair64_tc.cu)
   void* w_tc = nullptr;             // device, tensor-core operand packing (vt_conv_tc.cu)
   unsigned long long tap_skip = 0;  // all-zero (column tile, tap) pairs of a phase-decomposed transposed conv
   void* w_gemm = nullptr;           // device, K-blocked tensor-core packing (vt_gemm_tc.cu)

@@ -22,15 +22,6 @@
 
 namespace vt {
 
-struct PairArgs {
-  const float* x_in;      // fp32 residual stream [rows][C]; gap rows are zero
-  const float* alpha1;    // Snake before conv1
-  const float* alpha2;    // Snake before conv2
-  const float* bias1;     // conv1 bias
-  const uint8_t* w1;      // conv1 / conv2 weights, pack_conv_tc images (chunk = (tap, 64-channel block))
-  const uint8_t* w2;
-  int k, dil;
-};
 
 namespace tc {
 
@@ -147,7 +138,8 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
       mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], NMID * 32);
       mbar_init(&d2_full[i], 1); mbar_init(&d2i_full[i], kFin * 32);
     }
-    for (int i = 0; i < W_ST; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    // weight-ring slots are released by the MMA warps of every CTA that received the multicast copy
+    for (int i = 0; i < W_ST; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], a.mc ? 2 : 1); }
     fence_barrier_init();
   }
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -164,9 +156,19 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Weight multicast (a.mc): the two CTAs of a cluster walk the same weight sequence in lockstep, each fetching half
+  // of every ring slot for both.  They must run the same number of tiles: an odd tile count is padded with a dummy
+  // (the last tile again with n = 0: every store of the epilogues is masked by n).
+  if (a.mc) cluster_sync_all();              // the peer's barriers are initialised before anything remote lands on them
 
-  const int n_tiles = a.n_tiles;
+  const int n_tiles = a.mc ? (a.n_tiles + 1) & ~1 : a.n_tiles;
   const int n_my = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  auto get_tile = [&](int i) {
+    const int t = (int)blockIdx.x + i * (int)gridDim.x;
+    ConvTile tl = a.tiles[t < a.n_tiles ? t : a.n_tiles - 1];
+    if (t >= a.n_tiles) tl.n = 0;
+    return tl;
+  };
   const int H2 = (p.k - 1) / 2, H1 = (p.k - 1) * p.dil / 2;
   const int nchunks = p.k * CB;
 
@@ -256,6 +258,7 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
         return done != 0;
       };
       const int R1 = 256 + 2 * H1;
+      const uint32_t mc_rank = a.mc ? cluster_ctarank() : 0u;
       // weight ring state: step s, pass, chunk c
       uint32_t ws = 0, wph = 0;
       int w_s = 0, w_pass = 0, w_c = 0;
@@ -277,7 +280,12 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
           if (a.dbg & 1) mbar_arrive(&w_full[ws]);
           else {
             mbar_arrive_expect_tx(&w_full[ws], W_BYTES);
-            bulk_g2s(sW + ws * W_BYTES, wsrc + (size_t)w_c * W_BYTES, W_BYTES, &w_full[ws]);
+            if (a.mc) {
+              const uint32_t hoff = mc_rank * (uint32_t)(W_BYTES / 2);
+              bulk_g2s_mc(sW + ws * W_BYTES + hoff, wsrc + (size_t)w_c * W_BYTES + hoff, W_BYTES / 2, &w_full[ws], (uint16_t)3);
+            } else {
+              bulk_g2s(sW + ws * W_BYTES, wsrc + (size_t)w_c * W_BYTES, W_BYTES, &w_full[ws]);
+            }
           }
           if (++ws == (uint32_t)W_ST) { ws = 0; wph ^= 1u; }
           if (++w_c == nchunks) {
@@ -289,7 +297,7 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
         }
         if (xi < n_my && test(&x_empty[xs], xph ^ 1u)) {
           if (xr == 0) {
-            const ConvTile tl = a.tiles[blockIdx.x + xi * gridDim.x];
+            const ConvTile tl = get_tile(xi);
             xsrc = p.x_in + (tl.in_row0 + tl.q0 - H1 - H2) * (long long)C;
           }
           const int rows = R1 - xr < SLAB_ROWS ? R1 - xr : SLAB_ROWS;
@@ -306,6 +314,13 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
         if (!progress) {
           __nanosleep(32);
           if (clock64() - t0 > 8000000000LL) __trap();     // a protocol bug must fault the launch, not hang
+        }
+      }
+      if (a.mc) {
+        // the peer's last slot releases arrive on THIS CTA's barriers: take them before the CTA may exit
+        for (int q = 0; q < W_ST; ++q) {
+          mbar_wait_relaxed(&w_empty[ws], wph ^ 1u);
+          if (++ws == (uint32_t)W_ST) { ws = 0; wph ^= 1u; }
         }
       }
     }
@@ -370,7 +385,8 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
                                   idesc, ks == 0 ? acc : 1u);
                 }
               }
-              umma_commit(&w_empty[ws]);
+              if (a.mc) umma_commit_mc(&w_empty[ws], (uint16_t)3);
+              else umma_commit(&w_empty[ws]);
             }
             __syncwarp();
             acc = 1u;
@@ -400,7 +416,7 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
       const uint32_t coff = (uint32_t)(c >> 6) * (uint32_t)(kPairRA2 * 128) + (uint32_t)((c & 7) * 2);
       const uint32_t chunk = (uint32_t)((c & 63) >> 3);
       for (int i = 0; i < n_my; ++i) {
-        const ConvTile tile = a.tiles[blockIdx.x + i * gridDim.x];
+        const ConvTile tile = get_tile(i);
         mbar_wait_relaxed(&d1_full[0], (uint32_t)i & 1u);
         mbar_wait_relaxed(&a2_empty[0], ((uint32_t)i & 1u) ^ 1u);
         tc_fence_after();
@@ -441,7 +457,7 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
       float x[32];
       // only (first element of this thread's column, rows) of a tile are kept in registers
       auto tile_base = [&](int i, int& n) {
-        const ConvTile tl = a.tiles[blockIdx.x + i * gridDim.x];
+        const ConvTile tl = get_tile(i);
         n = tl.n;
         return (tl.out_row0 + tl.q0) * (long long)C + c;
       };
@@ -612,7 +628,7 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
     auto pf_issue = [&](int n, float4 (&pr)[8]) {
       const int ti = n / BPW;
       if (ti >= n_my) return;
-      const ConvTile tl = a.tiles[blockIdx.x + ti * gridDim.x];
+      const ConvTile tl = get_tile(ti);
       int mb, c0, nvalid; long long idx0;
       blk_geom(tl, grp + (n - ti * BPW) * (NEPI / 4), mb, c0, idx0, nvalid);
 #pragma unroll
@@ -675,7 +691,7 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
     // prologue: preload D2 for the first NBUF tiles
     if (do_fin && kPreload) {
       for (int j = 0; j < NBUF && j < n_my; ++j) {
-        const ConvTile tl = a.tiles[blockIdx.x + j * gridDim.x];
+        const ConvTile tl = get_tile(j);
 #pragma unroll 1
         for (int blk = grp; blk < NBLK; blk += NEPI / 4) {
           float4 pre[8];
@@ -690,7 +706,7 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
     for (int i = 0; i < n_my; ++i) {
       const int b = i % NBUF;
       const uint32_t u = (uint32_t)(i / NBUF);
-      const ConvTile tile = a.tiles[blockIdx.x + i * gridDim.x];
+      const ConvTile tile = get_tile(i);
       if (do_mid) {
         const int b2 = i % NA2;
         mbar_wait_relaxed(&d1_full[b], u & 1u);
@@ -740,7 +756,7 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
         if (warp == 0 && lane == 0) trace_ev(a.trace, i, 4);
         if constexpr (kPreload) {
           const bool has_next = i + NBUF < n_my;
-          const ConvTile tnext = has_next ? a.tiles[blockIdx.x + (i + NBUF) * gridDim.x] : tile;
+          const ConvTile tnext = has_next ? get_tile(i + NBUF) : tile;
 #pragma unroll 1
           for (int blk = grp; blk < NBLK && !(a.dbg & 4); blk += NEPI / 4) {
             float4 pre[8];
@@ -770,6 +786,7 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
 
   tc_fence_before();
   __syncthreads();
+  if (a.mc) cluster_sync_all();              // no CTA leaves while its peer may still multicast into it
   if (warp == W_MMA) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -790,7 +807,17 @@ int launch_pair_em(const ConvArgs& a, const PairArgs& p, uint32_t idesc, int gri
     VT_CUDA_OK(cudaFuncSetAttribute(k_pair_tc<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, kPreload, TR, ActT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  k_pair_tc<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, kPreload, TR, ActT><<<grid, PC::WARPS * 32, smem, st>>>(a, p, idesc);
+  if (a.mc) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(PC::WARPS * 32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    VT_CUDA_OK(cudaLaunchKernelEx(&cfg, k_pair_tc<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, kPreload, TR, ActT>, a, p, idesc));
+  } else {
+    k_pair_tc<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, kPreload, TR, ActT><<<grid, PC::WARPS * 32, smem, st>>>(a, p, idesc);
+  }
   VT_LAUNCHED();
   return VT_OK;
 }
@@ -862,7 +889,13 @@ int launch_pair_tc(const ConvArgs& a_in, const ConvLayer& c1, const ConvLayer& c
     VT_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
   }
   const int C = c1.cin;
-  const int grid = a.n_tiles < sm_count ? a.n_tiles : sm_count;
+  // VT_PAIR_MC=1: the two CTAs of a cluster share one weight stream (each fetches half of every ring slot and
+  // multicasts it).  Verified, but measured equal to per-CTA streams (29.85 against 29.84-30.13 ms per forward): the
+  // cost of the weight stream is on the SM side (shared-memory writes), not in L2 reads - off by default.
+  static const bool use_mc = getenv("VT_PAIR_MC") && getenv("VT_PAIR_MC")[0] == '1';
+  a.mc = use_mc ? 1 : 0;
+  const int n_even = (a.n_tiles + 1) & ~1;
+  const int grid = a.mc ? (n_even < (sm_count & ~1) ? n_even : (sm_count & ~1)) : (a.n_tiles < sm_count ? a.n_tiles : sm_count);
   // debug timeline: VT_TC_TRACE=<conv1 layer name> dumps CTA 0's per-tile role timestamps to stderr
   static const char* trace_name = getenv("VT_TC_TRACE");
   static long long* d_trace = nullptr;

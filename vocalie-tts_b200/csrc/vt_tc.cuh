@@ -5,6 +5,18 @@
 #include "vt_hift.cuh"
 
 namespace vt {
+
+// One ResBlock iteration run as a fused pair (vt_pair_tc.cu, vt_pair64_tc.cu)
+struct PairArgs {
+  const float* x_in;      // fp32 residual stream [rows][C]; gap rows are zero
+  const float* alpha1;    // Snake before conv1
+  const float* alpha2;    // Snake before conv2
+  const float* bias1;     // conv1 bias
+  const uint8_t* w1;      // conv1 / conv2 weights: pack_conv_tc images (chunk = (tap, 64-channel block)), or the
+  const uint8_t* w2;      // tap-pair images of pack_pair64
+  int k, dil;
+};
+
 namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -72,6 +84,22 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// Same copy delivered to the same CTA-relative offset of every CTA in `mask` (cluster ranks); each destination's
+// mbarrier at the offset of `bar` receives the complete_tx.
+__device__ __forceinline__ void bulk_g2s_mc(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -125,6 +153,12 @@ __device__ __forceinline__ void umma_f16_lh(uint32_t d_tmem, uint32_t a_lo, uint
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// The arrive is delivered to the barrier at this offset in every CTA of `mask`.
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -181,6 +215,26 @@ constexpr int kStageLd = 36;   // floats per staged row (32 + 4 pad: conflict-fr
 __device__ __forceinline__ float snake_f(float v, float alpha, float inv_alpha) {
   const float s = __sinf(v * alpha);
   return fmaf(inv_alpha, s * s, v);
+}
+
+// The same function on the FMA pipe only.  MUFU.SIN issues one warp instruction per ~32 cycles per scheduler on
+// sm_100a (measured: a producer warp alone needs 32 cycles per Snake), i.e. 4 sines per clock per SM - a fused
+// ResBlock pair at C = 64 needs 35 k of them per tile, more time than its MMAs.  Here: u = v*alpha/pi rounded to the
+// nearest integer by the 1.5*2^23 trick, r = u - rint(u) in [-0.5, 0.5], sin^2(pi r) = t*P(t) with t = r^2 and a
+// degree-4 minimax P (absolute error 1.3e-6 in fp32 Horner - the class of sin.approx squared).  10 FMA-pipe
+// instructions against 4 + 1 MUFU: kernels split their elements between the two forms so that both pipes are busy.
+// alpha / pi is loop-invariant per channel and hoisted by the compiler.  |v*alpha| < 2^22 * pi is assumed.
+__device__ __forceinline__ float snake_poly(float v, float alpha, float inv_alpha) {
+  const float a_pi = alpha * 0.318309886f;
+  const float m = fmaf(v, a_pi, 12582912.0f);
+  const float rn = m - 12582912.0f;
+  const float r = fmaf(v, a_pi, -rn);
+  const float t = r * r;
+  float p = fmaf(t, 10.603050f, -29.434399f);
+  p = fmaf(t, p, 42.643887f);
+  p = fmaf(t, p, -32.465050f);
+  p = fmaf(t, p, 9.8695183f);
+  return fmaf(inv_alpha * t, p, v);
 }
 
 // Debug timeline (VT_TC_TRACE): CTA 0 records clock64 at role events of its first kTraceTiles tiles.
