@@ -373,7 +373,7 @@ Workspace carve_ws(const vt_hift* h, int B, long long total_T, void* base) {
   w.f0a = (float*)take((size_t)rowsM * kF0Ch * 4);
   w.f0b = (float*)take((size_t)rowsM * kF0Ch * 4);
   w.f0 = (float*)take((size_t)rowsM * 4);
-  w.phase_base = (double*)take((size_t)kHarm * rowsM * 8);
+  w.phase_base = (double*)take((size_t)kHarm * rowsM * 16);   // phase prefix | increment, per (harmonic, frame)
   w.s = (float*)take((size_t)total_T * kSPF * 4 + 64);
   w.cap_rowsM = total_T + (long long)B * kGap + kGap + 512;
   w.xpre = (float*)take((size_t)w.cap_rowsM * kBase * 4);

@@ -54,16 +54,20 @@ __global__ void k_phase_base(const float* __restrict__ f0, const int* __restrict
   const long long o = mel_off[b];
   double acc = 0.0;
   double* dst = base + (long long)h * total_T + o;
+  double* inc = dst + (long long)kHarm * total_T;      // second half of the buffer: the per-frame increment itself
   for (int t = 0; t < T[b]; ++t) {
+    const double d = (double)harmonic_inc(f0[o + t], h);
     dst[t] = acc;
-    acc += (double)kSPF * (double)harmonic_inc(f0[o + t], h);
+    inc[t] = d;                                          // (k_sine_source: no IEEE division per sample and harmonic)
+    acc += (double)kSPF * d;
   }
 }
 
-// Philox4x32-10 counter-based generator for the performance mode (no explicit noise given).
+// Philox4x32-7 counter-based generator for the performance mode (no explicit noise given; 7 rounds is the
+// fewest that passes BigCrush in Salmon et al., SC'11 - the generator is a third of this kernel's instructions).
 __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
 #pragma unroll
-  for (int i = 0; i < 10; ++i) {
+  for (int i = 0; i < 7; ++i) {
     const unsigned hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
     const unsigned hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
     ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
@@ -118,7 +122,8 @@ k_sine_source(const float* __restrict__ f0, const int* __restrict__ mel_off, con
     const bool voiced = f > 10.0f;
     const float uv = voiced ? 1.0f : 0.0f;
     // upstream: noise_amp = uv * noise_std + (1 - uv) * sine_amp / 3
-    const float namp = __fadd_rn(__fmul_rn(uv, 0.003f), __fdiv_rn(__fmul_rn(1.0f - uv, 0.1f), 3.0f));
+    // (uv in {0, 1}: both values are exact compile-time constants of the same fp32 expression)
+    const float namp = voiced ? 0.003f : 0.1f / 3.0f;
     float z[kHarm];
     if (noise) {
 #pragma unroll
@@ -139,8 +144,8 @@ k_sine_source(const float* __restrict__ f0, const int* __restrict__ mel_off, con
     float acc = lb;
 #pragma unroll
     for (int h = 0; h < kHarm; ++h) {
-      const float inc = harmonic_inc(f, h);
-      const double c64 = base[(long long)h * total_T + o + t] + (double)(j + 1) * (double)inc;
+      const long long bi = (long long)h * total_T + o + t;
+      const double c64 = base[bi] + (double)(j + 1) * base[bi + (long long)kHarm * total_T];
       const float c = __double2float_rn(c64);
       const float frac = c - truncf(c);                       // torch `% 1` on a non-negative value
       const float theta = __fmul_rn(frac, 6.283185307179586f);  // 2*pi as an fp32 scalar
