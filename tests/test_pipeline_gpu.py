@@ -96,6 +96,38 @@ def test_host_api_roundtrip_and_pcm16(setup):
     assert np.array_equal(c.audio, po.pcm16_encode(a.audio))
 
 
+def test_submit_collect_pipelines_jobs_with_identical_results(setup):
+    """The asynchronous serving loop (two jobs in flight, device-to-host copies on a second stream) returns exactly
+    what the synchronous run() returns, job by job, and refuses a third job in flight."""
+    torch, sd, voc = setup
+    from vocalie_tts_b200.pipeline import VocoderPipeline
+    jobs = [np.array([20, 35], np.int32), np.array([12], np.int32), np.array([30, 9, 17], np.int32), np.array([25, 25], np.int32)]
+    mels = [torch.cat([H.synth_mel(int(T), 40 + j, b).t() for b, T in enumerate(Ts)]).contiguous().numpy() for j, Ts in enumerate(jobs)]
+    pipe = VocoderPipeline(voc, chunk_gap_ms=250)
+    want = []
+    for j, Ts in enumerate(jobs):
+        r = pipe.run(mels[j], Ts, seed=j)
+        want.append((r.audio.copy(), r.total_samples, r.segments.copy()))
+    got, pending = [], None
+    for j, Ts in enumerate(jobs):
+        t = pipe.submit(mels[j], Ts, seed=j)
+        if pending is not None:
+            r = pipe.collect(pending)
+            got.append((r.audio.copy(), r.total_samples, r.segments.copy()))
+        pending = t
+    with pytest.raises(RuntimeError):
+        pipe.submit(mels[0], jobs[0], seed=0)
+        pipe.submit(mels[0], jobs[0], seed=0)          # slot of the uncollected job
+    # drain whatever is in flight, oldest first
+    for t in range(pending, pipe._n_submitted):
+        r = pipe.collect(t)
+        if t == pending:
+            got.append((r.audio.copy(), r.total_samples, r.segments.copy()))
+    assert len(got) == len(want)
+    for (ga, gn, gs), (wa, wn, ws) in zip(got, want):
+        assert gn == wn and np.array_equal(ga, wa) and np.array_equal(gs, ws)
+
+
 def test_backend_drop_in(setup, tmp_path):
     torch, sd, voc = setup
     from vocalie_tts_b200 import backend as B, BackendUnavailableError

@@ -45,6 +45,10 @@ class VocoderPipeline:
         self._wav = None
         self._out = None
         self.last_launches = 0
+        self._slots = None            # submit()/collect(): double-buffered device output + pinned host staging
+        self._copy_stream = None
+        self._h2d_done = None
+        self._n_submitted = 0
 
     def set_shard(self, chunk_ids, n_total_chunks: int) -> None:
         """Declare that this pipeline holds ``chunk_ids`` (sorted job-order indices) of a job sharded
@@ -84,6 +88,7 @@ class VocoderPipeline:
         r = _post.post_process_device(wav, seg_off, prm, out=self._out, read_back=read_back)
         # the library's per-thread launch counter is reset by vt_hift_forward and keeps counting through the post calls
         self.last_launches = _post.last_launch_count()
+        self._last_post = r
         return JobResult(r.out, r.total if r.total is not None else cap, r.results)
 
     def run(self, mel_host, T, *, seed: int = 0) -> JobResult:
@@ -108,6 +113,77 @@ class VocoderPipeline:
         self._host_out[:n].copy_(res.audio[:n], non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return JobResult(self._host_out[:n].numpy(), n, res.segments)
+
+    # ---- pipelined serving loop: submit(job k+1) is enqueued while job k's audio is still crossing PCIe
+    def submit(self, mel_host, T, *, seed: int = 0) -> int:
+        """Enqueue one job (pinned host mels -> device -> HiFT -> post) without waiting for it and start the
+        device-to-host copy of its audio on a second stream; returns a ticket for ``collect``.  At most two jobs may
+        be in flight (two output slots).  The input is staged exactly like ``run``; a caller that fills
+        ``pinned_input()`` in place must not overwrite it before the NEXT submit/collect returns."""
+        torch = _torch()
+        T = np.ascontiguousarray(T, dtype=np.int32)
+        total_T = int(T.astype(np.int64).sum())
+        n_cap = total_T * SAMPLES_PER_FRAME + len(T) * int(self.post_params(len(T)).gap_frames)
+        odt = torch.int16 if self.opts["out_pcm16"] else torch.float32
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.voc.device)
+        if self._slots is None:
+            self._slots = [dict(dev=None, host=None, tot=torch.zeros(1, dtype=torch.int64).pin_memory(), res=None, n_seg=0,
+                                done=torch.cuda.Event(), busy=False) for _ in range(2)]
+        ticket = self._n_submitted
+        slot = self._slots[ticket & 1]
+        if slot["busy"]:
+            raise RuntimeError("two jobs are already in flight: collect() one first")
+        if slot["dev"] is None or slot["dev"].numel() < max(n_cap, 4) or slot["dev"].dtype != odt:
+            # a free slot grows on its own: the other one may still be in flight
+            slot["dev"] = torch.empty(max(n_cap, 4), dtype=odt, device=self.voc.device)
+            slot["host"] = torch.empty(max(n_cap, 4), dtype=odt).pin_memory()
+        src = torch.as_tensor(mel_host, dtype=torch.float32).reshape(total_T, N_MEL)
+        if self._h2d_done is not None:
+            self._h2d_done.synchronize()      # the previous job's input has left the pinned staging buffer
+        hin = self.pinned_input(total_T)
+        if src.data_ptr() != hin.data_ptr():
+            hin.copy_(src)
+        dev = self._dev_in[: src.numel()].view(total_T, N_MEL)
+        cur = torch.cuda.current_stream()
+        dev.copy_(hin, non_blocking=True)
+        self._h2d_done = torch.cuda.Event()
+        self._h2d_done.record(cur)
+        saved_out = self._out
+        self._out = slot["dev"]
+        try:
+            self.run_device(dev, T, seed=seed, read_back=False)
+        finally:
+            self._out = saved_out
+        r = self._last_post
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        if slot["res"] is None or slot["res"].shape != r.results_dev.shape:
+            slot["res"] = torch.empty(r.results_dev.shape, dtype=r.results_dev.dtype).pin_memory()
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(ready)
+            slot["tot"].copy_(r.total_dev, non_blocking=True)
+            slot["res"].copy_(r.results_dev, non_blocking=True)
+            slot["host"][:n_cap].copy_(slot["dev"][:n_cap], non_blocking=True)   # worst-case length: the total is not known yet
+            slot["done"].record(self._copy_stream)
+        # the compute stream must not reuse the slot before its copy has left (it is reused two submits later)
+        slot.update(n_seg=len(T), busy=True, bytes=n_cap * slot["dev"].element_size(), keep=r)   # keep: the copy reads r's tensors
+        self._n_submitted += 1
+        return ticket
+
+    def collect(self, ticket: int) -> JobResult:
+        """Wait for a submitted job; returns its stitched audio as a numpy view of the pinned slot (valid until the
+        slot is reused by the second submit after this one)."""
+        torch = _torch()
+        slot = self._slots[ticket & 1]
+        if not slot["busy"]:
+            raise RuntimeError("ticket is not in flight")
+        slot["done"].synchronize()
+        torch.cuda.current_stream().wait_event(slot["done"])
+        slot["busy"] = False
+        n = int(slot["tot"].item())
+        self.last_d2h_bytes = slot["bytes"]
+        return JobResult(slot["host"][:n].numpy(), n, slot["res"].numpy()[: slot["n_seg"]].copy())
 
     def pinned_input(self, total_T: int):
         """A pinned host buffer [total_T, 80] callers can fill in place to skip the staging copy."""

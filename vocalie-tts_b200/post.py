@@ -55,6 +55,8 @@ class PostResult:
     out: Any                 # torch CUDA tensor (float32 or int16), capacity >= total
     total: Optional[int]     # total output samples (None when not read back)
     results: Optional[np.ndarray]  # [n_seg, 8] float64: start,end,peak,scale,dst,len,peak_used,-
+    results_dev: Any = None  # the same table and the total as CUDA tensors (always set: callers that defer the
+    total_dev: Any = None    # read-back copy them on their own stream)
 
 
 class _Workspace:
@@ -127,9 +129,9 @@ def post_process_device(audio, seg_off, params: PostParams, *, out=None, range_o
                             _ptr(peak_override), _ptr(out), out.numel(), _ptr(res), _ptr(tot),
                             _ptr(ws), ws.numel(), st), "vt_post_write")
     if not read_back:
-        return PostResult(out, None, None)
+        return PostResult(out, None, None, res, tot)
     res_h = res.cpu().numpy()[:n_seg]
-    return PostResult(out, int(tot.item()), res_h)
+    return PostResult(out, int(tot.item()), res_h, res, tot)
 
 
 # ------------------------------------------------------------------------- reference-facing layer
