@@ -1,3 +1,4 @@
+# Usage on a GPU box: bash tools/bench_ngpu.sh N   (torchrun bench.py on N GPUs, JSON record into gpurun_out/)
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 N=$1
