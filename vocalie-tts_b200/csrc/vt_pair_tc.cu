@@ -81,7 +81,11 @@ struct PairCfg {
   static constexpr bool kCombined = NBUF == 1 && !TR;
   static constexpr int W_MID = kCombined ? 0 : NEPI;
   static constexpr int W_MMA = kCombined ? NEPI : 2 * NEPI;
-  static constexpr int WARPS = W_MMA + 2 + NPROD;      // + MMA warp, loader warp (weights and x ring)
+  // C = 128 has a spare warp slot (22 warps are allocated as 24): the x ring gets its own loader thread there, so
+  // the weight loader never waits behind a tile-table load or an x slab.  At C = 64 (20 warps exactly) one thread
+  // polls both rings.
+  static constexpr bool kSplitLoader = C == 128;
+  static constexpr int WARPS = W_MMA + 2 + NPROD + (kSplitLoader ? 1 : 0);   // + MMA warp, loader warp(s)
 };
 
 template <typename T> __device__ __forceinline__ unsigned short to_op_bits(float v);
@@ -172,7 +176,9 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
   const int H2 = (p.k - 1) / 2, H1 = (p.k - 1) * p.dil / 2;
   const int nchunks = p.k * CB;
 
-  if (warp >= W_AP) {
+  constexpr bool kSplitLoader = PC::kSplitLoader;
+  constexpr int W_XL = W_AP + NPROD;                      // x loader (split mode)
+  if (warp >= W_AP && warp < W_AP + NPROD) {
     // ---------------- producers: fp32 slabs of the x ring -> Snake1 -> fp16 A1 tile (SWIZZLE_128B).  All global
     // latency is taken by the bulk-copy engine; this loop is shared-memory to shared-memory.  A thread owns the
     // channels [4*ch, 4*ch+4) and [C/2 + 4*ch, +4) (two conflict-free 16-byte reads per row) for every row it
@@ -240,6 +246,59 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
       fence_proxy_async();
       if (pt == 0) trace_ev(a.trace, i, 1);
       mbar_arrive(&a1_full[b1]);
+    }
+  } else if (kSplitLoader && warp == W_XL) {
+    // ---------------- x loader (split mode): the tiles' fp32 rows (with halo), slab by slab
+    if (lane == 0) {
+      const int R1 = 256 + 2 * H1;
+      uint32_t xs = 0, xph = 0;
+      ConvTile tl = n_my > 0 ? get_tile(0) : ConvTile{};
+      for (int xi = 0; xi < n_my; ++xi) {
+        const float* xsrc = p.x_in + (tl.in_row0 + tl.q0 - H1 - H2) * (long long)C;
+        if (xi + 1 < n_my) tl = get_tile(xi + 1);          // next tile's entry: off the critical path
+        for (int xr = 0; xr < R1; xr += SLAB_ROWS) {
+          const int rows = R1 - xr < SLAB_ROWS ? R1 - xr : SLAB_ROWS;
+          mbar_wait(&x_empty[xs], xph ^ 1u);
+          if (a.dbg & 2) mbar_arrive(&x_full[xs]);
+          else {
+            mbar_arrive_expect_tx(&x_full[xs], (uint32_t)(rows * C * 4));
+            bulk_g2s(sX + xs * kSlabBytes, xsrc + (long long)xr * C, (uint32_t)(rows * C * 4), &x_full[xs]);
+          }
+          if (++xs == (uint32_t)NSLAB) { xs = 0; xph ^= 1u; }
+        }
+      }
+    }
+  } else if (kSplitLoader && warp == W_WP) {
+    // ---------------- weight loader (split mode): chunk order mirrors the MMA issue order
+    if (lane == 0) {
+      const uint32_t mc_rank = a.mc ? cluster_ctarank() : 0u;
+      uint32_t ws = 0, wph = 0;
+      for (int s = 0; s < n_my + SKEW; ++s)
+        for (int pass = 0; pass < 2; ++pass) {
+          if (pass == 0 ? s >= n_my : s < SKEW) continue;
+          const uint8_t* wsrc = pass == 0 ? p.w1 : p.w2;
+          for (int w_c = 0; w_c < nchunks; ++w_c) {
+            mbar_wait(&w_empty[ws], wph ^ 1u);
+            if (a.dbg & 1) mbar_arrive(&w_full[ws]);
+            else {
+              mbar_arrive_expect_tx(&w_full[ws], W_BYTES);
+              if (a.mc) {
+                const uint32_t hoff = mc_rank * (uint32_t)(W_BYTES / 2);
+                bulk_g2s_mc(sW + ws * W_BYTES + hoff, wsrc + (size_t)w_c * W_BYTES + hoff, W_BYTES / 2, &w_full[ws], (uint16_t)3);
+              } else {
+                bulk_g2s(sW + ws * W_BYTES, wsrc + (size_t)w_c * W_BYTES, W_BYTES, &w_full[ws]);
+              }
+            }
+            if (++ws == (uint32_t)W_ST) { ws = 0; wph ^= 1u; }
+          }
+        }
+      if (a.mc) {
+        // the peer's last slot releases arrive on THIS CTA's barriers: take them before the CTA may exit
+        for (int q = 0; q < W_ST; ++q) {
+          mbar_wait(&w_empty[ws], wph ^ 1u);
+          if (++ws == (uint32_t)W_ST) { ws = 0; wph ^= 1u; }
+        }
+      }
     }
   } else if (warp == W_WP) {
     // ---------------- loader: ONE thread feeds both rings by polling (non-blocking test_wait), so neither ring
