@@ -331,6 +331,7 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
       uint32_t xs = 0, xph = 0;
       int xi = 0, xr = 0;
       const float* xsrc = nullptr;
+      ConvTile tl_next = n_my > 0 ? get_tile(0) : ConvTile{};
       const long long t0 = clock64();
       while (w_s < n_my + SKEW || xi < n_my) {
         bool progress = false;
@@ -356,8 +357,9 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
         }
         if (xi < n_my && test(&x_empty[xs], xph ^ 1u)) {
           if (xr == 0) {
-            const ConvTile tl = get_tile(xi);
-            xsrc = p.x_in + (tl.in_row0 + tl.q0 - H1 - H2) * (long long)C;
+            // the entry was requested one tile ahead: the loader never stalls on the table while weights are due
+            xsrc = p.x_in + (tl_next.in_row0 + tl_next.q0 - H1 - H2) * (long long)C;
+            if (xi + 1 < n_my) tl_next = get_tile(xi + 1);
           }
           const int rows = R1 - xr < SLAB_ROWS ? R1 - xr : SLAB_ROWS;
           if (a.dbg & 2) mbar_arrive(&x_full[xs]);
