@@ -889,10 +889,13 @@ int launch_pair_pre(const ConvArgs& a, const PairArgs& p, uint32_t idesc, int gr
     if (p.k == 3) return launch_pair_em<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, false, false, ActT>(a, p, idesc, grid, st);
     return launch_pair_em<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, true, false, ActT>(a, p, idesc, grid, st);
   } else {
+    // VT_PAIR_TR=0: never transposed; =7: only k <= 7 (the k = 11 pairs then run the combined TMEM-preload kernel,
+    // which was faster while one thread polled both rings: 0.88 against ~1.0 ms; with separate loader threads the
+    // transposed kernel wins for every kernel size - level 1 5.9 -> 5.67 ms)
     static const bool tr = !(getenv("VT_PAIR_TR") && getenv("VT_PAIR_TR")[0] == '0');
-    if (tr && p.k <= 7) {
-      // transposed MMA: M = 128 output channels, N = 256 time steps (k = 11 tiles keep the TMEM-preload kernel: under
-      // their weight stream the residual loads of a register-prefetch epilogue take several microseconds)
+    static const bool tr_k7 = getenv("VT_PAIR_TR") && getenv("VT_PAIR_TR")[0] == '7';
+    if (tr && (p.k <= 7 || !tr_k7)) {
+      // transposed MMA: M = 128 output channels, N = 256 time steps
       const uint32_t idesc_t = (idesc & ~((0x3Fu << 17) | (0x1Fu << 24))) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
       return launch_pair_em<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, false, true, ActT>(a, p, idesc_t, grid, st);
     }
