@@ -81,9 +81,8 @@ struct PairCfg {
   static constexpr bool kCombined = NBUF == 1 && !TR;
   static constexpr int W_MID = kCombined ? 0 : NEPI;
   static constexpr int W_MMA = kCombined ? NEPI : 2 * NEPI;
-  // C = 128 has a spare warp slot (22 warps are allocated as 24): the x ring gets its own loader thread there, so
-  // the weight loader never waits behind a tile-table load or an x slab.  At C = 64 (20 warps exactly) one thread
-  // polls both rings.
+  // C = 128 has a spare warp slot (22 warps are allocated as 24): the x ring's loader thread gets its own warp there;
+  // at C = 64 (20 warps exactly) it shares the weight loader's warp.
   static constexpr bool kSplitLoader = C == 128;
   static constexpr int WARPS = W_MMA + 2 + NPROD + (kSplitLoader ? 1 : 0);   // + MMA warp, loader warp(s)
 };
@@ -177,7 +176,8 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
   const int nchunks = p.k * CB;
 
   constexpr bool kSplitLoader = PC::kSplitLoader;
-  constexpr int W_XL = W_AP + NPROD;                      // x loader (split mode)
+  constexpr int W_XL = kSplitLoader ? W_AP + NPROD : W_WP;    // x loader: its own warp, or lane 1 of the weight loader's
+  constexpr int kXlLane = kSplitLoader ? 0 : 1;
   if (warp >= W_AP && warp < W_AP + NPROD) {
     // ---------------- producers: fp32 slabs of the x ring -> Snake1 -> fp16 A1 tile (SWIZZLE_128B).  All global
     // latency is taken by the bulk-copy engine; this loop is shared-memory to shared-memory.  A thread owns the
@@ -247,9 +247,12 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
       if (pt == 0) trace_ev(a.trace, i, 1);
       mbar_arrive(&a1_full[b1]);
     }
-  } else if (kSplitLoader && warp == W_XL) {
-    // ---------------- x loader (split mode): the tiles' fp32 rows (with halo), slab by slab
-    if (lane == 0) {
+  } else if (warp == W_XL || warp == W_WP) {
+    // ---------------- loaders: one THREAD per ring, each in its own blocking loop (a thread that polled both rings
+    // delayed weight copies behind tile-table loads and x slabs).  C = 128 has a spare warp slot for the x loader; at
+    // C = 64 (20 warps exactly) it is lane 1 of the weight loader's warp - diverged lanes make progress independently.
+    if (warp == W_XL && lane == kXlLane) {
+      // x ring: the tiles' fp32 rows (with halo), slab by slab (whole rows are contiguous in HBM -> 1-D bulk copies)
       const int R1 = 256 + 2 * H1;
       uint32_t xs = 0, xph = 0;
       ConvTile tl = n_my > 0 ? get_tile(0) : ConvTile{};
@@ -267,10 +270,8 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
           if (++xs == (uint32_t)NSLAB) { xs = 0; xph ^= 1u; }
         }
       }
-    }
-  } else if (kSplitLoader && warp == W_WP) {
-    // ---------------- weight loader (split mode): chunk order mirrors the MMA issue order
-    if (lane == 0) {
+    } else if (warp == W_WP && lane == 0) {
+      // weight ring: chunk order mirrors the MMA issue order
       const uint32_t mc_rank = a.mc ? cluster_ctarank() : 0u;
       uint32_t ws = 0, wph = 0;
       for (int s = 0; s < n_my + SKEW; ++s)
@@ -296,91 +297,6 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
         // the peer's last slot releases arrive on THIS CTA's barriers: take them before the CTA may exit
         for (int q = 0; q < W_ST; ++q) {
           mbar_wait(&w_empty[ws], wph ^ 1u);
-          if (++ws == (uint32_t)W_ST) { ws = 0; wph ^= 1u; }
-        }
-      }
-    }
-  } else if (warp == W_WP) {
-    // ---------------- loader: ONE thread feeds both rings by polling (non-blocking test_wait), so neither ring
-    // can stall the other.  Weights: chunk order mirrors the MMA issue order.  x: the tiles' fp32 rows (with
-    // halo), slab by slab (whole rows are contiguous in HBM -> 1-D bulk copies).
-    if (lane == 0) {
-      auto test = [](uint64_t* bar, uint32_t parity) {
-        uint32_t done;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-        return done != 0;
-      };
-      const int R1 = 256 + 2 * H1;
-      const uint32_t mc_rank = a.mc ? cluster_ctarank() : 0u;
-      // weight ring state: step s, pass, chunk c
-      uint32_t ws = 0, wph = 0;
-      int w_s = 0, w_pass = 0, w_c = 0;
-      auto w_skip = [&]() {            // advance (w_s, w_pass) to the next existing conv of the issue order
-        while (w_s < n_my + SKEW && (w_pass == 0 ? w_s >= n_my : w_s < SKEW)) {
-          if (++w_pass == 2) { w_pass = 0; ++w_s; }
-        }
-      };
-      w_skip();
-      // x ring state: tile xi, first row xr of the next slab
-      uint32_t xs = 0, xph = 0;
-      int xi = 0, xr = 0;
-      const float* xsrc = nullptr;
-      ConvTile tl_next = n_my > 0 ? get_tile(0) : ConvTile{};
-      const long long t0 = clock64();
-      while (w_s < n_my + SKEW || xi < n_my) {
-        bool progress = false;
-        if (w_s < n_my + SKEW && test(&w_empty[ws], wph ^ 1u)) {
-          const uint8_t* wsrc = w_pass == 0 ? p.w1 : p.w2;
-          if (a.dbg & 1) mbar_arrive(&w_full[ws]);
-          else {
-            mbar_arrive_expect_tx(&w_full[ws], W_BYTES);
-            if (a.mc) {
-              const uint32_t hoff = mc_rank * (uint32_t)(W_BYTES / 2);
-              bulk_g2s_mc(sW + ws * W_BYTES + hoff, wsrc + (size_t)w_c * W_BYTES + hoff, W_BYTES / 2, &w_full[ws], (uint16_t)3);
-            } else {
-              bulk_g2s(sW + ws * W_BYTES, wsrc + (size_t)w_c * W_BYTES, W_BYTES, &w_full[ws]);
-            }
-          }
-          if (++ws == (uint32_t)W_ST) { ws = 0; wph ^= 1u; }
-          if (++w_c == nchunks) {
-            w_c = 0;
-            if (++w_pass == 2) { w_pass = 0; ++w_s; }
-            w_skip();
-          }
-          progress = true;
-        }
-        if (xi < n_my && test(&x_empty[xs], xph ^ 1u)) {
-          if (xr == 0) {
-            // the entry was requested one tile ahead: the loader never stalls on the table while weights are due
-            xsrc = p.x_in + (tl_next.in_row0 + tl_next.q0 - H1 - H2) * (long long)C;
-            if (xi + 1 < n_my) tl_next = get_tile(xi + 1);
-          }
-          const int rows = R1 - xr < SLAB_ROWS ? R1 - xr : SLAB_ROWS;
-          if (a.dbg & 2) mbar_arrive(&x_full[xs]);
-          else {
-            mbar_arrive_expect_tx(&x_full[xs], (uint32_t)(rows * C * 4));
-            bulk_g2s(sX + xs * kSlabBytes, xsrc + (long long)xr * C, (uint32_t)(rows * C * 4), &x_full[xs]);
-          }
-          if (++xs == (uint32_t)NSLAB) { xs = 0; xph ^= 1u; }
-          xr += SLAB_ROWS;
-          if (xr >= R1) { xr = 0; ++xi; }
-          progress = true;
-        }
-        if (!progress) {
-          __nanosleep(32);
-          if (clock64() - t0 > 8000000000LL) __trap();     // a protocol bug must fault the launch, not hang
-        }
-      }
-      if (a.mc) {
-        // the peer's last slot releases arrive on THIS CTA's barriers: take them before the CTA may exit
-        for (int q = 0; q < W_ST; ++q) {
-          mbar_wait_relaxed(&w_empty[ws], wph ^ 1u);
           if (++ws == (uint32_t)W_ST) { ws = 0; wph ^= 1u; }
         }
       }
