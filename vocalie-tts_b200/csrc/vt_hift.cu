@@ -549,12 +549,12 @@ int vt_hift_create(const vt_tensor* tensors, int n_tensors, int operand_dtype, v
       // Tap-paired kernel per kernel size.  Measured per launch (ncu, us; plain pairs, tap-paired / activation-major):
       // k = 11: 860-890 / 1010, k = 7: 760-785 / 770-777, k = 3: 717-721 / 593-594 - the paired MMAs halve the
       // tensor-pipe time, but with it gone the tile period is bound by the CUDA-core work (two Snakes and two epilogues
-      // per step), so only the MMA-bound k = 11 pairs gain.  VT_PAIR64=0: never, VT_PAIR64=all: every kernel size and
+      // per step), so only the MMA-bound k = 11 pairs gain.  VT_PAIR64=0: never, VT_PAIR64=7: k = 7 and 11, VT_PAIR64=all: every kernel size and
       // also the last pair of each ResBlock.
       const char* e64 = getenv("VT_PAIR64");
       h->pair64_last = e64 && e64[0] == 'a';
       for (int kk = 0; kk < 3; ++kk) {
-        bool p64 = e64 ? (e64[0] == 'a') : kRbKernels[kk] == 11;
+        bool p64 = e64 ? (e64[0] == 'a' || (e64[0] == '7' && kRbKernels[kk] >= 7)) : kRbKernels[kk] == 11;
         for (int j = 0; j < 3; ++j) {
           p64 = p64 && pair64_tc_supported(h->rb_c1[i * 3 + kk][j], h->rb_c2[i * 3 + kk][j]);
           if (kSrcRbKernels[i] == kRbKernels[kk]) p64 = p64 && pair64_tc_supported(h->src_c1[i][j], h->src_c2[i][j]);
