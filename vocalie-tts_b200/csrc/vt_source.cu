@@ -92,12 +92,15 @@ __device__ __forceinline__ float sin_2pi_range(float t) {
   return __sinf(t);
 }
 
-// One thread per output sample: 9 harmonics, noise mix, Linear(9->1), tanh.
+// One thread per FOUR consecutive output samples (480 samples per frame: the four share the frame, hence f0, the
+// voicing decision and the per-harmonic phase prefix / increment): 9 harmonics, noise mix, Linear(9->1), tanh.
+// Performance-mode noise: one Philox call per (sample quad, harmonic) yields the quad's four normal deviates.
 __global__ void __launch_bounds__(256)
 k_sine_source(const float* __restrict__ f0, const int* __restrict__ mel_off, const int* __restrict__ T, int B,
               long long total_T, const float* __restrict__ phase_vec, const float* __restrict__ noise,
               unsigned long long seed, const float* __restrict__ lin_w, const float* __restrict__ lin_b,
               const double* __restrict__ base, float* __restrict__ s) {
+  static_assert(kSPF % 4 == 0, "a sample quad must not straddle a frame");
   const int b = blockIdx.y;
   const long long o = mel_off[b];
   const long long L = (long long)T[b] * kSPF;
@@ -108,15 +111,16 @@ k_sine_source(const float* __restrict__ f0, const int* __restrict__ mel_off, con
     lw[h] = lin_w[h];
     pv[h] = phase_vec ? phase_vec[b * kHarm + h] : 0.0f;
   }
+  const uint2 key = make_uint2((unsigned)seed, (unsigned)(seed >> 32));
   if (!phase_vec) {
     // U(-pi, pi) per (sequence, harmonic), harmonic 0 -> 0 (upstream SineGen)
-    const uint4 r0 = philox4x32(make_uint4((unsigned)b, 0u, 0u, 0x51u), make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
-    const uint4 r1 = philox4x32(make_uint4((unsigned)b, 1u, 0u, 0x51u), make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+    const uint4 r0 = philox4x32(make_uint4((unsigned)b, 0u, 0u, 0x51u), key);
+    const uint4 r1 = philox4x32(make_uint4((unsigned)b, 1u, 0u, 0x51u), key);
     const unsigned rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
     for (int h = 1; h < kHarm; ++h) pv[h] = ((float)rr[h - 1] * 2.3283064365386963e-10f * 2.0f - 1.0f) * 3.14159265358979f;
   }
-  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < L; n += (long long)gridDim.x * blockDim.x) {
+  for (long long n = 4 * ((long long)blockIdx.x * blockDim.x + threadIdx.x); n < L; n += 4 * (long long)gridDim.x * blockDim.x) {
     const int t = (int)(n / kSPF), j = (int)(n - (long long)t * kSPF);
     const float f = f0[o + t];
     const bool voiced = f > 10.0f;
@@ -124,36 +128,33 @@ k_sine_source(const float* __restrict__ f0, const int* __restrict__ mel_off, con
     // upstream: noise_amp = uv * noise_std + (1 - uv) * sine_amp / 3
     // (uv in {0, 1}: both values are exact compile-time constants of the same fp32 expression)
     const float namp = voiced ? 0.003f : 0.1f / 3.0f;
-    float z[kHarm];
-    if (noise) {
-#pragma unroll
-      for (int h = 0; h < kHarm; ++h) z[h] = noise[(o * kSPF) * kHarm + (long long)h * L + n];
-    } else {
-      const uint2 key = make_uint2((unsigned)seed, (unsigned)(seed >> 32));
-      const unsigned long long gi = (unsigned long long)(o * kSPF + n);
-#pragma unroll
-      for (int g = 0; g < 3; ++g) {
-        const uint4 r = philox4x32(make_uint4((unsigned)gi, (unsigned)(gi >> 32), (unsigned)g, 0xA5u), key);
-        const float2 n0 = box_muller(r.x, r.y), n1 = box_muller(r.z, r.w);
-        if (4 * g + 0 < kHarm) z[4 * g + 0] = n0.x;
-        if (4 * g + 1 < kHarm) z[4 * g + 1] = n0.y;
-        if (4 * g + 2 < kHarm) z[4 * g + 2] = n1.x;
-        if (4 * g + 3 < kHarm) z[4 * g + 3] = n1.y;
-      }
-    }
-    float acc = lb;
+    const unsigned long long gi = (unsigned long long)(o * kSPF + n) >> 2;      // global index of the quad
+    float acc[4] = {lb, lb, lb, lb};
 #pragma unroll
     for (int h = 0; h < kHarm; ++h) {
+      float z[4];
+      if (noise) {
+        const float4 zz = *reinterpret_cast<const float4*>(noise + (o * kSPF) * kHarm + (long long)h * L + n);
+        z[0] = zz.x; z[1] = zz.y; z[2] = zz.z; z[3] = zz.w;
+      } else {
+        const uint4 r = philox4x32(make_uint4((unsigned)gi, (unsigned)(gi >> 32), (unsigned)h, 0xA5u), key);
+        const float2 n0 = box_muller(r.x, r.y), n1 = box_muller(r.z, r.w);
+        z[0] = n0.x; z[1] = n0.y; z[2] = n1.x; z[3] = n1.y;
+      }
       const long long bi = (long long)h * total_T + o + t;
-      const double c64 = base[bi] + (double)(j + 1) * base[bi + (long long)kHarm * total_T];
-      const float c = __double2float_rn(c64);
-      const float frac = c - truncf(c);                       // torch `% 1` on a non-negative value
-      const float theta = __fmul_rn(frac, 6.283185307179586f);  // 2*pi as an fp32 scalar
-      const float sine = __fmul_rn(0.1f, sin_2pi_range(theta + pv[h]));
-      const float v = __fadd_rn(__fmul_rn(sine, uv), __fmul_rn(namp, z[h]));
-      acc = fmaf(v, lw[h], acc);
+      const double b64 = base[bi], i64 = base[bi + (long long)kHarm * total_T];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const double c64 = b64 + (double)(j + q + 1) * i64;
+        const float c = __double2float_rn(c64);
+        const float frac = c - truncf(c);                       // torch `% 1` on a non-negative value
+        const float theta = __fmul_rn(frac, 6.283185307179586f);  // 2*pi as an fp32 scalar
+        const float sine = __fmul_rn(0.1f, sin_2pi_range(theta + pv[h]));
+        const float v = __fadd_rn(__fmul_rn(sine, uv), __fmul_rn(namp, z[q]));
+        acc[q] = fmaf(v, lw[h], acc[q]);
+      }
     }
-    s[o * kSPF + n] = tanhf(acc);
+    *reinterpret_cast<float4*>(s + o * kSPF + n) = make_float4(tanhf(acc[0]), tanhf(acc[1]), tanhf(acc[2]), tanhf(acc[3]));
   }
 }
 
@@ -163,7 +164,7 @@ int launch_sine_source(const float* f0, const int* mel_off, const int* T, int B,
   if (B == 0 || total_T == 0) return VT_OK;
   k_phase_base<<<(B * kHarm + 63) / 64, 64, 0, st>>>(f0, mel_off, T, B, total_T, phase_base);
   VT_LAUNCHED();
-  // grid.x sized for the longest sequence (grid-stride inside): aim at ~148*8 blocks in total
+  // grid.x sized for the longest sequence (grid-stride inside, four samples per thread): aim at ~148*8 blocks in total
   int gx = (148 * 8 + B - 1) / B;
   if (gx < 1) gx = 1;
   dim3 grid(gx, B);
