@@ -249,6 +249,8 @@ int launch_em(const ConvArgs& a, const void* wtc, uint32_t idesc, int grid, cuda
   if (!configured) {
     VT_CUDA_OK(cudaFuncSetAttribute(k_conv_tc<CIN, NT, MB, A_ST, W_ST, NEPI, HALO, EM, ActT>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    VT_CUDA_OK(cudaFuncSetAttribute(k_conv_tc<CIN, NT, MB, A_ST, W_ST, NEPI, HALO, EM, ActT>,
+                                    cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     configured = true;
   }
   k_conv_tc<CIN, NT, MB, A_ST, W_ST, NEPI, HALO, EM, ActT><<<grid, (NEPI + 2 + kProdWarps) * 32, smem, st>>>(
@@ -402,6 +404,8 @@ static int launch_conv_tc_t(const ConvArgs& a, const ConvLayer& L, int inst, uin
     case 5: return tc::launch_plain<256, 128, 1, 2, 4, 4, 2, ActT>(a, L.w_tc, idesc, grid, st);
     case 6: return tc::launch_plain<128, 64, 1, 2, 4, 8, 2, ActT>(a, L.w_tc, idesc, grid, st);
     case 7: return tc::launch_plain<64, 32, 2, 2, 4, 8, 6, ActT>(a, L.w_tc, idesc, grid, st);
+    case 16: return tc::launch_plain<128, 64, 1, 2, 3, 4, 2, ActT>(a, L.w_tc, idesc, grid, st);  // 110 KB: two CTAs per SM
+    case 17: return tc::launch_plain<64, 32, 2, 2, 4, 4, 6, ActT>(a, L.w_tc, idesc, grid, st);   // 102 KB: two CTAs per SM
     case 8: return tc::launch_plain<128, 128, 1, 2, 4, 4, 6, ActT>(a, L.w_tc, idesc, grid, st);
   }
   VT_REQUIRE(false, "conv_tc: layer %s has no tensor-core instance", L.name.c_str());
@@ -439,13 +443,21 @@ int launch_conv_tc(const ConvArgs& a_in, const ConvLayer& L, int act_elem, const
     a.trace = d_trace;
   }
   const long long total = (long long)n_tc_tiles * (L.cout / NT);
-  const int grid = total < sm_count ? (int)total : sm_count;
+  // conv_post (64 -> 18 channels, instance 7) and the last transposed conv (128 -> 3 x 64, instance 6) are
+  // latency-bound pipelines at ~30 % issue and 30-35 % DRAM utilisation with one CTA per SM.  With 4 instead of 8
+  // epilogue warps (and a 3-deep weight ring for instance 6) a CTA needs 102 / 110 KB of shared memory and 128 TMEM
+  // columns, so two CTAs share an SM and hide each other's stalls: conv_post 0.32 -> 0.21 ms.
+  // VT_CONV_2CTA=0: one CTA per SM.
+  static const bool two_cta = !(getenv("VT_CONV_2CTA") && getenv("VT_CONV_2CTA")[0] == '0');
+  const int launch_inst = ((inst == 7 || inst == 6) && two_cta) ? inst + 10 : inst;
+  const int slots = launch_inst >= 16 ? 2 * sm_count : sm_count;
+  const int grid = total < slots ? (int)total : slots;
   const uint32_t fmt = act_elem == ELEM_F16 ? 0u : 1u;
   // instruction descriptor: D = f32 (bits 4-5 = 1), A/B format (bits 7-9, 10-12), K-major A and B,
   // N>>3 at bits 17-22, M>>4 at bits 24-28
   const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
-  const int rc = act_elem == ELEM_F16 ? launch_conv_tc_t<__half>(a, L, inst, idesc, grid, st)
-                                      : launch_conv_tc_t<__nv_bfloat16>(a, L, inst, idesc, grid, st);
+  const int rc = act_elem == ELEM_F16 ? launch_conv_tc_t<__half>(a, L, launch_inst, idesc, grid, st)
+                                      : launch_conv_tc_t<__nv_bfloat16>(a, L, launch_inst, idesc, grid, st);
   if (tracing && rc == VT_OK) {
     std::vector<long long> h(tc::kTraceTiles * tc::kTraceEvents);
     VT_CUDA_OK(cudaStreamSynchronize(st));
