@@ -280,7 +280,7 @@ def test_bf16_operand_mode_runs_at_its_documented_accuracy(torch, weights):
 
 
 @pytest.mark.parametrize("env", [
-    {"VT_CONVT": "0", "VT_PAIR_TR": "0", "VT_PAIR64": "0"},
+    {"VT_CONVT": "0", "VT_PAIR_TR": "0", "VT_PAIR64": "0", "VT_CONV_2CTA": "0"},
     {"VT_PAIR64": "all"},
     {"VT_PAIR64": "all", "VT_P64_NA1": "1"},
     {"VT_PAIR_MC": "1"},
