@@ -35,7 +35,7 @@ extern "C" {
 #define VT_ERR_UNSUPPORTED -3   /* not an sm_100 device / unsupported shape */
 #define VT_ERR_NOMEM       -4
 
-#define VT_ABI_VERSION 2
+#define VT_ABI_VERSION 3
 
 /* ---- library ------------------------------------------------------------------------- */
 int         vt_abi_version(void);
@@ -60,6 +60,15 @@ int64_t vt_post_workspace_bytes(int n_seg, int64_t n_samples);
 int vt_find_active_range(const float* audio, const int64_t* seg_off, int n_seg, int64_t n_samples,
                          int64_t max_seg_len, float threshold, int min_silence_frames,
                          int64_t* ranges, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Raw statistics of every segment in one read pass: first_last[2*i], first_last[2*i+1] = first and last sample
+ * with |x| > threshold (segment-relative; -1, -1 when there is none), peak[i] = max|x| over the segment.  This is
+ * what the ranks of a sharded job exchange (min / max / max all-reduce of three scalars) to reproduce the whole-file
+ * trim and the single peak of apply_minimal_edit (backend/services/tts_service.py:195-207, audio_edit.py:44-66):
+ * the min-silence rule of _find_active_range is then applied once, on the global range. */
+int vt_post_stats(const float* audio, const int64_t* seg_off, int n_seg, int64_t n_samples,
+                  int64_t max_seg_len, float threshold, int64_t* first_last, float* peak,
+                  void* workspace, int64_t workspace_bytes, void* stream);
 
 /* _snap_zero_crossing (tts_pipeline.py:114-137), batched: idx_out[i] = snapped idx_in[i]
  * inside segment i (radius inclusive, ties -> lower index, none -> clamped idx). */

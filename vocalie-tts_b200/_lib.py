@@ -21,6 +21,7 @@ VT_OPERAND_FP16 = 0
 VT_OPERAND_BF16 = 1
 VT_OPERAND_FP32 = 2
 POST_RESULT_STRIDE = 8
+ABI_VERSION = 3
 
 
 class PostParams(C.Structure):
@@ -49,6 +50,7 @@ _SIGS = {
     "vt_device_check": (C.c_int, [C.POINTER(C.c_int)] * 3),
     "vt_post_workspace_bytes": (_I64, [C.c_int, _I64]),
     "vt_find_active_range": (C.c_int, [_P, _P, C.c_int, _I64, _I64, C.c_float, C.c_int, _P, _P, _I64, _P]),
+    "vt_post_stats": (C.c_int, [_P, _P, C.c_int, _I64, _I64, C.c_float, _P, _P, _P, _I64, _P]),
     "vt_snap_zero_crossing": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P, _P]),
     "vt_post_analyze": (C.c_int, [_P, _P, C.c_int, _I64, _I64, C.POINTER(PostParams), _P, _P, _I64, _P]),
     "vt_post_write": (C.c_int, [_P, _P, C.c_int, _I64, _I64, C.POINTER(PostParams), _P, _P, _I64, _P, _P, _P, _I64, _P]),
@@ -90,7 +92,7 @@ def load_library():
                 raise BackendUnavailableError(f"{LIB_PATH} does not export {name}") from exc
             fn.restype = res
             fn.argtypes = args
-        if lib.vt_abi_version() != 2:
+        if lib.vt_abi_version() != ABI_VERSION:
             raise BackendUnavailableError("ABI version mismatch between Python shim and libvocalie_b200.so")
         _lib = lib
         return lib

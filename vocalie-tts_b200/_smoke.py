@@ -1,5 +1,5 @@
 """One small invocation of the hot path on cuda:0 checked against the oracle
-(``__graft_entry__.smoke()``): mel -> HiFT -> trim / normalise / gap stitch."""
+(``__graft_entry__.smoke()``): mel -> HiFT -> gap stitch -> whole-file trim / normalise (reference order)."""
 from __future__ import annotations
 
 import sys
@@ -39,7 +39,8 @@ def run() -> None:
         snr = H.snr_db(ref, got)
         assert err <= 1e-3 and snr >= 60.0, f"HiFT parity failed: max-abs {err:.3g}, SNR {snr:.1f} dB"
         refs.append(got.numpy())
-    # post: per-chunk trim + normalise + gap stitch of the GPU waveforms vs the numpy oracle (bit-exact)
+    # post in the reference's order: gap stitch of the raw chunks -> PCM_16 raw file -> one whole-file
+    # apply_minimal_edit (trim, ONE peak, clip), GPU waveforms vs the numpy oracle (bit-exact)
     pipe = VocoderPipeline(voc)
     mel, T = voc.pack_mels(mels)
     f0p = torch.cat(f0s).cuda()
@@ -47,20 +48,10 @@ def run() -> None:
     nz = torch.cat([n.reshape(-1) for _, n in pn]).cuda()
     res = pipe.run_device(mel, T, f0=f0p, phase_vec=pv, noise=nz, read_back=True)
     out = res.audio[: res.total_samples].cpu().numpy()
-    chunks = []
-    for i, x in enumerate(refs):
-        s, e = po.trim_range_snapped(x, 24000)
-        y = x[s:e].copy()
-        if i < len(refs) - 1:
-            po.fade_out(y, 240)
-        if i > 0:
-            po.fade_in(y, 240)
-        peak = float(np.max(np.abs(y))) if y.size else 0.0
-        if peak > 0:
-            y = y * (float(10 ** (-1.0 / 20.0)) / peak)
-        chunks.append(y.astype(np.float32))
-        assert (int(res.segments[i, 0]), int(res.segments[i, 1])) == (s, e), "trim indices differ from the oracle"
-    want = np.concatenate([chunks[0], np.zeros(6000, np.float32), chunks[1]])
+    raw = po.pcm16_encode(po.apply_inter_chunk_gap(refs, sr=24000, gap_ms=250))
+    assert np.array_equal(res.raw[: res.raw_samples].cpu().numpy(), raw), "stitched raw file is not bit-exact"
+    want, meta = po.apply_minimal_edit_array(po.pcm16_decode(raw), 24000, trim_enabled=True, normalize_enabled=True, target_dbfs=-1.0)
     assert out.size == want.size, (out.size, want.size)
-    assert np.array_equal(out.view(np.uint32), want.view(np.uint32)), "post-processing is not bit-exact"
+    assert np.array_equal(out.view(np.uint32), want.astype(np.float32).view(np.uint32)), "post-processing is not bit-exact"
+    assert res.edit["peak_before"] == meta["peak_before"] and res.edit["gain"] == meta["gain"]
     print(f"smoke ok: {sum(Ts) * 480} samples, {pipe.last_launches} kernel launches, operand=fp16")

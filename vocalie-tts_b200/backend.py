@@ -18,6 +18,8 @@ optionally ``f0``).  ``get_backend`` instantiates a new object per call
 """
 from __future__ import annotations
 
+import itertools
+import os
 import threading
 from pathlib import Path
 from typing import Any, Callable, Dict, List, Optional, Sequence
@@ -102,6 +104,16 @@ class ChatterboxB200Backend(TTSBackend):
     _vocoder = None
     _mel_provider: Optional[Callable[..., Any]] = None
     _why_unavailable: Optional[str] = "not configured: call ChatterboxB200Backend.configure(...)"
+
+    # Upstream draws fresh SineGen randomness (phase_vec, noise) from torch's global RNG on every call; the in-kernel
+    # Philox stream is keyed on (seed, sequence, sample), so a caller that passes no seed gets a new one per call
+    # (process-random base + counter) instead of the same phases and noise for every chunk of every job.
+    _seed_base = int.from_bytes(os.urandom(7), "little")
+    _seed_counter = itertools.count()
+
+    @classmethod
+    def _next_seed(cls) -> int:
+        return (cls._seed_base + 0x9E3779B97F4A7C15 * next(cls._seed_counter)) & (2 ** 63 - 1)
 
     # ------------------------------------------------------------------ configuration
     @classmethod
@@ -222,7 +234,8 @@ class ChatterboxB200Backend(TTSBackend):
             f0 = [torch.as_tensor(f) for f in f0s]
         try:
             with self._lock:
-                wavs = voc.inference(mels, f0=f0, seed=int(params.get("seed", 0)))
+                seed = int(params["seed"]) if params.get("seed") is not None else self._next_seed()
+                wavs = voc.inference(mels, f0=f0, seed=seed)
                 out = [w.cpu().numpy() for w in wavs]
         except BackendUnavailableError:
             raise

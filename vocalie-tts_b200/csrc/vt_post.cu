@@ -300,6 +300,28 @@ __global__ void k_range_out(const SegPlan* plan, const int64_t* seg_off, int n_s
   ranges[2 * i + 1] = e;
 }
 
+// Raw per-segment statistics for callers that merge ranges across ranks: first / last index with |x| > thr
+// (-1 / -1 when the segment has none) and max|x| over the whole segment, from k_scan's plan and tile maxima.
+__global__ void __launch_bounds__(kThreads)
+k_seg_stats(const SegPlan* __restrict__ plan, const int64_t* __restrict__ seg_off, const float* __restrict__ tile_max,
+            int64_t* __restrict__ first_last, float* __restrict__ peak) {
+  __shared__ float sh_f[kThreads / 32];
+  const int seg = blockIdx.x;
+  const long long a = seg_off[seg], b = seg_off[seg + 1];
+  const long long A = a & ~3LL;
+  const long long n_tiles = b > a ? (b - A + kScanTile - 1) / kScanTile : 0;
+  const long long tbase = plan[seg].tile_base;
+  float m = 0.0f;
+  for (long long t = threadIdx.x; t < n_tiles; t += kThreads) m = fmaxf(m, tile_max[tbase + t]);
+  m = block_max(m, sh_f);
+  if (threadIdx.x == 0) {
+    const bool any = plan[seg].last >= 0;
+    first_last[2 * seg] = any ? plan[seg].first : -1;
+    first_last[2 * seg + 1] = any ? plan[seg].last : -1;
+    peak[seg] = m;
+  }
+}
+
 // ------------------------------------------------------------------------------------ fix
 // Per segment: min-silence rule, snap, fallback, fade lengths (one block per segment).
 __global__ void __launch_bounds__(kThreads)
@@ -761,6 +783,29 @@ int vt_find_active_range(const float* audio, const int64_t* seg_off, int n_seg, 
   k_scan<<<g, kThreads, 0, st>>>(audio, seg_off, n_seg, threshold, 1, w.plan, w.tile_max);
   VT_LAUNCHED();
   k_range_out<<<(n_seg + 255) / 256, 256, 0, st>>>(w.plan, seg_off, n_seg, min_silence_frames, ranges);
+  VT_LAUNCHED();
+  return VT_OK;
+}
+
+int vt_post_stats(const float* audio, const int64_t* seg_off, int n_seg, int64_t n_samples, int64_t max_seg_len,
+                  float threshold, int64_t* first_last, float* peak, void* workspace, int64_t workspace_bytes,
+                  void* stream_v) {
+  int rc = check_audio(audio, seg_off, n_seg);
+  if (rc) return rc;
+  VT_REQUIRE((first_last != nullptr && peak != nullptr) || n_seg == 0, "vt_post_stats: NULL output");
+  VT_REQUIRE(workspace_bytes >= post_ws_bytes(n_seg, n_samples), "post workspace too small");
+  if (n_seg == 0) return VT_OK;
+  launch_counter() = 0;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
+  PostWs w = carve(workspace, n_seg, n_samples);
+  k_post_init<<<(n_seg + 255) / 256, 256, 0, st>>>(w.plan, w.hdr, seg_off, n_seg, nullptr);
+  VT_LAUNCHED();
+  k_tile_bases<<<1, 256, 0, st>>>(w.plan, seg_off, n_seg);
+  VT_LAUNCHED();
+  dim3 g(grid_x_for(n_seg, max_seg_len, kScanTile * (kThreads / 32)), n_seg);
+  k_scan<<<g, kThreads, 0, st>>>(audio, seg_off, n_seg, threshold, 1, w.plan, w.tile_max);
+  VT_LAUNCHED();
+  k_seg_stats<<<n_seg, kThreads, 0, st>>>(w.plan, seg_off, w.tile_max, first_last, peak);
   VT_LAUNCHED();
   return VT_OK;
 }

@@ -1,16 +1,22 @@
 """Chunk-level data parallelism for one job on N GPUs of a node.
 
-The chunks of a job are independent through HiFT and through per-chunk post-processing, so they are
-sharded across ranks with no data-path collective.  The one exchange step is output assembly:
-every rank holds ``[chunk][gap][chunk][gap]...`` for its chunks; rank 0 needs them interleaved in
-job order.  Trimmed lengths are data dependent, so the ranks first all-gather their per-chunk
-output lengths (a few hundred int64), compute the global offsets (exclusive scan of
-``len_i + gap``), then the stitched shards are gathered to rank 0 (NCCL over NVLink on GPUs, gloo
-in the CPU tests) and copied run by run into place.
+The chunks of a job are independent through HiFT and through the stitch pass, so they are sharded across
+ranks with no data-path collective.  What is exchanged:
+
+  * reference order (``granularity="job"``): the whole-file edit needs the file's trim range and its ONE
+    peak (apply_minimal_edit on the stitched file, backend/services/tts_service.py:195-207,
+    backend/shared/audio_edit.py:44-66).  Every rank reduces its own part of the raw file to three
+    scalars (first active sample, last active sample, max|x|) and one ``all_reduce(MAX)`` of an int64[3]
+    merges them; the min-silence rule of ``_find_active_range`` is applied once to the global range.
+  * output assembly: every rank's pieces go STRAIGHT into their final position ``out[dst:dst+n]`` on rank 0
+    with grouped send / recv (``ncclSend`` / ``ncclRecv`` over NVLink on GPUs, gloo in the CPU tests) - no
+    staging buffer, no second copy.  Piece geometry is known on every rank: raw chunk lengths are ``480 T``
+    (static), and data-dependent lengths (per-chunk trim) are all-gathered first (a few hundred int64).
 """
 from __future__ import annotations
 
-from typing import List, Optional, Sequence
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -57,61 +63,261 @@ def _runs(chunk_ids: Sequence[int]):
     return runs
 
 
+Piece = Tuple[int, int, int]   # (src offset in the rank's local buffer, samples, dst offset in the final file)
+
+
+def stitched_pieces(all_lens: np.ndarray, gap: int, shards: Sequence[Sequence[int]]) -> List[List[Piece]]:
+    """Pieces of a stitched job: rank r holds ``[chunk][gap][chunk][gap]...`` for its chunks (every chunk but the
+    job's last followed by its gap); a run of globally consecutive chunks is contiguous on both sides."""
+    lens = np.asarray(all_lens, dtype=np.int64)
+    n_total = lens.size
+    offs = global_offsets(lens, gap)
+    out: List[List[Piece]] = []
+    for ids in shards:
+        pieces: List[Piece] = []
+        if ids:
+            l = lens[np.asarray(ids)]
+            local_off = np.concatenate([[0], np.cumsum(l + gap)[:-1]])
+            for first, count in _runs(ids):
+                last = first + count - 1
+                src0 = int(local_off[first])
+                n = int(local_off[last] + l[last] - src0)
+                if ids[last] != n_total - 1:          # the gap after the run belongs to the file
+                    n += int(gap)
+                pieces.append((src0, n, int(offs[ids[first]])))
+        out.append(pieces)
+    return out
+
+
+def assemble_pieces(local, pieces_by_rank: Sequence[Sequence[Piece]], total: int, *, dst: int = 0, group=None, out=None):
+    """Move every rank's pieces straight into ``out[dst_off:dst_off+n]`` on rank ``dst``: one grouped batch of
+    send / recv operations whose receive buffers ARE the destination slices.  Returns ``out[:total]`` on ``dst``,
+    None elsewhere."""
+    import torch
+    import torch.distributed as dist
+    rank = dist.get_rank(group)
+    ops = []
+    if rank == dst:
+        if out is None:
+            out = torch.empty(max(total, 1), dtype=local.dtype, device=local.device)
+        for r, pieces in enumerate(pieces_by_rank):
+            for src0, n, d0 in pieces:
+                if n <= 0:
+                    continue
+                if r == rank:
+                    out[d0:d0 + n].copy_(local[src0:src0 + n])
+                else:
+                    ops.append(dist.P2POp(dist.irecv, out[d0:d0 + n], dist.get_global_rank(group, r) if group is not None else r, group))
+    else:
+        for src0, n, d0 in pieces_by_rank[rank]:
+            if n > 0:
+                ops.append(dist.P2POp(dist.isend, local[src0:src0 + n], dist.get_global_rank(group, dst) if group is not None else dst, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return out[:total] if rank == dst else None
+
+
 def assemble_on_rank0(local_audio, local_lens: Sequence[int], chunk_ids: Sequence[int], n_total: int, gap: int,
                       shards: Sequence[Sequence[int]], *, group=None, out=None):
-    """Gather the stitched shards to rank 0 and interleave them in job order.
+    """Assembly for data-dependent chunk lengths (``granularity="chunk"``: every chunk was trimmed on its own).
 
     ``local_audio``: this rank's stitched shard (1-D tensor, CPU or CUDA), chunk j at
     ``sum_{j'<j}(len_j' + gap)``; ``local_lens``: its per-chunk output lengths; ``shards``: the chunk
-    ids of every rank (same on all ranks).  Returns (final audio tensor on rank 0 | None, total samples).
+    ids of every rank (same on all ranks).  The lengths are all-gathered, then the pieces are sent straight into
+    place.  Returns (final audio tensor on rank 0 | None, total samples).
     """
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
     dev = local_audio.device
     max_n = max(len(s) for s in shards)
     lens_pad = torch.zeros(max_n, dtype=torch.int64, device=dev)
     if len(local_lens):
         lens_pad[: len(local_lens)] = torch.as_tensor(np.asarray(local_lens, dtype=np.int64), device=dev)
-    all_pad = [torch.zeros_like(lens_pad) for _ in range(world)]
-    dist.all_gather(all_pad, lens_pad, group=group)
+    all_pad = torch.zeros(world * max_n, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_pad, lens_pad, group=group) if dev.type == "cuda" else \
+        dist.all_gather(list(all_pad.view(world, max_n).unbind(0)), lens_pad, group=group)
+    all_host = all_pad.view(world, max_n).cpu().numpy()
     all_lens = np.zeros(n_total, dtype=np.int64)
     for r, ids in enumerate(shards):
         if ids:
-            all_lens[np.asarray(ids)] = all_pad[r][: len(ids)].cpu().numpy()
+            all_lens[np.asarray(ids)] = all_host[r, : len(ids)]
     total = final_length(all_lens, gap)
-    # fixed-size gather (shards are padded to the largest one; the pad is never copied)
-    cap = 0
-    for ids in shards:
-        cap = max(cap, int(all_lens[np.asarray(ids, dtype=np.int64)].sum() + len(ids) * gap) if ids else 0)
-    cap = max(cap, 1)
-    send = local_audio
-    if send.numel() < cap:
-        send = torch.zeros(cap, dtype=local_audio.dtype, device=dev)
-        send[: local_audio.numel()] = local_audio
-    else:
-        send = send[:cap].contiguous()
-    bufs = [torch.empty(cap, dtype=local_audio.dtype, device=dev) for _ in range(world)] if rank == 0 else None
-    dist.gather(send, bufs, dst=0, group=group)
-    if rank != 0:
-        return None, total
-    offs = global_offsets(all_lens, gap)
-    if out is None:
-        out = torch.empty(max(total, 1), dtype=local_audio.dtype, device=dev)
-    for r, ids in enumerate(shards):
-        if not ids:
-            continue
-        l = all_lens[np.asarray(ids)]
-        local_off = np.concatenate([[0], np.cumsum(l + gap)[:-1]])
-        for first, count in _runs(ids):
-            last = first + count - 1
-            src0 = int(local_off[first])
-            n = int(local_off[last] + l[last] - src0)
-            # the gap after the run's last chunk belongs to the file unless it is the job's last chunk
-            if ids[last] != n_total - 1:
-                n += gap
-            dst0 = int(offs[ids[first]])
-            n = min(n, total - dst0)
-            out[dst0:dst0 + n].copy_(bufs[r][src0:src0 + n])
-    return out[:total], total
+    pieces = stitched_pieces(all_lens, gap, shards)
+    # the trailing gap of the file's last piece may have been cut by the producer
+    pieces = [[(s, min(n, total - d), d) for s, n, d in p] for p in pieces]
+    out = assemble_pieces(local_audio, pieces, total, group=group, out=out)
+    return out, total
+
+
+# ------------------------------------------------------------------------------------ reference order, sharded
+def merge_file_range(first_g: int, last_g: int, n_file: int, *, trim: bool, min_silence_frames: int) -> Tuple[int, int]:
+    """``_find_active_range`` on the whole file from the merged extremes (tts_pipeline.py:192-209) followed by
+    apply_minimal_edit's guard (audio_edit.py:53: ``0 <= start < end <= len`` or leave the file alone)."""
+    if not trim or n_file == 0 or last_g < 0:
+        return 0, n_file
+    start, end = int(first_g), int(last_g) + 1
+    if start < min_silence_frames:
+        start = 0
+    if n_file - end < min_silence_frames:
+        end = n_file
+    if not (0 <= start < end <= n_file):
+        return 0, n_file
+    return start, end
+
+
+@dataclass
+class ShardedJobResult:
+    audio: "object"            # final file on rank 0 (device tensor, int16 or float32), None elsewhere
+    total_samples: int
+    raw_samples: int
+    edit: Optional[dict]
+
+
+class ShardedJob:
+    """One job in reference order over the ranks of a process group: every rank vocodes and stitches its chunks,
+    one int64[3] all-reduce gives the file's trim range and peak, every rank edits its own part of the file and the
+    parts are sent straight into place on rank 0."""
+
+    def __init__(self, pipe, T_all: Sequence[int], shards: Sequence[Sequence[int]], *, group=None):
+        import torch.distributed as dist
+        from .hift import SAMPLES_PER_FRAME
+        from . import post as _post
+        if pipe.granularity != "job":
+            raise ValueError("ShardedJob runs the reference order: build the pipeline with granularity='job'")
+        if pipe.editing and pipe.edit != "minimal_edit":
+            raise ValueError("sharded jobs support edit='minimal_edit' (the variant run_tts_job calls) only")
+        self.pipe, self.group = pipe, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.T_all = np.asarray(T_all, dtype=np.int64)
+        self.shards = [list(s) for s in shards]
+        self.n_total = int(self.T_all.size)
+        pipe.set_shard(self.shards[self.rank], self.n_total)
+        o = pipe.opts
+        gap_on = o["chunk_gap_ms"] > 0 and self.n_total > 1
+        self.gap = _post._ms_to_frames(pipe.sr, o["chunk_gap_ms"]) if gap_on else 0
+        if not gap_on:
+            pipe.stitch_head = pipe.stitch_tail = 1          # plain concatenate: no fades anywhere (tts_pipeline.py:171-172)
+            pipe.opts = dict(o, chunk_gap_ms=0)
+        self.lens = self.T_all * SAMPLES_PER_FRAME
+        self.n_raw = final_length(self.lens, self.gap)
+        self.raw_pieces = stitched_pieces(self.lens, self.gap, self.shards)
+        self.local_T = self.T_all[np.asarray(self.shards[self.rank], dtype=np.int64)].astype(np.int32)
+        mine = self.raw_pieces[self.rank]
+        self.runs_off = np.concatenate([[0], np.cumsum([n for _, n, _ in mine])]).astype(np.int64)
+        self.min_sil = int(pipe.sr * (int(o["silence_min_ms"]) / 1000.0))
+
+    def run_device(self, mel, *, f0=None, phase_vec=None, noise=None, seed: int = 0, out=None) -> ShardedJobResult:
+        """``mel``: this rank's chunks, float32 CUDA [sum(local_T), 80]."""
+        import torch
+        from .hift import SAMPLES_PER_FRAME
+        pipe = self.pipe
+        T = self.local_T
+        n = int(T.astype(np.int64).sum()) * SAMPLES_PER_FRAME
+        with torch.cuda.device(pipe.voc.device):
+            wav = pipe.voc.forward_packed(mel, T, f0=f0, phase_vec=phase_vec, noise=noise, seed=seed,
+                                          out=pipe._buf("_wav", n + 4, torch.float32))
+            seg_off = np.concatenate([[0], np.cumsum(T.astype(np.int64) * SAMPLES_PER_FRAME)])
+            res = self.post_device(wav, seg_off, out=out)
+            from . import post as _post
+            pipe.last_launches = _post.last_launch_count()
+        return res
+
+    def post_device(self, wav, seg_off, *, out=None, ops=None) -> ShardedJobResult:
+        """Stitch -> (all-reduce -> whole-file edit) -> assembly, from this rank's packed raw chunks.  ``ops`` are the
+        four device passes (default: the CUDA kernels; the gloo CPU tests inject the numpy oracle to exercise this
+        host logic without a GPU)."""
+        import torch
+        import torch.distributed as dist
+        pipe = self.pipe
+        o = pipe.opts
+        dev = wav.device
+        ops = ops or _CudaOps(pipe)
+        seg_off = np.ascontiguousarray(seg_off, dtype=np.int64)
+        n_chunks = seg_off.size - 1
+        n_local_raw = int(self.runs_off[-1])
+        if not pipe.editing:
+            local = ops.stitch(wav, seg_off, n_local_raw, final=True) if n_chunks else torch.zeros(0, device=dev)
+            final = assemble_pieces(local, self.raw_pieces, self.n_raw, group=self.group, out=out)
+            return ShardedJobResult(final, self.n_raw, self.n_raw, None)
+        stats = torch.tensor([-(1 << 62), -1, 0], dtype=torch.int64, device=dev)     # [-first, last, peak bits]
+        x = None
+        if n_chunks:
+            raw = ops.stitch(wav, seg_off, n_local_raw, final=False)        # PCM_16: stage B reads the file back
+            x = ops.decode(raw, n_local_raw)
+            fl, pk = ops.stats(x, self.runs_off, o["silence_threshold"])
+            goff = torch.as_tensor(np.asarray([d for _, _, d in self.raw_pieces[self.rank]], dtype=np.int64), device=dev)
+            active = fl[:, 1] >= 0
+            first = torch.where(active, fl[:, 0] + goff, torch.full_like(goff, 1 << 62)).min()
+            last = torch.where(active, fl[:, 1] + goff, torch.full_like(goff, -1)).max()
+            stats = torch.stack([-first, last, pk.max().view(torch.int32).to(torch.int64)])   # non-negative floats order like their bits
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX, group=self.group)
+        neg_first, last_g, peak_bits = (int(v) for v in stats.cpu().tolist())
+        peak = float(np.array([peak_bits], dtype=np.int64).astype(np.int32).view(np.float32)[0])
+        start_g, end_g = merge_file_range(-neg_first, last_g, self.n_raw, trim=o["trim_silence"], min_silence_frames=self.min_sil)
+        total = end_g - start_g
+        # every rank's pieces of the edited file: its runs clipped to [start_g, end_g)
+        pieces: List[List[Piece]] = []
+        for r in range(self.world):
+            src, pr = 0, []
+            for _, nrun, d0 in self.raw_pieces[r]:
+                s = min(max(start_g - d0, 0), nrun)
+                e = min(max(end_g - d0, s), nrun)
+                pr.append((src, e - s, d0 + s - start_g))
+                src += e - s
+            pieces.append(pr)
+        local = torch.zeros(0, device=dev)
+        if n_chunks:
+            rng = np.zeros((self.runs_off.size - 1, 2), dtype=np.int64)
+            for i, (_, nrun, d0) in enumerate(self.raw_pieces[self.rank]):
+                s = min(max(start_g - d0, 0), nrun)
+                rng[i] = (s, min(max(end_g - d0, s), nrun))
+            local = ops.edit(x, self.runs_off, rng, peak if o["normalize"] else 0.0)
+        final = assemble_pieces(local, pieces, total, group=self.group, out=out)
+        target_peak = 10 ** (o["target_dbfs"] / 20.0)
+        normalized = bool(o["normalize"] and peak > 0.0 and target_peak > 0.0)
+        edit = {"start_sample": start_g, "end_sample": end_g, "peak_before": peak,
+                "gain": (target_peak / peak) if normalized else 1.0,
+                "trimmed": bool(o["trim_silence"] and 0 <= start_g < end_g <= self.n_raw), "normalized": normalized,
+                "target_dbfs": o["target_dbfs"], "edit": pipe.edit}
+        return ShardedJobResult(final, total, self.n_raw, edit)
+
+
+class _CudaOps:
+    """The four device passes of a sharded job on the CUDA kernels (csrc/vt_post.cu)."""
+
+    def __init__(self, pipe):
+        self.pipe = pipe
+
+    def stitch(self, wav, seg_off, n_local_raw, *, final):
+        import torch
+        from . import post as _post
+        pipe = self.pipe
+        pcm = True if not final else pipe.opts["out_pcm16"]
+        prm = pipe.stitch_params(len(seg_off) - 1, out_pcm16=pcm)
+        buf = pipe._buf("_out" if final else "_raw", n_local_raw + int(prm.gap_frames), torch.int16 if pcm else torch.float32)
+        _post.post_process_device(wav, seg_off, prm, out=buf, read_back=False)
+        return buf
+
+    def decode(self, raw, n):
+        import torch
+        from . import _lib
+        x = self.pipe._buf("_rawf", n + 4, torch.float32)
+        _lib.check(_lib.load_library().vt_pcm16_decode(int(raw.data_ptr()), int(x.data_ptr()), n,
+                                                       int(torch.cuda.current_stream().cuda_stream)), "vt_pcm16_decode")
+        return x
+
+    def stats(self, x, runs_off, threshold):
+        from . import post as _post
+        return _post.stats_device(x, runs_off, threshold=threshold)
+
+    def edit(self, x, runs_off, rng, peak):
+        import torch
+        from . import post as _post
+        pipe = self.pipe
+        out = pipe._buf("_out", int(runs_off[-1]), torch.int16 if pipe.opts["out_pcm16"] else torch.float32)
+        _post.post_process_device(x, runs_off, pipe.edit_params(), out=out, read_back=False,
+                                  range_override=torch.as_tensor(rng, device=x.device),
+                                  peak_override=torch.tensor([peak], dtype=torch.float32, device=x.device))
+        return out

@@ -1,39 +1,67 @@
-"""Mel -> finished audio on the GPU: the B200 replacement of the reference's serial chunk loop
-tail (backend/shared/tts_pipeline.py:353-409 after synthesis, plus the post-processing of
-tts_pipeline.py:162-274 / audio_edit.py:16-79), batched over the independent chunks of a job.
+"""Mel -> finished audio on the GPU: the B200 replacement of the reference's serial chunk loop tail
+(backend/shared/tts_pipeline.py:353-409 after synthesis) plus the job-level edit of
+backend/services/tts_service.py:195-207, batched over the independent chunks of a job.
 
-``VocoderPipeline.run`` is the call a user of this package makes: host mel buffers in, host audio
-out.  ``run_device`` is the same with device-resident tensors (no copies) for callers that
-already hold mels on the GPU.
+Two granularities:
+
+``granularity="job"`` (default) follows the REFERENCE ORDER:
+  A. the raw chunks are stitched with ``_apply_inter_chunk_gap`` (edge fades out -> in, gap zeros;
+     tts_pipeline.py:398-405) and quantised to the PCM_16 "raw" file (``sf.write`` default subtype,
+     tts_pipeline.py:409);
+  B. if editing is on, ONE whole-file pass runs on that file as read back by ``sf.read``
+     (``q / 32768``): ``edit="minimal_edit"`` = ``apply_minimal_edit`` (trim without snap or fades, ONE
+     peak, clip; audio_edit.py:16-79, the variant ``run_tts_job`` calls) or ``edit="minimal_post_process"``
+     (trim + snap + fades + ONE peak, no clip; tts_pipeline.py:212-274).
+  Pauses inside the job survive and the loudness balance between chunks is kept, exactly like the
+  reference.  Bit-exact against the reference's own functions (tests/golden/job_golden.npz).
+
+``granularity="chunk"`` (opt-in, NOT what the reference does) trims, snaps, fades and peak-normalises
+every chunk on its own and then stitches (north_star's "per-chunk post-processing" wording): each chunk
+ends up at the target peak, per-chunk head/tail silences are removed.
+
+``VocoderPipeline.run`` is the call a user of this package makes: host mel buffers in, host audio out.
+``run_device`` is the same with device-resident tensors (no copies); ``submit``/``collect`` pipeline jobs.
 """
 from __future__ import annotations
 
+import ctypes as C
 from dataclasses import dataclass
-from typing import Optional, Sequence
+from typing import Optional
 
 import numpy as np
 
+from . import _lib
 from . import post as _post
 from .hift import HiFTVocoder, SAMPLES_PER_FRAME, S3GEN_SR, N_MEL, _torch
 
 
 @dataclass
 class JobResult:
-    audio: "object"              # float32 (or int16) tensor/array holding the stitched job audio
+    audio: "object"                  # float32 (or int16) tensor/array holding the finished job audio
     total_samples: int
-    segments: Optional[np.ndarray]   # [n_chunks, 8] per-chunk start,end,peak,scale,dst,len,peak_used,-
+    segments: Optional[np.ndarray]   # [n_chunks, 8] per-chunk start,end,peak,scale,dst,len,peak_used,- (stitch pass)
     sr: int = S3GEN_SR
+    edit: Optional[dict] = None      # job granularity: the whole-file pass (start, end, peak_before, gain, trimmed, normalized)
+    raw: "object" = None             # job granularity with editing: the stitched PCM_16 "raw" file (device int16)
+    raw_samples: int = 0
 
 
 class VocoderPipeline:
-    """HiFT vocoder + per-chunk post-processing + gap stitching on one GPU."""
+    """HiFT vocoder + post-processing + gap stitching on one GPU (or one rank's shard of a job)."""
 
     def __init__(self, vocoder: HiFTVocoder, *, chunk_gap_ms: int = 250, trim_silence: bool = True,
                  normalize: bool = True, target_dbfs: float = -1.0, fade_ms: int = 10,
                  zero_cross_radius_ms: int = 10, silence_threshold: float = _post.SILENCE_THRESHOLD,
-                 silence_min_ms: int = _post.SILENCE_MIN_MS, out_pcm16: bool = False):
+                 silence_min_ms: int = _post.SILENCE_MIN_MS, out_pcm16: bool = False,
+                 granularity: str = "job", edit: str = "minimal_edit"):
+        if granularity not in ("job", "chunk"):
+            raise ValueError("granularity must be 'job' (reference order) or 'chunk'")
+        if edit not in ("minimal_edit", "minimal_post_process"):
+            raise ValueError("edit must be 'minimal_edit' or 'minimal_post_process'")
         self.voc = vocoder
         self.sr = S3GEN_SR
+        self.granularity = granularity
+        self.edit = edit
         self.opts = dict(chunk_gap_ms=int(chunk_gap_ms), trim_silence=bool(trim_silence), normalize=bool(normalize),
                          target_dbfs=float(target_dbfs), fade_ms=int(fade_ms), zero_cross_radius_ms=int(zero_cross_radius_ms),
                          silence_threshold=float(silence_threshold), silence_min_ms=int(silence_min_ms),
@@ -44,11 +72,29 @@ class VocoderPipeline:
         self._dev_in = None
         self._wav = None
         self._out = None
+        self._raw = None              # job granularity: stitched PCM_16 raw file
+        self._rawf = None             # ... as sf.read returns it (float32), the input of the whole-file pass
+        self._zero_peak = None
         self.last_launches = 0
         self._slots = None            # submit()/collect(): double-buffered device output + pinned host staging
         self._copy_stream = None
         self._h2d_done = None
         self._n_submitted = 0
+
+    # ------------------------------------------------------------------ configuration helpers
+    @property
+    def editing(self) -> bool:
+        return self.opts["trim_silence"] or self.opts["normalize"]
+
+    def describe(self) -> str:
+        """One-line statement of the post semantics (bench.py puts it in its config string)."""
+        o = self.opts
+        if self.granularity == "chunk":
+            return (f"per-chunk trim+snap+fade+peak-normalise ({o['target_dbfs']:g} dBFS), then {o['chunk_gap_ms']} ms gap "
+                    f"stitch (opt-in; not the reference's order)")
+        e = "no edit" if not self.editing else (
+            f"one whole-file {self.edit} (trim={o['trim_silence']}, normalise={o['normalize']} to {o['target_dbfs']:g} dBFS, one peak)")
+        return f"reference order: {o['chunk_gap_ms']} ms gap stitch of the raw chunks -> PCM_16 raw file -> {e}"
 
     def set_shard(self, chunk_ids, n_total_chunks: int) -> None:
         """Declare that this pipeline holds ``chunk_ids`` (sorted job-order indices) of a job sharded
@@ -58,6 +104,7 @@ class VocoderPipeline:
         self.stitch_head, self.stitch_tail = stitch_flags(chunk_ids, n_total_chunks)
 
     def post_params(self, n_chunks: int):
+        """Parameter block of the per-chunk (granularity='chunk') pass."""
         o = self.opts
         sr = self.sr
         gap_on = o["chunk_gap_ms"] > 0 and (n_chunks > 1 or not (self.stitch_head and self.stitch_tail))
@@ -71,48 +118,136 @@ class VocoderPipeline:
             normalize=1 if o["normalize"] else 0, target_peak=float(10 ** (o["target_dbfs"] / 20.0)), concat=1,
             out_pcm16=1 if o["out_pcm16"] else 0, stitch_head=self.stitch_head, stitch_tail=self.stitch_tail)
 
+    def stitch_params(self, n_chunks: int, *, out_pcm16: bool):
+        """Parameter block of stage A (``_apply_inter_chunk_gap`` on the raw chunks, tts_pipeline.py:398-405):
+        the gap applies only when the JOB has more than one chunk; a shard of a sharded job always has."""
+        o = self.opts
+        whole_job = bool(self.stitch_head and self.stitch_tail)
+        n_job = n_chunks if whole_job else max(n_chunks, 2)
+        return _post.stitch_params(n_job, sr=self.sr, gap_ms=o["chunk_gap_ms"], fade_ms=o["fade_ms"],
+                                   out_pcm16=1 if out_pcm16 else 0, stitch_head=self.stitch_head,
+                                   stitch_tail=self.stitch_tail)
+
+    def edit_params(self):
+        """Parameter block of stage B, the whole-file pass (one segment)."""
+        o = self.opts
+        sr = self.sr
+        common = dict(sr=sr, trim=1 if o["trim_silence"] else 0, silence_threshold=o["silence_threshold"],
+                      min_silence_frames=int(sr * (int(o["silence_min_ms"]) / 1000.0)), normalize=1,
+                      target_peak=float(10 ** (o["target_dbfs"] / 20.0)), concat=1, out_pcm16=1 if o["out_pcm16"] else 0)
+        if self.edit == "minimal_edit":       # audio_edit.py:16-79: no snap, no fades, clip
+            return _post.make_params(snap_radius=-1, clip=1, **common)
+        fade = int(sr * (int(o["fade_ms"]) / 1000.0))   # tts_pipeline.py:212-274: snap + fades, no clip; trim is unconditional there
+        common["trim"] = 1
+        return _post.make_params(snap_radius=int(sr * (int(o["zero_cross_radius_ms"]) / 1000.0)),
+                                 fade_in_frames=fade, fade_out_frames=fade, **common)
+
+    def out_capacity(self, T) -> int:
+        """Worst-case output samples of a job with mel lengths ``T`` (what submit() stages)."""
+        T = np.asarray(T)
+        gap = _post._ms_to_frames(self.sr, self.opts["chunk_gap_ms"])
+        return int(T.astype(np.int64).sum()) * SAMPLES_PER_FRAME + len(T) * gap
+
+    # ------------------------------------------------------------------ device path
+    def _buf(self, name, n, dtype):
+        torch = _torch()
+        cur = getattr(self, name)
+        if cur is None or cur.numel() < max(n, 4) or cur.dtype != dtype:
+            cur = torch.empty(max(n, 4), dtype=dtype, device=self.voc.device)
+            setattr(self, name, cur)
+        return cur
+
     def run_device(self, mel, T, *, f0=None, phase_vec=None, noise=None, seed: int = 0, read_back: bool = False) -> JobResult:
         """``mel``: float32 CUDA [sum_T, 80]; ``T``: int32 frames per chunk (host)."""
         torch = _torch()
         T = np.ascontiguousarray(T, dtype=np.int32)
         n = int(T.astype(np.int64).sum()) * SAMPLES_PER_FRAME
-        if self._wav is None or self._wav.numel() < n + 4:
-            self._wav = torch.empty(n + 4, dtype=torch.float32, device=self.voc.device)
-        wav = self.voc.forward_packed(mel, T, f0=f0, phase_vec=phase_vec, noise=noise, seed=seed, out=self._wav)
-        seg_off = np.concatenate([[0], np.cumsum(T.astype(np.int64) * SAMPLES_PER_FRAME)])
-        prm = self.post_params(len(T))
-        cap = n + len(T) * int(prm.gap_frames)
-        odt = torch.int16 if prm.out_pcm16 else torch.float32
-        if self._out is None or self._out.numel() < max(cap, 4) or self._out.dtype != odt:
-            self._out = torch.empty(max(cap, 4), dtype=odt, device=self.voc.device)
-        r = _post.post_process_device(wav, seg_off, prm, out=self._out, read_back=read_back)
-        # the library's per-thread launch counter is reset by vt_hift_forward and keeps counting through the post calls
-        self.last_launches = _post.last_launch_count()
-        self._last_post = r
-        return JobResult(r.out, r.total if r.total is not None else cap, r.results)
+        with torch.cuda.device(self.voc.device):
+            wav = self.voc.forward_packed(mel, T, f0=f0, phase_vec=phase_vec, noise=noise, seed=seed,
+                                          out=self._buf("_wav", n + 4, torch.float32))
+            seg_off = np.concatenate([[0], np.cumsum(T.astype(np.int64) * SAMPLES_PER_FRAME)])
+            res = self.post_device(wav, seg_off, read_back=read_back)
+            # the library's per-thread launch counter is reset by vt_hift_forward and keeps counting through the post calls
+            self.last_launches = _post.last_launch_count()
+        return res
 
+    def post_device(self, wav, seg_off, *, read_back: bool = False, range_override=None, peak_override=None) -> JobResult:
+        """The post stage alone on a packed float32 waveform (``seg_off``: int64[n_chunks+1], host).
+        ``range_override`` / ``peak_override`` replace the whole-file analysis of stage B (device tensors: int64[1][2]
+        and float32[1]) - the hook distributed.py uses for the cross-rank trim range and peak."""
+        torch = _torch()
+        seg_off = np.ascontiguousarray(seg_off, dtype=np.int64)
+        n_chunks = seg_off.size - 1
+        n = int(seg_off[-1])
+        odt = torch.int16 if self.opts["out_pcm16"] else torch.float32
+        if self.granularity == "chunk":
+            prm = self.post_params(n_chunks)
+            cap = n + n_chunks * int(prm.gap_frames)
+            r = _post.post_process_device(wav, seg_off, prm, out=self._buf("_out", cap, odt), read_back=read_back)
+            self._last_post = r
+            return JobResult(r.out, r.total if r.total is not None else cap, r.results)
+        # ---- reference order.  Stage A: stitch the raw chunks; the file is PCM_16 whenever a later stage reads it back
+        prmA = self.stitch_params(n_chunks, out_pcm16=True if self.editing else self.opts["out_pcm16"])
+        gapA = int(prmA.gap_frames)
+        n_raw = n + (n_chunks - (1 if self.stitch_tail else 0)) * gapA if n_chunks else 0
+        if not self.editing:
+            rA = _post.post_process_device(wav, seg_off, prmA, out=self._buf("_out", n + n_chunks * gapA, odt), read_back=read_back)
+            self._last_post = rA
+            return JobResult(rA.out, n_raw, rA.results, raw_samples=n_raw)
+        raw = self._buf("_raw", n + n_chunks * gapA, torch.int16)
+        rA = _post.post_process_device(wav, seg_off, prmA, out=raw, read_back=read_back)
+        # Stage B input = the raw file as sf.read returns it (audio_edit.py:41-45)
+        x = self._buf("_rawf", n_raw + 4, torch.float32)
+        lib = _lib.load_library()
+        _lib.check(lib.vt_pcm16_decode(int(raw.data_ptr()), int(x.data_ptr()), n_raw,
+                                       int(torch.cuda.current_stream().cuda_stream)), "vt_pcm16_decode")
+        prmB = self.edit_params()
+        if peak_override is None and not self.opts["normalize"]:
+            # the peak is still measured (peak_before is reported); a zero override applies no gain
+            if self._zero_peak is None:
+                self._zero_peak = torch.zeros(1, dtype=torch.float32, device=self.voc.device)
+            peak_override = self._zero_peak
+        rB = _post.post_process_device(x, [0, n_raw], prmB, out=self._buf("_out", n_raw, odt), read_back=read_back,
+                                       range_override=range_override, peak_override=peak_override)
+        self._last_post = _post.PostResult(rB.out, rB.total, rA.results, self._merge_tables(rA, rB), rB.total_dev)
+        edit = self._edit_dict(rB.results[0], n_raw) if read_back else None
+        return JobResult(rB.out, rB.total if rB.total is not None else n_raw, rA.results, edit=edit, raw=raw, raw_samples=n_raw)
+
+    @staticmethod
+    def _merge_tables(rA, rB):
+        """Stage A's per-chunk table with stage B's single row appended (one device tensor for deferred read-backs)."""
+        torch = _torch()
+        return torch.cat([rA.results_dev, rB.results_dev[:1]], dim=0)
+
+    def _edit_dict(self, row, n_raw: int) -> dict:
+        o = self.opts
+        start, end, peak, gain = int(row[0]), int(row[1]), float(row[2]), float(row[3])
+        normalized = bool(o["normalize"] and peak > 0.0 and 10 ** (o["target_dbfs"] / 20.0) > 0.0)
+        return {"start_sample": start, "end_sample": end, "peak_before": peak, "gain": gain if normalized else 1.0,
+                "trimmed": bool(o["trim_silence"] and 0 <= start < end <= n_raw), "normalized": normalized,
+                "target_dbfs": o["target_dbfs"], "edit": self.edit}
+
+    # ------------------------------------------------------------------ host API
     def run(self, mel_host, T, *, seed: int = 0) -> JobResult:
         """Host in / host out: ``mel_host`` float32 [sum_T, 80] (numpy or CPU tensor; pinned staging is
-        managed here), returns the stitched job audio as a numpy array of exactly the right length."""
+        managed here), returns the finished job audio as a numpy array of exactly the right length."""
         torch = _torch()
         T = np.ascontiguousarray(T, dtype=np.int32)
         total_T = int(T.astype(np.int64).sum())
         src = torch.as_tensor(mel_host, dtype=torch.float32).reshape(total_T, N_MEL)
-        if self._host_in is None or self._host_in.numel() < src.numel():
-            self._host_in = torch.empty(src.numel(), dtype=torch.float32).pin_memory()
-            self._dev_in = torch.empty(src.numel(), dtype=torch.float32, device=self.voc.device)
-        hin = self._host_in[: src.numel()].view(total_T, N_MEL)
-        if src.data_ptr() != hin.data_ptr():
-            hin.copy_(src)
-        dev = self._dev_in[: src.numel()].view(total_T, N_MEL)
-        dev.copy_(hin, non_blocking=True)
-        res = self.run_device(dev, T, seed=seed, read_back=True)
-        n = int(res.total_samples)
-        if self._host_out is None or self._host_out.numel() < n or self._host_out.dtype != res.audio.dtype:
-            self._host_out = torch.empty(max(n, 4), dtype=res.audio.dtype).pin_memory()
-        self._host_out[:n].copy_(res.audio[:n], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return JobResult(self._host_out[:n].numpy(), n, res.segments)
+        with torch.cuda.device(self.voc.device):
+            hin = self.pinned_input(total_T)
+            if src.data_ptr() != hin.data_ptr():
+                hin.copy_(src)
+            dev = self._dev_in[: src.numel()].view(total_T, N_MEL)
+            dev.copy_(hin, non_blocking=True)
+            res = self.run_device(dev, T, seed=seed, read_back=True)
+            n = int(res.total_samples)
+            if self._host_out is None or self._host_out.numel() < n or self._host_out.dtype != res.audio.dtype:
+                self._host_out = torch.empty(max(n, 4), dtype=res.audio.dtype).pin_memory()
+            self._host_out[:n].copy_(res.audio[:n], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return JobResult(self._host_out[:n].numpy(), n, res.segments, edit=res.edit, raw=res.raw, raw_samples=res.raw_samples)
 
     # ---- pipelined serving loop: submit(job k+1) is enqueued while job k's audio is still crossing PCIe
     def submit(self, mel_host, T, *, seed: int = 0) -> int:
@@ -123,67 +258,73 @@ class VocoderPipeline:
         torch = _torch()
         T = np.ascontiguousarray(T, dtype=np.int32)
         total_T = int(T.astype(np.int64).sum())
-        n_cap = total_T * SAMPLES_PER_FRAME + len(T) * int(self.post_params(len(T)).gap_frames)
+        n_cap = self.out_capacity(T)
         odt = torch.int16 if self.opts["out_pcm16"] else torch.float32
-        if self._copy_stream is None:
-            self._copy_stream = torch.cuda.Stream(device=self.voc.device)
-        if self._slots is None:
-            self._slots = [dict(dev=None, host=None, tot=torch.zeros(1, dtype=torch.int64).pin_memory(), res=None, n_seg=0,
-                                done=torch.cuda.Event(), busy=False) for _ in range(2)]
-        ticket = self._n_submitted
-        slot = self._slots[ticket & 1]
-        if slot["busy"]:
-            raise RuntimeError("two jobs are already in flight: collect() one first")
-        if slot["dev"] is None or slot["dev"].numel() < max(n_cap, 4) or slot["dev"].dtype != odt:
-            # a free slot grows on its own: the other one may still be in flight
-            slot["dev"] = torch.empty(max(n_cap, 4), dtype=odt, device=self.voc.device)
-            slot["host"] = torch.empty(max(n_cap, 4), dtype=odt).pin_memory()
-        src = torch.as_tensor(mel_host, dtype=torch.float32).reshape(total_T, N_MEL)
-        if self._h2d_done is not None:
-            self._h2d_done.synchronize()      # the previous job's input has left the pinned staging buffer
-        hin = self.pinned_input(total_T)
-        if src.data_ptr() != hin.data_ptr():
-            hin.copy_(src)
-        dev = self._dev_in[: src.numel()].view(total_T, N_MEL)
-        cur = torch.cuda.current_stream()
-        dev.copy_(hin, non_blocking=True)
-        self._h2d_done = torch.cuda.Event()
-        self._h2d_done.record(cur)
-        saved_out = self._out
-        self._out = slot["dev"]
-        try:
-            self.run_device(dev, T, seed=seed, read_back=False)
-        finally:
-            self._out = saved_out
-        r = self._last_post
-        ready = torch.cuda.Event()
-        ready.record(cur)
-        if slot["res"] is None or slot["res"].shape != r.results_dev.shape:
-            slot["res"] = torch.empty(r.results_dev.shape, dtype=r.results_dev.dtype).pin_memory()
-        with torch.cuda.stream(self._copy_stream):
-            self._copy_stream.wait_event(ready)
-            slot["tot"].copy_(r.total_dev, non_blocking=True)
-            slot["res"].copy_(r.results_dev, non_blocking=True)
-            slot["host"][:n_cap].copy_(slot["dev"][:n_cap], non_blocking=True)   # worst-case length: the total is not known yet
-            slot["done"].record(self._copy_stream)
-        # the compute stream must not reuse the slot before its copy has left (it is reused two submits later)
-        slot.update(n_seg=len(T), busy=True, bytes=n_cap * slot["dev"].element_size(), keep=r)   # keep: the copy reads r's tensors
-        self._n_submitted += 1
+        with torch.cuda.device(self.voc.device):
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=self.voc.device)
+            if self._slots is None:
+                self._slots = [dict(dev=None, host=None, tot=torch.zeros(1, dtype=torch.int64).pin_memory(), res=None, n_seg=0,
+                                    done=torch.cuda.Event(), busy=False) for _ in range(2)]
+            ticket = self._n_submitted
+            slot = self._slots[ticket & 1]
+            if slot["busy"]:
+                raise RuntimeError("two jobs are already in flight: collect() one first")
+            if slot["dev"] is None or slot["dev"].numel() < max(n_cap, 4) or slot["dev"].dtype != odt:
+                # a free slot grows on its own: the other one may still be in flight
+                slot["dev"] = torch.empty(max(n_cap, 4), dtype=odt, device=self.voc.device)
+                slot["host"] = torch.empty(max(n_cap, 4), dtype=odt).pin_memory()
+            src = torch.as_tensor(mel_host, dtype=torch.float32).reshape(total_T, N_MEL)
+            if self._h2d_done is not None:
+                self._h2d_done.synchronize()      # the previous job's input has left the pinned staging buffer
+            hin = self.pinned_input(total_T)
+            if src.data_ptr() != hin.data_ptr():
+                hin.copy_(src)
+            dev = self._dev_in[: src.numel()].view(total_T, N_MEL)
+            cur = torch.cuda.current_stream()
+            dev.copy_(hin, non_blocking=True)
+            self._h2d_done = torch.cuda.Event()
+            self._h2d_done.record(cur)
+            saved_out = self._out
+            self._out = slot["dev"]
+            try:
+                self.run_device(dev, T, seed=seed, read_back=False)
+            finally:
+                self._out = saved_out
+            r = self._last_post
+            ready = torch.cuda.Event()
+            ready.record(cur)
+            if slot["res"] is None or slot["res"].shape != r.results_dev.shape:
+                slot["res"] = torch.empty(r.results_dev.shape, dtype=r.results_dev.dtype).pin_memory()
+            with torch.cuda.stream(self._copy_stream):
+                self._copy_stream.wait_event(ready)
+                slot["tot"].copy_(r.total_dev, non_blocking=True)
+                slot["res"].copy_(r.results_dev, non_blocking=True)
+                slot["host"][:n_cap].copy_(slot["dev"][:n_cap], non_blocking=True)   # worst-case length: the total is not known yet
+                slot["done"].record(self._copy_stream)
+            # the compute stream must not reuse the slot before its copy has left (it is reused two submits later)
+            slot.update(n_seg=len(T), busy=True, bytes=n_cap * slot["dev"].element_size(), keep=r,   # keep: the copy reads r's tensors
+                        n_raw=n_cap - (int(self.stitch_params(len(T), out_pcm16=True).gap_frames) if self.stitch_tail else 0) if len(T) else 0)
+            self._n_submitted += 1
         return ticket
 
     def collect(self, ticket: int) -> JobResult:
-        """Wait for a submitted job; returns its stitched audio as a numpy view of the pinned slot (valid until the
+        """Wait for a submitted job; returns its finished audio as a numpy view of the pinned slot (valid until the
         slot is reused by the second submit after this one)."""
         torch = _torch()
         slot = self._slots[ticket & 1]
         if not slot["busy"]:
             raise RuntimeError("ticket is not in flight")
         slot["done"].synchronize()
-        torch.cuda.current_stream().wait_event(slot["done"])
+        torch.cuda.current_stream(self.voc.device).wait_event(slot["done"])
         slot["busy"] = False
         n = int(slot["tot"].item())
         self.last_d2h_bytes = slot["bytes"]
-        return JobResult(slot["host"][:n].numpy(), n, slot["res"].numpy()[: slot["n_seg"]].copy())
+        table = slot["res"].numpy()
+        edit = None
+        if self.granularity == "job" and self.editing:
+            edit = self._edit_dict(table[slot["n_seg"]], slot["n_raw"])
+        return JobResult(slot["host"][:n].numpy(), n, table[: slot["n_seg"]].copy(), edit=edit)
 
     def pinned_input(self, total_T: int):
         """A pinned host buffer [total_T, 80] callers can fill in place to skip the staging copy."""

@@ -15,6 +15,7 @@ Two layers:
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from dataclasses import dataclass
 from pathlib import Path
 from typing import Any, Optional, Sequence
@@ -60,15 +61,25 @@ class PostResult:
 
 
 class _Workspace:
-    """Grow-only device scratch shared by the post calls of one process (guarded by the GIL;
-    kernels are stream-ordered)."""
-    buf = None
+    """Grow-only device scratch of the post calls, one buffer PER THREAD AND DEVICE.
+
+    ``vt_post_analyze`` leaves its plan in the workspace and ``vt_post_write`` reads it back, and ctypes drops
+    the GIL during both calls; the reference runs up to ``MAX_CONCURRENT_JOBS = 2`` job threads
+    (backend/config.py:11), so a process-wide buffer would let thread B's analyse overwrite thread A's plan
+    between A's two calls.  Thread-local buffers make every analyse -> write pair private without serialising
+    the threads (kernels stay stream-ordered on the caller's stream)."""
+    _tls = threading.local()
 
     @classmethod
-    def get(cls, torch, nbytes: int):
-        if cls.buf is None or cls.buf.numel() < nbytes:
-            cls.buf = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, device="cuda")
-        return cls.buf
+    def get(cls, torch, nbytes: int, device=None):
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        bufs = getattr(cls._tls, "bufs", None)
+        if bufs is None:
+            bufs = cls._tls.bufs = {}
+        buf = bufs.get(device)
+        if buf is None or buf.numel() < nbytes:
+            buf = bufs[device] = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
+        return buf
 
 
 def last_launch_count() -> int:
@@ -85,14 +96,14 @@ def make_params(*, sr=TARGET_SR, trim=0, silence_threshold=SILENCE_THRESHOLD, mi
                       int(out_pcm16), int(stitch_head), int(stitch_tail))
 
 
-def _seg_arrays(torch, seg_off):
+def _seg_arrays(torch, seg_off, device=None):
     seg_np = np.ascontiguousarray(seg_off, dtype=np.int64)
     if seg_np.ndim != 1 or seg_np.size < 1 or np.any(np.diff(seg_np) < 0) or seg_np[0] != 0:
         raise ValueError("seg_off must be a non-decreasing int64 array starting at 0")
     n_seg = seg_np.size - 1
     n_samples = int(seg_np[-1])
     max_len = int(np.max(np.diff(seg_np))) if n_seg else 0
-    seg_dev = torch.from_numpy(seg_np).cuda()
+    seg_dev = torch.from_numpy(seg_np).to(device if device is not None else "cuda")
     return seg_np, seg_dev, n_seg, n_samples, max_len
 
 
@@ -100,38 +111,63 @@ def post_process_device(audio, seg_off, params: PostParams, *, out=None, range_o
                         peak_override=None, read_back=True) -> PostResult:
     """Run analyse + write on device tensors.  ``audio``: 1-D float32 CUDA tensor holding all
     segments; ``seg_off``: int64[n_seg+1] (host).  Output capacity is the worst case
-    ``n_samples + (n_seg-1)*gap``."""
+    ``n_samples + (n_seg-1)*gap``.  Everything is allocated and launched on ``audio``'s device and on
+    the calling thread's current stream for that device (job threads default to device 0 otherwise)."""
     torch = _torch()
     lib = _lib.load_library()
     if audio.dtype != torch.float32 or audio.dim() != 1 or not audio.is_cuda:
         raise ValueError("audio must be a 1-D float32 CUDA tensor")
-    audio = audio.contiguous()
-    if audio.data_ptr() % 16:
-        audio = audio.clone()
-    seg_np, seg_dev, n_seg, n_samples, max_len = _seg_arrays(torch, seg_off)
-    if n_samples > audio.numel():
-        raise ValueError("seg_off exceeds the audio buffer")
-    cap = n_samples + n_seg * max(int(params.gap_frames), 0) if params.concat else n_samples
-    odt = torch.int16 if params.out_pcm16 else torch.float32
-    if out is None:
-        out = torch.empty(max(cap, 4), dtype=odt, device="cuda") if params.concat else \
-            torch.zeros(max(cap, 4), dtype=odt, device="cuda")
-    elif out.dtype != odt or out.numel() < cap or not out.is_cuda:
-        raise ValueError("out tensor has the wrong dtype/size")
-    ws_bytes = int(lib.vt_post_workspace_bytes(n_seg, n_samples))
-    ws = _Workspace.get(torch, ws_bytes)
-    res = torch.empty((max(n_seg, 1), _lib.POST_RESULT_STRIDE), dtype=torch.float64, device="cuda")
-    tot = torch.zeros(1, dtype=torch.int64, device="cuda")
-    st = _stream(torch)
-    check(lib.vt_post_analyze(_ptr(audio), _ptr(seg_dev), n_seg, n_samples, max_len, C.byref(params),
-                              _ptr(range_override), _ptr(ws), ws.numel(), st), "vt_post_analyze")
-    check(lib.vt_post_write(_ptr(audio), _ptr(seg_dev), n_seg, n_samples, max_len, C.byref(params),
-                            _ptr(peak_override), _ptr(out), out.numel(), _ptr(res), _ptr(tot),
-                            _ptr(ws), ws.numel(), st), "vt_post_write")
-    if not read_back:
-        return PostResult(out, None, None, res, tot)
-    res_h = res.cpu().numpy()[:n_seg]
-    return PostResult(out, int(tot.item()), res_h, res, tot)
+    dev = audio.device
+    with torch.cuda.device(dev):
+        audio = audio.contiguous()
+        if audio.data_ptr() % 16:
+            audio = audio.clone()
+        seg_np, seg_dev, n_seg, n_samples, max_len = _seg_arrays(torch, seg_off, dev)
+        if n_samples > audio.numel():
+            raise ValueError("seg_off exceeds the audio buffer")
+        cap = n_samples + n_seg * max(int(params.gap_frames), 0) if params.concat else n_samples
+        odt = torch.int16 if params.out_pcm16 else torch.float32
+        if out is None:
+            out = torch.empty(max(cap, 4), dtype=odt, device=dev) if params.concat else \
+                torch.zeros(max(cap, 4), dtype=odt, device=dev)
+        elif out.dtype != odt or out.numel() < cap or not out.is_cuda or out.device != dev:
+            raise ValueError("out tensor has the wrong dtype/size/device")
+        for name, t in (("range_override", range_override), ("peak_override", peak_override)):
+            if t is not None and (not t.is_cuda or t.device != dev):
+                raise ValueError(f"{name} must live on the audio's device")
+        ws_bytes = int(lib.vt_post_workspace_bytes(n_seg, n_samples))
+        ws = _Workspace.get(torch, ws_bytes, dev)
+        res = torch.empty((max(n_seg, 1), _lib.POST_RESULT_STRIDE), dtype=torch.float64, device=dev)
+        tot = torch.zeros(1, dtype=torch.int64, device=dev)
+        st = _stream(torch)
+        check(lib.vt_post_analyze(_ptr(audio), _ptr(seg_dev), n_seg, n_samples, max_len, C.byref(params),
+                                  _ptr(range_override), _ptr(ws), ws.numel(), st), "vt_post_analyze")
+        check(lib.vt_post_write(_ptr(audio), _ptr(seg_dev), n_seg, n_samples, max_len, C.byref(params),
+                                _ptr(peak_override), _ptr(out), out.numel(), _ptr(res), _ptr(tot),
+                                _ptr(ws), ws.numel(), st), "vt_post_write")
+        if not read_back:
+            return PostResult(out, None, None, res, tot)
+        res_h = res.cpu().numpy()[:n_seg]
+        return PostResult(out, int(tot.item()), res_h, res, tot)
+
+
+def stats_device(audio, seg_off, *, threshold: float = SILENCE_THRESHOLD):
+    """One read pass over ``audio`` (float32 CUDA, segments ``seg_off``): returns device tensors
+    ``first_last`` int64[n_seg, 2] (first / last sample with |x| > threshold, -1 / -1 if none) and ``peak``
+    float32[n_seg].  No host synchronisation."""
+    torch = _torch()
+    lib = _lib.load_library()
+    if audio.dtype != torch.float32 or audio.dim() != 1 or not audio.is_cuda:
+        raise ValueError("audio must be a 1-D float32 CUDA tensor")
+    dev = audio.device
+    with torch.cuda.device(dev):
+        seg_np, seg_dev, n_seg, n_samples, max_len = _seg_arrays(torch, seg_off, dev)
+        fl = torch.full((max(n_seg, 1), 2), -1, dtype=torch.int64, device=dev)
+        pk = torch.zeros(max(n_seg, 1), dtype=torch.float32, device=dev)
+        ws = _Workspace.get(torch, int(lib.vt_post_workspace_bytes(n_seg, n_samples)), dev)
+        check(lib.vt_post_stats(_ptr(audio), _ptr(seg_dev), n_seg, n_samples, max_len, float(threshold), _ptr(fl),
+                                _ptr(pk), _ptr(ws), ws.numel(), _stream(torch)), "vt_post_stats")
+    return fl[:n_seg], pk[:n_seg]
 
 
 # ------------------------------------------------------------------------- reference-facing layer

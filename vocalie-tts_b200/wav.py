@@ -20,7 +20,7 @@ def read_pcm16(path) -> tuple[np.ndarray, int]:
         raise ValueError(f"{path}: only PCM_16 WAV is supported (sample width {sw})")
     if nch != 1:
         raise ValueError(f"{path}: only mono audio is supported ({nch} channels)")
-    return np.frombuffer(raw, dtype="<i2").astype(np.int16, copy=False), int(sr)
+    return np.frombuffer(raw, dtype="<i2").astype(np.int16, copy=True), int(sr)   # writable (torch.from_numpy)
 
 
 def write_pcm16(path, samples: np.ndarray, sr: int) -> None:
