@@ -256,7 +256,7 @@ def sine_source(f0, W, phase_vec, noise):
     """
     dt = f0.dtype
     f0u = f0.repeat_interleave(SAMPLES_PER_FRAME, dim=1).unsqueeze(1)          # nearest upsample [B,1,L]
-    F_mat = torch.zeros(f0.size(0), NB_HARM + 1, f0u.size(-1), dtype=dt)
+    F_mat = torch.zeros(f0.size(0), NB_HARM + 1, f0u.size(-1), dtype=dt, device=f0.device)
     for i in range(NB_HARM + 1):
         F_mat[:, i:i + 1, :] = f0u * (i + 1) / SR
     theta = 2 * np.pi * (torch.cumsum(F_mat, dim=-1) % 1)
@@ -271,7 +271,7 @@ def sine_source(f0, W, phase_vec, noise):
 
 def stft_source(s):
     """upstream HiFTGenerator._stft: [B, L] -> real||imag [B, 18, L/4+1]."""
-    win = torch.hann_window(N_FFT, periodic=True, dtype=s.dtype)
+    win = torch.hann_window(N_FFT, periodic=True, dtype=s.dtype, device=s.device)
     spec = torch.stft(s, N_FFT, HOP, N_FFT, window=win, return_complex=True)
     return torch.cat([spec.real, spec.imag], dim=1)
 
@@ -281,7 +281,7 @@ def istft_head(mag, phase):
     mag = torch.clip(mag, max=1e2)
     real = mag * torch.cos(phase)
     img = mag * torch.sin(phase)
-    win = torch.hann_window(N_FFT, periodic=True, dtype=mag.dtype)
+    win = torch.hann_window(N_FFT, periodic=True, dtype=mag.dtype, device=mag.device)
     return torch.istft(torch.complex(real, img), N_FFT, HOP, N_FFT, window=win)
 
 
@@ -352,13 +352,13 @@ def hift_inference(mel: torch.Tensor, W: Dict[str, torch.Tensor], *, f0: Optiona
         f0 = f0_predictor(mel, Wd)
     else:
         f0 = f0.to(dtype).unsqueeze(0)
-    s = sine_source(f0, Wd, phase_vec.unsqueeze(0), noise.unsqueeze(0))
+    s = sine_source(f0, Wd, phase_vec.unsqueeze(0).to(mel.device), noise.unsqueeze(0).to(mel.device))
     if taps is not None:
         taps["f0"] = f0
         taps["s"] = s
     y = decode(mel, s, Wd, quant, taps)
     if apply_trim_fade:
-        tf = trim_fade(dtype)
+        tf = trim_fade(dtype).to(y.device)
         n = min(tf.numel(), y.size(1))
         y[:, :n] *= tf[:n]
     return y.squeeze(0)

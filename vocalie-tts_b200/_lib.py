@@ -12,7 +12,10 @@ from pathlib import Path
 from .errors import BackendUnavailableError
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libvocalie_b200.so"
+# VT_LIB_PATH: A/B timing sessions load an alternative build of the same sources (tools/ab_build.sh); never set in
+# production, tests or bench
+import os as _os
+LIB_PATH = Path(_os.environ["VT_LIB_PATH"]) if _os.environ.get("VT_LIB_PATH") else _PKG / "libvocalie_b200.so"
 _lock = threading.Lock()
 _lib = None
 

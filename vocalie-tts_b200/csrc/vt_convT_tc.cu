@@ -54,9 +54,9 @@ k_convT_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ide
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NA * CB; ++i) { mbar_init(&a_full[i], kProd); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < NA * CB; ++i) { mbar_init(&a_full[i], kProdWarps); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < kTWst; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kTEpi * 32); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kTEpi); }
     fence_barrier_init();
   }
   if (warp == W_MMA) {
@@ -91,7 +91,7 @@ k_convT_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ide
         }
         cp_async_wait_all();
         fence_proxy_async();
-        mbar_arrive(&a_full[ab * CB + cb]);
+        mbar_arrive_warp(&a_full[ab * CB + cb]);
       }
     }
   } else if (warp == W_WP) {
@@ -250,7 +250,7 @@ k_convT_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ide
           }
         }
         tc_fence_before();
-        mbar_arrive(&acc_empty[buf]);
+        mbar_arrive_warp(&acc_empty[buf]);
       }
     }
   }

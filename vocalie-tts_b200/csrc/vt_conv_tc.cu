@@ -61,9 +61,9 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < A_ST * CB; ++i) { mbar_init(&a_full[i], kProd); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < A_ST * CB; ++i) { mbar_init(&a_full[i], kProdWarps); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < W_ST; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], NEPI * 32); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], NEPI); }
     fence_barrier_init();
   }
   if (warp == W_MMA) {
@@ -114,8 +114,8 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
         cp_async_wait_all();
         fence_proxy_async();
         if (pt == 0 && cb == NB - 1) trace_ev(a.trace, it, 2);
-        mbar_arrive(&a_full[ab * CB + cb]);
-        if (NB == 1) for (int x = 1; x < CB; ++x) mbar_arrive(&a_full[ab * CB + x]);
+        mbar_arrive_warp(&a_full[ab * CB + cb]);
+        if (NB == 1) for (int x = 1; x < CB; ++x) mbar_arrive_warp(&a_full[ab * CB + x]);
       }
     }
   } else if (warp == W_WP) {
@@ -221,7 +221,7 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
       tc_fence_after();
       epilogue_tile<NT, MB, NEPI, EM, ActT>(a, tile, nt, tmem_base + (uint32_t)(as * K::ACC_COLS), stage, warp, lane);
       tc_fence_before();
-      mbar_arrive(&acc_empty[as]);
+      mbar_arrive_warp(&acc_empty[as]);
       if (threadIdx.x == 0) trace_ev(a.trace, it, 7);
     }
   }

@@ -50,8 +50,8 @@ k_gemm_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const KBlock* __res
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < ST; ++i) { mbar_init(&full[i], kProd + 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], NEPI * 32); }
+    for (int i = 0; i < ST; ++i) { mbar_init(&full[i], kProdWarps + 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], NEPI); }
     fence_barrier_init();
   }
   if (warp == W_MMA) {
@@ -95,14 +95,14 @@ k_gemm_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const KBlock* __res
         if (issued - arrived > (uint32_t)LAG) {
           cp_async_wait_group<LAG>();
           fence_proxy_async();
-          mbar_arrive(&full[arrived % ST]);
+          mbar_arrive_warp(&full[arrived % ST]);
           ++arrived;
         }
       }
     }
     cp_async_wait_all();
     fence_proxy_async();
-    for (; arrived < issued; ++arrived) mbar_arrive(&full[arrived % ST]);
+    for (; arrived < issued; ++arrived) mbar_arrive_warp(&full[arrived % ST]);
   } else if (warp == W_WP) {
     // ---------------- weight producer: one bulk copy per K block
     if (lane == 0) {
@@ -162,7 +162,7 @@ k_gemm_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const KBlock* __res
       tc_fence_after();
       epilogue_tile<NT, MB, NEPI, EM, ActT>(a, tile, nt, tmem_base + (uint32_t)(as * ACC_COLS), stage, warp, lane);
       tc_fence_before();
-      mbar_arrive(&acc_empty[as]);
+      mbar_arrive_warp(&acc_empty[as]);
     }
   }
 

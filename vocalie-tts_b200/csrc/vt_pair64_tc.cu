@@ -151,8 +151,15 @@ __global__ void __launch_bounds__(kP64Warps * 32, 1) k_pair64_tc(const ConvArgs 
     uint32_t xs = 0, xph = 0;
     float4 ca[TPS], cb[TPS], na[TPS], nb[TPS];
     uint32_t slot_c = 0, slot_n = 0;
+    long long x_wait = 0;
     auto load_slab = [&](float4 (&va)[TPS], float4 (&vb)[TPS], uint32_t& slot) {
-      mbar_wait(&x_full[xs], xph);
+      if (a.trace) {
+        const long long tw = clock64();
+        mbar_wait(&x_full[xs], xph);
+        x_wait += clock64() - tw;
+      } else {
+        mbar_wait(&x_full[xs], xph);
+      }
       const uint32_t xsrc = smem_u32(sX + xs * kP64SlabBytes);
 #pragma unroll
       for (int t = 0; t < TPS; ++t) {
@@ -196,6 +203,7 @@ __global__ void __launch_bounds__(kP64Warps * 32, 1) k_pair64_tc(const ConvArgs 
       if (++sl == n_slab) {
         fence_proxy_async();
         if (pt == 0) trace_ev(a.trace, ti, 1);
+        if (pt == 0 && a.trace && blockIdx.x == 0 && ti < kTraceTiles) { a.trace[ti * kTraceEvents + 12] = x_wait; x_wait = 0; }
         __syncwarp();
         if (lane == 0) mbar_arrive(&a1_full[ti % kP64NA1]);
         sl = 0;
@@ -611,7 +619,7 @@ int launch_pair64_tc(const ConvArgs& a_in, const ConvLayer& c1, const ConvLayer&
       if (!h[it * tc::kTraceEvents + 0]) break;
       fprintf(stderr, "[vt trace] %2d", it);
       for (int e = 0; e < 10; ++e) fprintf(stderr, " %7lld", h[it * tc::kTraceEvents + e] ? h[it * tc::kTraceEvents + e] - t0 : -1);
-      fprintf(stderr, "  w_wait c1=%lld c2=%lld\n", h[it * tc::kTraceEvents + 10], h[it * tc::kTraceEvents + 11]);
+      fprintf(stderr, "  w_wait c1=%lld c2=%lld x_wait=%lld\n", h[it * tc::kTraceEvents + 10], h[it * tc::kTraceEvents + 11], h[it * tc::kTraceEvents + 12]);
     }
   }
   return rc;

@@ -134,12 +134,12 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NA1; ++i) { mbar_init(&a1_full[i], kProdT); mbar_init(&a1_empty[i], 1); }
-    for (int i = 0; i < NA2; ++i) { mbar_init(&a2_full[i], NMID * 32); mbar_init(&a2_empty[i], 1); }
-    for (int i = 0; i < NSLAB; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], kProdT); }
+    for (int i = 0; i < NA1; ++i) { mbar_init(&a1_full[i], NPROD); mbar_init(&a1_empty[i], 1); }
+    for (int i = 0; i < NA2; ++i) { mbar_init(&a2_full[i], NMID); mbar_init(&a2_empty[i], 1); }
+    for (int i = 0; i < NSLAB; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], NPROD); }
     for (int i = 0; i < NBUF; ++i) {
-      mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], NMID * 32);
-      mbar_init(&d2_full[i], 1); mbar_init(&d2i_full[i], kFin * 32);
+      mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], NMID);
+      mbar_init(&d2_full[i], 1); mbar_init(&d2i_full[i], kFin);
     }
     // weight-ring slots are released by the MMA warps of every CTA that received the multicast copy
     for (int i = 0; i < W_ST; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], a.mc ? 2 : 1); }
@@ -210,8 +210,15 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
       mbar_wait_relaxed(&a1_empty[b1], ((uint32_t)(i / NA1) & 1u) ^ 1u);
       if (pt == 0) trace_ev(a.trace, i, 0);
       const uint32_t a1 = a1_base + (uint32_t)(b1 * A1_BYTES);
+      long long x_wait = 0;
       for (int sl = 0; sl < n_slab; ++sl) {
-        mbar_wait_relaxed(&x_full[xs], xph);
+        if (a.trace) {
+          const long long tw = clock64();
+          mbar_wait_relaxed(&x_full[xs], xph);
+          x_wait += clock64() - tw;
+        } else {
+          mbar_wait_relaxed(&x_full[xs], xph);
+        }
         const uint32_t xsrc = smem_u32(sX + xs * kSlabBytes);
         // all shared-memory reads of this slab first (the volatile asm statements keep program order, so
         // interleaving loads and stores task by task would serialise the tasks), then convert and store
@@ -240,12 +247,13 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
             asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(rowb + blkB + ((chkB ^ swz) << 4) + halfB), "r"(pb.x), "r"(pb.y) : "memory");
           }
         }
-        mbar_arrive(&x_empty[xs]);                  // the slab has been read: the loader may refill it
+        mbar_arrive_warp(&x_empty[xs]);                  // the slab has been read: the loader may refill it
         if (++xs == (uint32_t)NSLAB) { xs = 0; xph ^= 1u; }
       }
       fence_proxy_async();
       if (pt == 0) trace_ev(a.trace, i, 1);
-      mbar_arrive(&a1_full[b1]);
+      if (pt == 0 && a.trace && blockIdx.x == 0 && i < kTraceTiles) a.trace[i * kTraceEvents + 12] = x_wait;
+      mbar_arrive_warp(&a1_full[b1]);
     }
   } else if (warp == W_XL || warp == W_WP) {
     // ---------------- loaders: one THREAD per ring, each in its own blocking loop (a thread that polled both rings
@@ -418,8 +426,8 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
         tc_fence_before();
         fence_proxy_async();
         if (ew == 0 && lane == 0) trace_ev(a.trace, i, 3);
-        mbar_arrive(&d1_empty[0]);
-        mbar_arrive(&a2_full[0]);
+        mbar_arrive_warp(&d1_empty[0]);
+        mbar_arrive_warp(&a2_full[0]);
       }
     } else {
       constexpr bool kRes2 = (EM & EM_RES2) != 0, kAccum = (EM & EM_ACCUM) != 0;
@@ -494,7 +502,7 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
         }
         tc_fence_before();
         if (warp == 0 && lane == 0) trace_ev(a.trace, i, 5);
-        mbar_arrive(&d2i_full[0]);
+        mbar_arrive_warp(&d2i_full[0]);
       }
     }
   } else {
@@ -677,7 +685,7 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
         }
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&d2i_full[j]);
+        mbar_arrive_warp(&d2i_full[j]);
       }
     }
     for (int i = 0; i < n_my; ++i) {
@@ -724,8 +732,8 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
         tc_fence_before();
         fence_proxy_async();
         if (ew == 0 && lane == 0) trace_ev(a.trace, i, 3);
-        mbar_arrive(&d1_empty[b]);
-        mbar_arrive(&a2_full[b2]);
+        mbar_arrive_warp(&d1_empty[b]);
+        mbar_arrive_warp(&a2_full[b2]);
       }
       if (do_fin) {
         mbar_wait_relaxed(&d2_full[b], u & 1u);
@@ -744,7 +752,7 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
           if (has_next) tmem_st_wait();
           tc_fence_before();
           if (warp == 0 && lane == 0) trace_ev(a.trace, i, 5);
-          if (has_next) mbar_arrive(&d2i_full[b]);
+          if (has_next) mbar_arrive_warp(&d2i_full[b]);
         } else {
 #pragma unroll
           for (int k = 0; k < BPW; ++k) {
@@ -753,7 +761,7 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
           }
           tc_fence_before();
           if (warp == 0 && lane == 0) trace_ev(a.trace, i, 5);
-          mbar_arrive(&d2i_full[b]);
+          mbar_arrive_warp(&d2i_full[b]);
         }
         // combined mode: the staging lives in the A2 tile; nobody may start mid(i+1) before everyone left fin(i)
         if (kCombined) asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");
@@ -888,7 +896,14 @@ int launch_pair_tc(const ConvArgs& a_in, const ConvLayer& c1, const ConvLayer& c
   const uint32_t fmt = act_elem == ELEM_F16 ? 0u : 1u;
   const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(C >> 3) << 17) | ((128u >> 4) << 24);
   int rc;
-  if (act_elem == ELEM_F16)
+  // experiment switch: C = 128 with a 2-slot weight ring and a 5-slab x ring (same shared memory)
+  static const bool ring5 = getenv("VT_P128_RING") && getenv("VT_P128_RING")[0] == '5';
+  static const bool nprod4 = getenv("VT_P64_NPROD") && getenv("VT_P64_NPROD")[0] == '4';   // experiment: 4 producer warps at C = 64
+  if (act_elem == ELEM_F16 && C == 128 && ring5)
+    rc = tc::launch_pair_c<128, 1, 1, 1, 2, 8, 4, 5, __half>(a, p, idesc, grid, st);
+  else if (act_elem == ELEM_F16 && C == 64 && nprod4)
+    rc = tc::launch_pair_c<64, 2, 2, 1, 4, 8, 4, 5, __half>(a, p, idesc, grid, st);
+  else if (act_elem == ELEM_F16)
     rc = C == 64 ? tc::launch_pair_c<64, 2, 2, 1, 4, 8, 2, 5, __half>(a, p, idesc, grid, st)
                  : tc::launch_pair_c<128, 1, 1, 1, 3, 8, 4, 3, __half>(a, p, idesc, grid, st);
   else
@@ -907,7 +922,7 @@ int launch_pair_tc(const ConvArgs& a_in, const ConvLayer& c1, const ConvLayer& c
       if (!h[it * tc::kTraceEvents + 0]) break;
       fprintf(stderr, "[vt trace] %2d", it);
       for (int e = 0; e < 10; ++e) fprintf(stderr, " %7lld", h[it * tc::kTraceEvents + e] ? h[it * tc::kTraceEvents + e] - t0 : -1);
-      fprintf(stderr, "  w_wait c1=%lld c2=%lld", h[it * tc::kTraceEvents + 10], h[it * tc::kTraceEvents + 11]);
+      fprintf(stderr, "  w_wait c1=%lld c2=%lld x_wait=%lld", h[it * tc::kTraceEvents + 10], h[it * tc::kTraceEvents + 11], h[it * tc::kTraceEvents + 12]);
       fprintf(stderr, "\n");
     }
   }

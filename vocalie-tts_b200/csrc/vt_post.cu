@@ -795,8 +795,7 @@ int vt_post_stats(const float* audio, const int64_t* seg_off, int n_seg, int64_t
   VT_REQUIRE((first_last != nullptr && peak != nullptr) || n_seg == 0, "vt_post_stats: NULL output");
   VT_REQUIRE(workspace_bytes >= post_ws_bytes(n_seg, n_samples), "post workspace too small");
   if (n_seg == 0) return VT_OK;
-  launch_counter() = 0;
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);     // (the launch counter keeps running: part of a job)
   PostWs w = carve(workspace, n_seg, n_samples);
   k_post_init<<<(n_seg + 255) / 256, 256, 0, st>>>(w.plan, w.hdr, seg_off, n_seg, nullptr);
   VT_LAUNCHED();

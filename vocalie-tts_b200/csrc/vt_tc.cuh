@@ -27,6 +27,12 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// One arrival per WARP: every lane has finished its part (and issued its own proxy / tcgen05 fence), the warp
+// converges, lane 0 arrives.  Barriers counted in warps see 32x fewer arrivals - and their waiters fewer wake-ups.
+__device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -48,11 +54,27 @@ __device__ __forceinline__ bool mbar_try(uint32_t addr, uint32_t parity) {
       : "memory");
   return done != 0;
 }
+// Slow path.  ncu's source view of the round-1 build showed 37-61 % of ALL executed warp instructions of the pair
+// kernels in this function: the hardware suspend of try_wait ends early (30-70 wake-ups per wait), and every
+// iteration also read the clock and did a 64-bit compare (11 instructions).  The bound is now an iteration count
+// checked in an outer loop: an iteration is try_wait + sleep + recheck + count + branch.
+#ifdef VT_AB_OLD_WAIT   // A/B builds only (tools/ab_build.sh): the round-1 loop with a clock read per probe
 static __device__ __noinline__ void mbar_wait_slow(uint32_t addr, uint32_t parity) {
   const long long t0 = clock64();
   while (!mbar_try(addr, parity))
     if (clock64() - t0 > 4000000000LL) __trap();
 }
+#else
+static __device__ __noinline__ void mbar_wait_slow(uint32_t addr, uint32_t parity) {
+#pragma unroll 1
+  for (int outer = 0; outer < (1 << 14); ++outer) {
+#pragma unroll 1
+    for (int i = 0; i < 2048; ++i)
+      if (mbar_try(addr, parity)) return;
+  }
+  __trap();   // ~3e7 failed probes (seconds): a protocol bug must fault the launch, not hang the GPU
+}
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   if (!mbar_try(addr, parity)) mbar_wait_slow(addr, parity);
@@ -233,7 +255,7 @@ __device__ __forceinline__ float snake_poly(float v, float alpha, float inv_alph
 }
 
 // Debug timeline (VT_TC_TRACE): CTA 0 records clock64 at role events of its first kTraceTiles tiles.
-constexpr int kTraceTiles = 48, kTraceEvents = 12;
+constexpr int kTraceTiles = 48, kTraceEvents = 14;   // 0-9 role timestamps, 10/11 weight-ring waits of conv1/conv2, 12 producer x-ring wait, 13 spare
 __device__ __forceinline__ void trace_ev(long long* trace, int it, int ev) {
   if (trace && blockIdx.x == 0 && it < kTraceTiles) trace[it * kTraceEvents + ev] = clock64();
 }

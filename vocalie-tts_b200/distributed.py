@@ -97,6 +97,8 @@ def assemble_pieces(local, pieces_by_rank: Sequence[Sequence[Piece]], total: int
     import torch.distributed as dist
     rank = dist.get_rank(group)
     ops = []
+    # torch's NCCL binding has no int16: PCM_16 pieces travel as bytes (same memory, no copy)
+    wire = (lambda t: t.view(torch.uint8)) if local.dtype == torch.int16 else (lambda t: t)
     if rank == dst:
         if out is None:
             out = torch.empty(max(total, 1), dtype=local.dtype, device=local.device)
@@ -107,11 +109,11 @@ def assemble_pieces(local, pieces_by_rank: Sequence[Sequence[Piece]], total: int
                 if r == rank:
                     out[d0:d0 + n].copy_(local[src0:src0 + n])
                 else:
-                    ops.append(dist.P2POp(dist.irecv, out[d0:d0 + n], dist.get_global_rank(group, r) if group is not None else r, group))
+                    ops.append(dist.P2POp(dist.irecv, wire(out[d0:d0 + n]), dist.get_global_rank(group, r) if group is not None else r, group))
     else:
         for src0, n, d0 in pieces_by_rank[rank]:
             if n > 0:
-                ops.append(dist.P2POp(dist.isend, local[src0:src0 + n], dist.get_global_rank(group, dst) if group is not None else dst, group))
+                ops.append(dist.P2POp(dist.isend, wire(local[src0:src0 + n]), dist.get_global_rank(group, dst) if group is not None else dst, group))
     if ops:
         for req in dist.batch_isend_irecv(ops):
             req.wait()
@@ -208,20 +210,24 @@ class ShardedJob:
         self.runs_off = np.concatenate([[0], np.cumsum([n for _, n, _ in mine])]).astype(np.int64)
         self.min_sil = int(pipe.sr * (int(o["silence_min_ms"]) / 1000.0))
 
-    def run_device(self, mel, *, f0=None, phase_vec=None, noise=None, seed: int = 0, out=None) -> ShardedJobResult:
-        """``mel``: this rank's chunks, float32 CUDA [sum(local_T), 80]."""
+    def run_device(self, mel, *, f0=None, phase_vec=None, noise=None, seed: int = 0, out=None,
+                   max_frames: Optional[int] = None) -> ShardedJobResult:
+        """``mel``: this rank's chunks, float32 CUDA [sum(local_T), 80].  ``max_frames`` bounds the mel frames per
+        vocoder call (length bucketing of long jobs, HiFTVocoder.forward_bucketed)."""
         import torch
         from .hift import SAMPLES_PER_FRAME
         pipe = self.pipe
         T = self.local_T
         n = int(T.astype(np.int64).sum()) * SAMPLES_PER_FRAME
         with torch.cuda.device(pipe.voc.device):
-            wav = pipe.voc.forward_packed(mel, T, f0=f0, phase_vec=phase_vec, noise=noise, seed=seed,
-                                          out=pipe._buf("_wav", n + 4, torch.float32))
+            wav = pipe._buf("_wav", n + 4, torch.float32)
+            if T.size:
+                pipe.voc.forward_bucketed(mel, T, f0=f0, phase_vec=phase_vec, noise=noise, seed=seed, out=wav, max_frames=max_frames)
             seg_off = np.concatenate([[0], np.cumsum(T.astype(np.int64) * SAMPLES_PER_FRAME)])
             res = self.post_device(wav, seg_off, out=out)
             from . import post as _post
-            pipe.last_launches = _post.last_launch_count()
+            pipe.last_launches = (pipe.voc.last_launches + _post.last_launch_count() - pipe.voc._last_call_launches) if T.size \
+                else _post.last_launch_count()
         return res
 
     def post_device(self, wav, seg_off, *, out=None, ops=None) -> ShardedJobResult:

@@ -121,6 +121,7 @@ class HiFTVocoder:
         self._lock = threading.Lock()   # reference jobs run on up to 2 threads (backend/config.py:11)
         self.device = torch.device("cuda", torch.cuda.current_device())
         self.last_launches = 0
+        self._last_call_launches = 0
 
     def close(self):
         if getattr(self, "_h", None):
@@ -183,7 +184,40 @@ class HiFTVocoder:
                                            ptr(phase_vec), ptr(noise), int(seed) & (2 ** 64 - 1), ptr(out), ptr(ws),
                                            ws.numel(), int(torch.cuda.current_stream().cuda_stream))
             check(rc, "vt_hift_forward")
-            self.last_launches = int(self._lib.vt_last_launch_count())
+            self.last_launches = self._last_call_launches = int(self._lib.vt_last_launch_count())
+        return out
+
+    def forward_bucketed(self, mel, T, *, f0=None, phase_vec=None, noise=None, seed: int = 0, out=None,
+                         max_frames: Optional[int] = None):
+        """``forward_packed`` over consecutive buckets of sequences holding at most ``max_frames`` mel frames each
+        (a single longer sequence gets a bucket of its own): the workspace is sized by the bucket, not by the job, so
+        a 2 048-chunk narration (BASELINE configs[3]) runs in bounded memory.  The ragged batch is packed, not padded,
+        so bucketing costs no arithmetic; results are identical to one call (sequences are independent; the in-kernel
+        generator is keyed on the seed and the sequence's index IN ITS BUCKET, so pass explicit ``phase_vec`` /
+        ``noise`` when bit-equality with an unbucketed call matters)."""
+        torch = _torch()
+        T = np.ascontiguousarray(T, dtype=np.int32)
+        total_T = int(T.astype(np.int64).sum())
+        if max_frames is None or total_T <= max_frames or T.size <= 1:
+            return self.forward_packed(mel, T, f0=f0, phase_vec=phase_vec, noise=noise, seed=seed, out=out)
+        if out is None:
+            out = torch.empty(total_T * SAMPLES_PER_FRAME, dtype=torch.float32, device=self.device)
+        off = np.concatenate([[0], np.cumsum(T.astype(np.int64))])
+        b0 = 0
+        launches = 0
+        while b0 < T.size:
+            b1 = b0 + 1
+            while b1 < T.size and off[b1 + 1] - off[b0] <= max_frames:
+                b1 += 1
+            f_lo, f_hi = int(off[b0]), int(off[b1])
+            self.forward_packed(mel[f_lo:f_hi], T[b0:b1], f0=None if f0 is None else f0[f_lo:f_hi],
+                                phase_vec=None if phase_vec is None else phase_vec.reshape(-1, N_HARMONICS)[b0:b1].contiguous(),
+                                noise=None if noise is None else noise.reshape(-1)[f_lo * SAMPLES_PER_FRAME * N_HARMONICS:
+                                                                                  f_hi * SAMPLES_PER_FRAME * N_HARMONICS],
+                                seed=seed + b0, out=out[f_lo * SAMPLES_PER_FRAME:f_hi * SAMPLES_PER_FRAME])
+            launches += self.last_launches
+            b0 = b1
+        self.last_launches = launches          # all buckets (the library's own counter restarts with every call)
         return out
 
     def inference(self, mels: Sequence, *, f0: Optional[Sequence] = None, phase_vec=None, noise: Optional[Sequence] = None,

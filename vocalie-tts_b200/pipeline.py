@@ -157,18 +157,21 @@ class VocoderPipeline:
             setattr(self, name, cur)
         return cur
 
-    def run_device(self, mel, T, *, f0=None, phase_vec=None, noise=None, seed: int = 0, read_back: bool = False) -> JobResult:
-        """``mel``: float32 CUDA [sum_T, 80]; ``T``: int32 frames per chunk (host)."""
+    def run_device(self, mel, T, *, f0=None, phase_vec=None, noise=None, seed: int = 0, read_back: bool = False,
+                   max_frames: Optional[int] = None) -> JobResult:
+        """``mel``: float32 CUDA [sum_T, 80]; ``T``: int32 frames per chunk (host).  ``max_frames`` bounds the mel
+        frames per vocoder call (length bucketing of long jobs, HiFTVocoder.forward_bucketed)."""
         torch = _torch()
         T = np.ascontiguousarray(T, dtype=np.int32)
         n = int(T.astype(np.int64).sum()) * SAMPLES_PER_FRAME
         with torch.cuda.device(self.voc.device):
-            wav = self.voc.forward_packed(mel, T, f0=f0, phase_vec=phase_vec, noise=noise, seed=seed,
-                                          out=self._buf("_wav", n + 4, torch.float32))
+            wav = self.voc.forward_bucketed(mel, T, f0=f0, phase_vec=phase_vec, noise=noise, seed=seed,
+                                            out=self._buf("_wav", n + 4, torch.float32), max_frames=max_frames)
             seg_off = np.concatenate([[0], np.cumsum(T.astype(np.int64) * SAMPLES_PER_FRAME)])
             res = self.post_device(wav, seg_off, read_back=read_back)
-            # the library's per-thread launch counter is reset by vt_hift_forward and keeps counting through the post calls
-            self.last_launches = _post.last_launch_count()
+            # the library's per-thread launch counter restarts with every vt_hift_forward and keeps counting through the
+            # post calls: kernels of this job = all vocoder buckets + what the post calls added to the last one
+            self.last_launches = self.voc.last_launches + _post.last_launch_count() - self.voc._last_call_launches
         return res
 
     def post_device(self, wav, seg_off, *, read_back: bool = False, range_override=None, peak_override=None) -> JobResult:
@@ -228,7 +231,7 @@ class VocoderPipeline:
                 "target_dbfs": o["target_dbfs"], "edit": self.edit}
 
     # ------------------------------------------------------------------ host API
-    def run(self, mel_host, T, *, seed: int = 0) -> JobResult:
+    def run(self, mel_host, T, *, seed: int = 0, max_frames: Optional[int] = None) -> JobResult:
         """Host in / host out: ``mel_host`` float32 [sum_T, 80] (numpy or CPU tensor; pinned staging is
         managed here), returns the finished job audio as a numpy array of exactly the right length."""
         torch = _torch()
@@ -241,7 +244,7 @@ class VocoderPipeline:
                 hin.copy_(src)
             dev = self._dev_in[: src.numel()].view(total_T, N_MEL)
             dev.copy_(hin, non_blocking=True)
-            res = self.run_device(dev, T, seed=seed, read_back=True)
+            res = self.run_device(dev, T, seed=seed, read_back=True, max_frames=max_frames)
             n = int(res.total_samples)
             if self._host_out is None or self._host_out.numel() < n or self._host_out.dtype != res.audio.dtype:
                 self._host_out = torch.empty(max(n, 4), dtype=res.audio.dtype).pin_memory()
