@@ -139,6 +139,15 @@ int vt_post_process(const float* audio, const int64_t* seg_off, int n_seg, int64
 int vt_pcm16_encode(const float* in, int16_t* out, int64_t n, void* stream);
 int vt_pcm16_decode(const int16_t* in, float* out, int64_t n, void* stream);
 
+/* The 44-byte RIFF/WAVE header of a mono PCM_16 file, written on the device in front of the samples vt_post_write
+ * produced (out_pcm16 = 1), so a finished - possibly trimmed - job leaves the GPU as a file image in one copy.  The
+ * sample count is *n_samples_dev (device int64, e.g. the writer's total_out) when non-NULL, else n_samples_host.
+ * Byte-identical to what the reference's writers produce for these parameters (tts_backends/chatterbox_runner.py:152,
+ * backend/shared/tts_pipeline.py:409, backend/shared/audio_edit.py:70). */
+#define VT_WAV_HEADER_BYTES 44
+int vt_wav_pcm16_header(void* dst /* device, 44 bytes */, int sample_rate, const int64_t* n_samples_dev,
+                        int64_t n_samples_host, void* stream);
+
 /* RMS helper the reference uses to validate clips (tts_backends/cosyvoice_backend.py:103,
  * tests/test_qwen3_runner.py:58): rms_out[i] = sqrt(mean(float64(x)^2)) over segment i, 0 for an empty
  * segment.  float64 accumulation in a fixed reduction order (deterministic; equal to numpy's pairwise

@@ -58,6 +58,7 @@ _SIGS = {
     "vt_post_analyze": (C.c_int, [_P, _P, C.c_int, _I64, _I64, C.POINTER(PostParams), _P, _P, _I64, _P]),
     "vt_post_write": (C.c_int, [_P, _P, C.c_int, _I64, _I64, C.POINTER(PostParams), _P, _P, _I64, _P, _P, _P, _I64, _P]),
     "vt_post_process": (C.c_int, [_P, _P, C.c_int, _I64, _I64, C.POINTER(PostParams), _P, _I64, _P, _P, _P, _I64, _P]),
+    "vt_wav_pcm16_header": (C.c_int, [_P, C.c_int, _P, _I64, _P]),
     "vt_pcm16_encode": (C.c_int, [_P, _P, _I64, _P]),
     "vt_pcm16_decode": (C.c_int, [_P, _P, _I64, _P]),
     "vt_hift_create": (C.c_int, [C.POINTER(Tensor), C.c_int, C.c_int, C.POINTER(_P)]),

@@ -253,13 +253,32 @@ class ChatterboxB200Backend(TTSBackend):
                    lang: Optional[str] = None, **params: Any) -> Dict[str, Any]:
         """Writes a PCM_16 WAV at ``out_path`` (the runner's wire format,
         tts_backends/chatterbox_runner.py:152) and returns the reference's meta dict
-        (chatterbox_backend.py:163-174)."""
-        audio, sr, _ = self.synthesize_chunk(script, voice_ref_path=voice_ref_path, lang=lang, **params)
+        (chatterbox_backend.py:163-174).  The file is finished ON THE DEVICE: the vocoder's float32 waveform goes
+        through the fused PCM_16 writer behind a device-written RIFF header and leaves the GPU in one copy
+        (``post.WavImage``) - no float32 round trip over PCIe, no host-side encode."""
         from . import post as _post
-        q = _post.pcm16_encode(audio)
-        _wav.write_pcm16(Path(out_path), q, sr)
+        torch = _post._torch()          # no CUDA device -> BackendUnavailableError (no CPU fallback below the boundary)
+        voc, _ = self._engine()
+        mels, f0s = self._mels_for([script], voice_ref_path, lang, params)
+        mel = torch.as_tensor(np.asarray(mels[0]) if not hasattr(mels[0], "shape") else mels[0])
+        f0 = None if f0s[0] is None else [torch.as_tensor(f0s[0])]
+        try:
+            with self._lock:
+                seed = int(params["seed"]) if params.get("seed") is not None else self._next_seed()
+                with torch.cuda.device(voc.device):
+                    wav = voc.inference([mel], f0=f0, seed=seed)[0]
+                    n = int(wav.numel())
+                    img = _post.WavImage(n, voc.device)
+                    prm = _post.make_params(sr=SR, concat=1, out_pcm16=1)
+                    _post.post_process_device(wav, [0, n], prm, out=img.samples, read_back=False)
+                    img.finish(SR, total=n)
+                    img.to_file(out_path, n)
+        except BackendUnavailableError:
+            raise
+        except RuntimeError as exc:
+            raise BackendUnavailableError(f"B200 vocoder failed: {exc}") from exc
         return {"backend_id": self.id, "backend_lang": lang, "out_path": str(out_path),
-                "duration_s": float(len(audio)) / float(sr), "retry": False}
+                "duration_s": float(n) / float(SR), "retry": False}
 
 
 def shard_chunks(lengths: Sequence[int], world: int) -> List[List[int]]:

@@ -583,6 +583,25 @@ __global__ void k_pcm16_decode(const short* __restrict__ in, float* __restrict__
   for (long long k = i; k < n; k += stride) out[k] = __fdiv_rn((float)in[k], 32768.0f);
 }
 
+// Canonical 44-byte RIFF/WAVE header of a mono PCM_16 file (what Python's wave module and libsndfile write for
+// sf.write(path, x, sr) with the default subtype: tts_backends/chatterbox_runner.py:152, tts_pipeline.py:409,
+// audio_edit.py:70), written on the device so that a trimmed job - whose length is data dependent and lives in device
+// memory - leaves the GPU as a finished file in ONE copy.
+__global__ void k_wav_header(unsigned char* dst, int sr, const long long* n_dev, long long n_host) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const unsigned long long n = (unsigned long long)(n_dev ? *n_dev : n_host);
+  const unsigned data = (unsigned)(n * 2ULL), riff = 36u + data, rate = (unsigned)sr, brate = rate * 2u;
+  auto u32 = [&](int o, unsigned v) { dst[o] = v & 255u; dst[o + 1] = (v >> 8) & 255u; dst[o + 2] = (v >> 16) & 255u; dst[o + 3] = v >> 24; };
+  auto tag = [&](int o, const char* t) { for (int i = 0; i < 4; ++i) dst[o + i] = (unsigned char)t[i]; };
+  tag(0, "RIFF"); u32(4, riff); tag(8, "WAVE"); tag(12, "fmt "); u32(16, 16u);
+  dst[20] = 1; dst[21] = 0;            // PCM
+  dst[22] = 1; dst[23] = 0;            // mono
+  u32(24, rate); u32(28, brate);
+  dst[32] = 2; dst[33] = 0;            // block align
+  dst[34] = 16; dst[35] = 0;           // bits per sample
+  tag(36, "data"); u32(40, data);
+}
+
 // ------------------------------------------------------------------------------------ host
 struct PostWs {
   PostHeader* hdr;
@@ -832,6 +851,16 @@ int vt_rms(const float* audio, const int64_t* seg_off, int n_seg, double* rms_ou
   k_rms_partial<<<dim3(VT_RMS_PARTIALS, n_seg), kThreads, 0, st>>>(audio, seg_off, reinterpret_cast<double*>(workspace));
   VT_LAUNCHED();
   k_rms_final<<<(n_seg + 7) / 8, 256, 0, st>>>(seg_off, n_seg, reinterpret_cast<const double*>(workspace), rms_out);
+  VT_LAUNCHED();
+  return VT_OK;
+}
+
+int vt_wav_pcm16_header(void* dst, int sample_rate, const int64_t* n_samples_dev, int64_t n_samples_host, void* stream_v) {
+  VT_REQUIRE(dst != nullptr, "vt_wav_pcm16_header: dst is NULL");
+  VT_REQUIRE(sample_rate > 0 && n_samples_host >= 0 && n_samples_host < (1LL << 31) - 64, "vt_wav_pcm16_header: bad sample rate / length");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
+  k_wav_header<<<1, 32, 0, st>>>(reinterpret_cast<unsigned char*>(dst), sample_rate,
+                                 reinterpret_cast<const long long*>(n_samples_dev), (long long)n_samples_host);
   VT_LAUNCHED();
   return VT_OK;
 }

@@ -252,6 +252,36 @@ class VocoderPipeline:
             torch.cuda.current_stream().synchronize()
         return JobResult(self._host_out[:n].numpy(), n, res.segments, edit=res.edit, raw=res.raw, raw_samples=res.raw_samples)
 
+    def run_wav(self, mel_host, T, out_path, *, seed: int = 0, max_frames: Optional[int] = None) -> JobResult:
+        """``run`` that leaves the finished job on disk as a PCM_16 WAV (what run_tts_pipeline / apply_minimal_edit
+        write: tts_pipeline.py:409, audio_edit.py:70).  The file image - RIFF header included, with the data-dependent
+        trimmed length taken from device memory - is assembled on the GPU and crosses PCIe once."""
+        torch = _torch()
+        if not self.opts["out_pcm16"]:
+            raise ValueError("run_wav needs a pipeline built with out_pcm16=True")
+        T = np.ascontiguousarray(T, dtype=np.int32)
+        total_T = int(T.astype(np.int64).sum())
+        src = torch.as_tensor(mel_host, dtype=torch.float32).reshape(total_T, N_MEL)
+        with torch.cuda.device(self.voc.device):
+            cap = self.out_capacity(T)
+            if getattr(self, "_img", None) is None or self._img.capacity < cap:
+                self._img = _post.WavImage(cap, self.voc.device)
+            hin = self.pinned_input(total_T)
+            if src.data_ptr() != hin.data_ptr():
+                hin.copy_(src)
+            dev = self._dev_in[: src.numel()].view(total_T, N_MEL)
+            dev.copy_(hin, non_blocking=True)
+            saved, self._out = self._out, self._img.samples
+            try:
+                res = self.run_device(dev, T, seed=seed, read_back=False, max_frames=max_frames)
+            finally:
+                self._out = saved
+            r = self._last_post
+            self._img.finish(self.sr, total_dev=r.total_dev)
+            total = int(r.total_dev.item())
+            self._img.to_file(out_path, total)
+        return JobResult(None, total, None, raw=res.raw, raw_samples=res.raw_samples)
+
     # ---- pipelined serving loop: submit(job k+1) is enqueued while job k's audio is still crossing PCIe
     def submit(self, mel_host, T, *, seed: int = 0) -> int:
         """Enqueue one job (pinned host mels -> device -> HiFT -> post) without waiting for it and start the

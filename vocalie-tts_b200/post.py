@@ -151,6 +151,52 @@ def post_process_device(audio, seg_off, params: PostParams, *, out=None, range_o
         return PostResult(out, int(tot.item()), res_h, res, tot)
 
 
+# ------------------------------------------------------------------------- WAV file images on the device
+WAV_HEADER_BYTES = 44
+_WAV_SAMPLES_AT = 48      # header at bytes [4, 48): the samples then start 16-byte aligned for the vectorised writer
+
+
+class WavImage:
+    """A mono PCM_16 WAV file assembled in device memory: ``samples`` is the int16 view the post writer fills
+    (``out=``), ``finish`` writes the RIFF header in front of it on the device and ``to_file`` moves the finished image
+    to the host in one copy - no float32 bounce, no host-side header (reference wire format:
+    tts_backends/chatterbox_runner.py:152, backend/shared/tts_pipeline.py:409, backend/shared/audio_edit.py:70)."""
+
+    def __init__(self, capacity_samples: int, device=None):
+        torch = _torch()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.capacity = max(int(capacity_samples), 4)
+        self.buf = torch.empty(_WAV_SAMPLES_AT + 2 * self.capacity + 16, dtype=torch.uint8, device=self.device)
+        self.samples = self.buf[_WAV_SAMPLES_AT:_WAV_SAMPLES_AT + 2 * self.capacity].view(torch.int16)
+        self._host = None
+
+    def finish(self, sr: int, *, total_dev=None, total: Optional[int] = None) -> None:
+        """Write the header for ``total`` samples (host int) or ``total_dev`` (device int64[1], e.g. PostResult.total_dev)."""
+        torch = _torch()
+        with torch.cuda.device(self.device):
+            check(_lib.load_library().vt_wav_pcm16_header(int(self.buf.data_ptr()) + 4, int(sr), _ptr(total_dev),
+                                                          int(total or 0), _stream(torch)), "vt_wav_pcm16_header")
+
+    def to_host(self, total: int):
+        """Pinned host bytes of the finished file (header + ``total`` samples); synchronises the current stream."""
+        torch = _torch()
+        n = WAV_HEADER_BYTES + 2 * int(total)
+        if self._host is None or self._host.numel() < n:
+            self._host = torch.empty(max(n, WAV_HEADER_BYTES + 2 * self.capacity), dtype=torch.uint8).pin_memory()
+        with torch.cuda.device(self.device):
+            self._host[:n].copy_(self.buf[4:4 + n], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return self._host[:n]
+
+    def to_file(self, path, total: int) -> int:
+        path = Path(path)
+        path.parent.mkdir(parents=True, exist_ok=True)
+        data = self.to_host(total).numpy()
+        with open(path, "wb") as f:
+            f.write(memoryview(data))
+        return int(data.size)
+
+
 def stats_device(audio, seg_off, *, threshold: float = SILENCE_THRESHOLD):
     """One read pass over ``audio`` (float32 CUDA, segments ``seg_off``): returns device tensors
     ``first_last`` int64[n_seg, 2] (first / last sample with |x| > threshold, -1 / -1 if none) and ``peak``
