@@ -101,7 +101,40 @@ def make_state_dict(seed: int = 0, kind: str = "init") -> Dict[str, torch.Tensor
       l_linear, classifier; Snake alpha = 1; weight-norm g = ||v||.
     kind="unit": every conv ``normal(0, 1/sqrt(C_in*k))`` so activations stay O(1) and the
       operand rounding of the tensor-core path is actually exercised; Snake alpha ~ U(0.5, 2).
+    kind="stress": "unit" pushed to what a trained checkpoint may hold - Snake alpha log-uniform in [0.05, 30];
+      the trunk scaled so that activations reach |x| ~ 50 (conv_pre / source_downs x 40, conv_post / 40); and in every
+      ResBlock pair a quarter of conv1's output channels carry a weight-norm gain 10^-4.5 .. 10^-1 times smaller (rows
+      down to ~1e-6, fp16-subnormal) compensated by the matching input columns of conv2 - the function is (almost)
+      unchanged, the operand ranges are not.
     """
+    if kind == "stress":
+        sd = make_state_dict(seed, "unit")
+        g = torch.Generator().manual_seed(seed + 7919)
+        for k in list(sd):
+            if k.endswith(".alpha"):
+                sd[k] = torch.exp(torch.empty_like(sd[k]).uniform_(math.log(0.05), math.log(30.0), generator=g))
+        for k in ("conv_pre.parametrizations.weight.original0", "conv_pre.bias"):
+            sd[k] = sd[k] * 40.0
+        for i in range(3):
+            sd[f"source_downs.{i}.weight"] = sd[f"source_downs.{i}.weight"] * 40.0
+            sd[f"source_downs.{i}.bias"] = sd[f"source_downs.{i}.bias"] * 40.0
+        sd["conv_post.parametrizations.weight.original0"] = sd["conv_post.parametrizations.weight.original0"] / 40.0
+        for k in list(sd):
+            if ".convs1." in k and k.endswith("original0"):
+                pre = k[: -len(".parametrizations.weight.original0")]
+                c = sd[k].shape[0]
+                r = torch.ones(c)
+                idx = torch.rand(c, generator=g) < 0.25
+                r[idx] = 10 ** torch.empty(int(idx.sum())).uniform_(-4.5, -1.0, generator=g)
+                sd[k] = sd[k] * r.reshape(-1, 1, 1)
+                sd[pre + ".bias"] = sd[pre + ".bias"] * r
+                p2 = pre.replace("convs1", "convs2")
+                v = sd[p2 + ".parametrizations.weight.original1"]
+                v2 = v / r.reshape(1, -1, 1)
+                gk = p2 + ".parametrizations.weight.original0"
+                sd[gk] = sd[gk] * v2.flatten(1).norm(dim=1).reshape(-1, 1, 1) / v.flatten(1).norm(dim=1).reshape(-1, 1, 1)
+                sd[p2 + ".parametrizations.weight.original1"] = v2
+        return sd
     g = torch.Generator().manual_seed(seed)
     sd: Dict[str, torch.Tensor] = {}
 

@@ -174,7 +174,7 @@ k_convT_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ide
       for (int h = 0; h < NH; ++h) {
         const int seq = it * NH + h, buf = seq & 1;
         const int co = h * 128 + quarter * 32 + lane;
-        const float bias = a.bias[co];
+        const float bias = a.bias[co], wsc = a.wscale[co];
         float al[NACT > 0 ? NACT : 1], ia[NACT > 0 ? NACT : 1];
 #pragma unroll
         for (int s = 0; s < NACT; ++s) {
@@ -228,7 +228,7 @@ k_convT_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ide
             for (int q = 0; q < 16; ++q) {
               const int row = col0 + hh * 16 + q;
               if (row < tile.n) {
-                float y = __uint_as_float(v[q]) + bias;
+                float y = fmaf(__uint_as_float(v[q]), wsc, bias);
                 if constexpr (kLoads) y += x[hh * 16 + q];
                 const long long idx = obase + (long long)row * C;
                 if constexpr ((EM & EM_OUT) != 0) {

@@ -136,6 +136,30 @@ int dev_upload(vt_hift* h, const void* src, size_t bytes, void** out) {
   return VT_OK;
 }
 
+// Per-output-channel power-of-two scaling of the tensor-core weight images.  fp16 operands lose precision below
+// 6.1e-5 (subnormals) and a trained checkpoint's weight-normed rows can sit orders of magnitude apart (w = g v / ||v||
+// with a per-row gain g), so row c of the packed weights holds s_c * w with s_c = 2^-e the power of two that brings
+// max|row| into [0.5, 1): exact in every format, the accumulators come out as s_c * (W a) and the epilogues undo it for
+// free in the FMA that adds the bias (ConvArgs::wscale = 1 / s_c).  `w` is [k][cin_pad][ncol] and is scaled IN PLACE
+// (callers pass a copy: the fp32 CUDA-core path keeps the unscaled weights).
+int scale_weight_rows(vt_hift* h, ConvLayer& L, std::vector<float>& w, int k, int cin_pad, int ncol) {
+  std::vector<float> inv(ncol, 1.0f);
+  for (int co = 0; co < ncol; ++co) {
+    float m = 0.0f;
+    for (int j = 0; j < k; ++j)
+      for (int ci = 0; ci < cin_pad; ++ci) m = std::max(m, std::fabs(w[((size_t)j * cin_pad + ci) * ncol + co]));
+    if (!(m > 0.0f) || !std::isfinite(m)) continue;
+    int e = 0;
+    std::frexp(m, &e);                       // m = f * 2^e, f in [0.5, 1)
+    e = std::max(-100, std::min(e, 100));
+    const float s = std::ldexp(1.0f, -e);
+    inv[co] = std::ldexp(1.0f, e);
+    for (int j = 0; j < k; ++j)
+      for (int ci = 0; ci < cin_pad; ++ci) w[((size_t)j * cin_pad + ci) * ncol + co] *= s;
+  }
+  return dev_upload(h, inv.data(), inv.size() * 4, (void**)&L.wscale);
+}
+
 // conv weight [cout][cin][k] -> [k][cin_pad][cout_pad]
 // K-blocked tensor-core packing of a layer (vt_gemm_tc.cu).  `w` is [k][cin_pad][cout].
 //   GEMM_CONV  : one K block per (tap, 64-channel block) of an operand buffer with `op_ld` channels
@@ -200,8 +224,11 @@ int pack_conv(vt_hift* h, ConvLayer& L, const std::map<std::string, HostTensor>&
   if (rc) return rc;
   rc = dev_upload(h, b.data(), b.size() * 4, (void**)&L.bias);
   if (rc) return rc;
-  if (h->use_tc && gemm_mode != GEMM_NONE) return pack_gemm(h, L, w, cin, cin_pad, gemm_mode, op_ld);
-  if (h->use_tc && conv_tc_supported(L)) {
+  if (!h->use_tc) return VT_OK;
+  rc = scale_weight_rows(h, L, w, k, cin_pad, cout_pad);       // w is a local copy: the upload above kept the plain weights
+  if (rc) return rc;
+  if (gemm_mode != GEMM_NONE) return pack_gemm(h, L, w, cin, cin_pad, gemm_mode, op_ld);
+  if (conv_tc_supported(L)) {
     rc = pack_conv_tc(L, w, h->act_elem, h->allocs);
     if (rc) return rc;
     return pack_pair64(L, h->allocs);
@@ -244,7 +271,10 @@ int pack_convT(vt_hift* h, ConvLayer& L, const std::map<std::string, HostTensor>
   if (rc) return rc;
   rc = dev_upload(h, b.data(), b.size() * 4, (void**)&L.bias);
   if (rc) return rc;
-  if (h->use_tc && conv_tc_supported(L)) return pack_conv_tc(L, w, h->act_elem, h->allocs);
+  if (!h->use_tc) return VT_OK;
+  rc = scale_weight_rows(h, L, w, 3, cin, cN);
+  if (rc) return rc;
+  if (conv_tc_supported(L)) return pack_conv_tc(L, w, h->act_elem, h->allocs);
   return VT_OK;
 }
 
@@ -440,7 +470,7 @@ static int mark(vt_hift* h, const char* name, cudaStream_t st) {
 
 static ConvArgs base_args(const ConvLayer& L, const Plan& P, const Plan::Seg& seg) {
   ConvArgs a{};
-  a.w = L.w; a.bias = L.bias;
+  a.w = L.w; a.bias = L.bias; a.wscale = L.wscale;
   a.cin = L.cin; a.cout = L.cout; a.k = L.k; a.dil = L.dil; a.stride = L.stride; a.pad = L.pad;
   a.in_ld = L.cin;
   a.pro_act = ACT_NONE; a.pro_slope = 0.f;

@@ -62,6 +62,8 @@ struct ConvArgs {
   int in_ld;
   const float* w;       // [k][cin][cout] fp32
   const float* bias;    // [cout]
+  const float* wscale;  // [cout] tensor-core paths: accumulators hold s_c * (W a) with the exact power of two s_c the host
+                        // folded into row c of the packed weights; wscale[c] = 1 / s_c, applied as fma(acc, wscale, bias)
   int cin, cout, k, dil, stride, pad;
   int pro_act;          // prologue activation applied to the input on load
   float pro_slope;
@@ -98,6 +100,7 @@ struct ConvLayer {
   int out_mul = 1, phase_c = 0;     // transposed convs run as a k'=3 conv with cout = s*C_out
   float* w = nullptr;               // device [k][cin][cout] fp32
   float* bias = nullptr;            // device [cout]
+  float* wscale = nullptr;          // device [cout]: 1 / (power-of-two row scale of the tensor-core weight images)
   void* w_tp = nullptr;             // device, tap-pair image for the C = 64 pair kernel (vt_pair64_tc.cu)
   void* w_tc = nullptr;             // device, tensor-core operand packing (vt_conv_tc.cu)
   unsigned long long tap_skip = 0;  // all-zero (column tile, tap) pairs of a phase-decomposed transposed conv

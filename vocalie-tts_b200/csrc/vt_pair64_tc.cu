@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(kP64Warps * 32, 1) k_pair64_tc(const ConvArgs 
     const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
     const int col_lo = 64 * tq + (hi ? 4 : 0);                            // first column this thread finalises
     const float b1 = prm[2 * C + c], al2 = prm[3 * C + c], ia2 = prm[4 * C + c];
-    const float b2 = a.bias[c];
+    const float b2 = a.bias[c], ws1 = p.wscale1[c], ws2 = a.wscale[c];   // inverse power-of-two weight-row scales
     const bool accum = kAccum && a.out_accum;
     const float inv = 1.0f / a.out_scale;
     const uint32_t a2_off = (uint32_t)((c & 7) * 2);
@@ -433,7 +433,7 @@ __global__ void __launch_bounds__(kP64Warps * 32, 1) k_pair64_tc(const ConvArgs 
             combine(v1[b & 1], v2[b & 1], sum);
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
-              float y = snake_f(sum[jj] + b1, al2, ia2);
+              float y = snake_f(fmaf(sum[jj], ws1, b1), al2, ia2);
               if (!inside) {
                 const int pseq = p0 + (hi ? 4 : 0) + 8 * b + jj;
                 if (pseq < 0 || pseq >= tile.out_len) y = 0.0f;
@@ -473,7 +473,7 @@ __global__ void __launch_bounds__(kP64Warps * 32, 1) k_pair64_tc(const ConvArgs 
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
               if (full || 8 * b + jj < nrel) {
-                const float o = (sum[jj] + b2 + xr[4 * b + jj]) * a.out_scale;
+                const float o = fmaf(sum[jj], ws2, b2 + xr[4 * b + jj]) * a.out_scale;
                 if (!(a.dbg & 64)) op[(8 * b + jj) * C] = o;
                 if constexpr (kOact) {
                   const float sl = a.act[0].slope;
@@ -582,7 +582,8 @@ int launch_pair64_tc(const ConvArgs& a_in, const ConvLayer& c1, const ConvLayer&
   a.cout = c2.cout; a.phase_c = c2.cout; a.out_mul = 1; a.out_shift = 0; a.dup_row2 = 0;
   PairArgs p{};
   p.x_in = a.res1;
-  p.alpha1 = alpha1; p.alpha2 = alpha2; p.bias1 = c1.bias;
+  p.alpha1 = alpha1; p.alpha2 = alpha2; p.bias1 = c1.bias; p.wscale1 = c1.wscale;
+  a.wscale = c2.wscale;
   p.w1 = reinterpret_cast<const uint8_t*>(c1.w_tp);
   p.w2 = reinterpret_cast<const uint8_t*>(c2.w_tp);
   p.k = c1.k; p.dil = c1.dil;

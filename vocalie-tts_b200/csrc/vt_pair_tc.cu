@@ -128,9 +128,9 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
   uint64_t* w_full = d2i_full + NBUF;
   uint64_t* w_empty = w_full + W_ST;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_empty + W_ST);
-  float* prm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(tmem_slot) + 16);   // al1 | ia1 | b1 | al2 | ia2
+  float* prm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(tmem_slot) + 16);   // al1 | ia1 | b1 | al2 | ia2 | ws1
   // fin staging (32 x kStageLd floats per warp): its own region, or the idle A2 tile in combined mode
-  float* stage_all = kCombined ? reinterpret_cast<float*>(sA2) : prm + 5 * C;
+  float* stage_all = kCombined ? reinterpret_cast<float*>(sA2) : prm + 6 * C;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -149,6 +149,7 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
     const float a1 = p.alpha1[c], a2 = p.alpha2[c];
     prm[c] = a1; prm[C + c] = __fdividef(1.0f, a1 + 1e-9f); prm[2 * C + c] = p.bias1[c];
     prm[3 * C + c] = a2; prm[4 * C + c] = __fdividef(1.0f, a2 + 1e-9f);
+    prm[5 * C + c] = p.wscale1[c];
   }
   if (warp == W_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
@@ -396,7 +397,7 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
     const int c = quarter * 32 + lane;                                   // this thread's channel
     const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
     if (!is_fin) {
-      const float b1 = prm[2 * C + c], al2 = prm[3 * C + c], ia2 = prm[4 * C + c];
+      const float b1 = prm[2 * C + c], al2 = prm[3 * C + c], ia2 = prm[4 * C + c], ws1 = prm[5 * C + c];
       // A2 element (row r, channel c): 64-channel block, 16-byte chunk XOR-swizzled by the row, 2 bytes inside
       const uint32_t coff = (uint32_t)(c >> 6) * (uint32_t)(kPairRA2 * 128) + (uint32_t)((c & 7) * 2);
       const uint32_t chunk = (uint32_t)((c & 63) >> 3);
@@ -418,7 +419,7 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
             const int row = col0 + t;                                      // conv1 output row of the tile = A2 row
             const int pseq = tile.q0 - H2 + row;
             const bool valid = pseq >= 0 && pseq < tile.out_len;          // warp-uniform
-            const float y = valid ? snake_f(__uint_as_float(v[t]) + b1, al2, ia2) : 0.0f;
+            const float y = valid ? snake_f(fmaf(__uint_as_float(v[t]), ws1, b1), al2, ia2) : 0.0f;
             const uint32_t addr = dst0 + (uint32_t)row * 128u + ((chunk ^ (uint32_t)(row & 7)) << 4);
             asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(to_op_bits<ActT>(y)) : "memory");
           }
@@ -431,7 +432,7 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
       }
     } else {
       constexpr bool kRes2 = (EM & EM_RES2) != 0, kAccum = (EM & EM_ACCUM) != 0;
-      const float b2 = a.bias[c];
+      const float b2 = a.bias[c], ws2 = a.wscale[c];
       const bool accum = kAccum && a.out_accum;
       const float inv = 1.0f / a.out_scale;
       const uint32_t d2 = tmem_base + lane_sel + (uint32_t)ACC_COLS;
@@ -482,7 +483,7 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
               for (int t = 0; t < 16; ++t) {
                 const int row = col0 + hh * 16 + t;
                 if (row < tile.n) {
-                  const float o = (__uint_as_float(v[t]) + b2 + x[hh * 16 + t]) * a.out_scale;
+                  const float o = fmaf(__uint_as_float(v[t]), ws2, b2 + x[hh * 16 + t]) * a.out_scale;
                   const long long idx = obase + (long long)row * C;
                   if (!(a.dbg & 64)) a.out[idx] = o;
                   if constexpr ((EM & EM_OACT) != 0) {
@@ -541,6 +542,9 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
       int mb, c0, nvalid; long long idx0;
       blk_geom(tl, blk, mb, c0, idx0, nvalid);
       const float4 bias = *reinterpret_cast<const float4*>(a.bias + c0 + sub * 4);
+      // conv2 accumulates s_c * (W2 a) on top of the preload, so the preload is s_c * (x + b2 + ...): exact (power of two)
+      const float4 wsq = *reinterpret_cast<const float4*>(a.wscale + c0 + sub * 4);
+      const float4 sc = make_float4(__frcp_rn(wsq.x), __frcp_rn(wsq.y), __frcp_rn(wsq.z), __frcp_rn(wsq.w));
       const bool accum = kAccum && a.out_accum;
       const float inv = 1.0f / a.out_scale;
 #pragma unroll
@@ -557,6 +561,7 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
             const float4 pv = *reinterpret_cast<const float4*>(a.out + idx);
             t.x = fmaf(pv.x, inv, t.x); t.y = fmaf(pv.y, inv, t.y); t.z = fmaf(pv.z, inv, t.z); t.w = fmaf(pv.w, inv, t.w);
           }
+          t.x *= sc.x; t.y *= sc.y; t.z *= sc.z; t.w *= sc.w;
         }
         *reinterpret_cast<float4*>(stage + (q * 4 + rsub) * kStageLd + sub * 4) = t;
       }
@@ -589,12 +594,14 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
       }
       __syncwarp();
       if (!(a.dbg & 8)) {
+        const float4 wsq = *reinterpret_cast<const float4*>(a.wscale + c0 + sub * 4);
+        const float4 osc = make_float4(wsq.x * a.out_scale, wsq.y * a.out_scale, wsq.z * a.out_scale, wsq.w * a.out_scale);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           if (4 * q >= nvalid) continue;
           const long long idx = idx0 + (long long)q * 4 * C;
           const float4 acc = *reinterpret_cast<const float4*>(stage + (q * 4 + rsub) * kStageLd + sub * 4);
-          const float4 o = make_float4(acc.x * a.out_scale, acc.y * a.out_scale, acc.z * a.out_scale, acc.w * a.out_scale);
+          const float4 o = make_float4(acc.x * osc.x, acc.y * osc.y, acc.z * osc.z, acc.w * osc.w);
           if (!(a.dbg & 64)) *reinterpret_cast<float4*>(a.out + idx) = o;
           if constexpr ((EM & EM_OACT) != 0) {
             const float sl = a.act[0].slope;
@@ -639,6 +646,7 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
       __syncwarp();
       if (!(a.dbg & 8)) {
         const float4 bias = *reinterpret_cast<const float4*>(a.bias + c0 + sub * 4);
+        const float4 wsq = *reinterpret_cast<const float4*>(a.wscale + c0 + sub * 4);
         const bool accum = kAccum && a.out_accum;
         const float inv = 1.0f / a.out_scale;
 #pragma unroll
@@ -646,8 +654,8 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
           if (4 * q >= nvalid) continue;
           const long long idx = idx0 + (long long)q * 4 * C;
           const float4 acc = *reinterpret_cast<const float4*>(stage + (q * 4 + rsub) * kStageLd + sub * 4);
-          float4 t = make_float4(acc.x + bias.x + pr[q].x, acc.y + bias.y + pr[q].y, acc.z + bias.z + pr[q].z,
-                                 acc.w + bias.w + pr[q].w);
+          float4 t = make_float4(fmaf(acc.x, wsq.x, bias.x + pr[q].x), fmaf(acc.y, wsq.y, bias.y + pr[q].y),
+                                 fmaf(acc.z, wsq.z, bias.z + pr[q].z), fmaf(acc.w, wsq.w, bias.w + pr[q].w));
           if constexpr (kRes2) {
             const float4 r2 = ldg_f4(a.res2 + idx);
             t.x += r2.x; t.y += r2.y; t.z += r2.z; t.w += r2.w;
@@ -718,10 +726,11 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
               const float4 bb = *reinterpret_cast<const float4*>(prm + 2 * C + c);
               const float4 aa = *reinterpret_cast<const float4*>(prm + 3 * C + c);
               const float4 ii = *reinterpret_cast<const float4*>(prm + 4 * C + c);
-              y[hh * 4 + 0] = snake_f(__uint_as_float(v[g * 8 + hh * 4 + 0]) + bb.x, aa.x, ii.x);
-              y[hh * 4 + 1] = snake_f(__uint_as_float(v[g * 8 + hh * 4 + 1]) + bb.y, aa.y, ii.y);
-              y[hh * 4 + 2] = snake_f(__uint_as_float(v[g * 8 + hh * 4 + 2]) + bb.z, aa.z, ii.z);
-              y[hh * 4 + 3] = snake_f(__uint_as_float(v[g * 8 + hh * 4 + 3]) + bb.w, aa.w, ii.w);
+              const float4 ww = *reinterpret_cast<const float4*>(prm + 5 * C + c);
+              y[hh * 4 + 0] = snake_f(fmaf(__uint_as_float(v[g * 8 + hh * 4 + 0]), ww.x, bb.x), aa.x, ii.x);
+              y[hh * 4 + 1] = snake_f(fmaf(__uint_as_float(v[g * 8 + hh * 4 + 1]), ww.y, bb.y), aa.y, ii.y);
+              y[hh * 4 + 2] = snake_f(fmaf(__uint_as_float(v[g * 8 + hh * 4 + 2]), ww.z, bb.z), aa.z, ii.z);
+              y[hh * 4 + 3] = snake_f(fmaf(__uint_as_float(v[g * 8 + hh * 4 + 3]), ww.w, bb.w), aa.w, ii.w);
             }
             uint4 pk = Pack8<ActT>::pack(y);
             if (!valid) pk = make_uint4(0u, 0u, 0u, 0u);
@@ -783,7 +792,7 @@ int launch_pair_em(const ConvArgs& a, const PairArgs& p, uint32_t idesc, int gri
   constexpr int CB = C / 64;
   using PC = PairCfg<C, NBUF, NEPI, NPROD, TR>;
   constexpr int smem = CB * (NA1 * kPairRA1 + NA2 * kPairRA2) * 128 + W_ST * C * 128 + NSLAB * 8192 +
-                       (2 * NA1 + 2 * NA2 + 2 * NSLAB + 4 * NBUF + 2 * W_ST) * 8 + 16 + 5 * C * 4 +
+                       (2 * NA1 + 2 * NA2 + 2 * NSLAB + 4 * NBUF + 2 * W_ST) * 8 + 16 + 6 * C * 4 +
                        ((PC::kCombined || TR) ? 0 : NEPI * 32 * kStageLd * 4);
   static_assert(smem <= 232448, "shared memory budget exceeded");
   static_assert(!PC::kCombined || NEPI * 32 * kStageLd * 4 <= CB * kPairRA2 * 128, "fin staging must fit the A2 tile");
@@ -866,7 +875,8 @@ int launch_pair_tc(const ConvArgs& a_in, const ConvLayer& c1, const ConvLayer& c
   a.cout = c2.cout; a.phase_c = c2.cout; a.out_mul = 1; a.out_shift = 0; a.dup_row2 = 0;
   PairArgs p{};
   p.x_in = a.res1;
-  p.alpha1 = alpha1; p.alpha2 = alpha2; p.bias1 = c1.bias;
+  p.alpha1 = alpha1; p.alpha2 = alpha2; p.bias1 = c1.bias; p.wscale1 = c1.wscale;
+  a.wscale = c2.wscale;
   p.w1 = reinterpret_cast<const uint8_t*>(c1.w_tc);
   p.w2 = reinterpret_cast<const uint8_t*>(c2.w_tc);
   p.k = c1.k; p.dil = c1.dil;

@@ -12,6 +12,7 @@ struct PairArgs {
   const float* alpha1;    // Snake before conv1
   const float* alpha2;    // Snake before conv2
   const float* bias1;     // conv1 bias
+  const float* wscale1;   // conv1 inverse weight-row scales (ConvArgs::wscale holds conv2's)
   const uint8_t* w1;      // conv1 / conv2 weights: pack_conv_tc images (chunk = (tap, 64-channel block)), or the
   const uint8_t* w2;      // tap-pair images of pack_pair64
   int k, dil;
@@ -306,6 +307,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const ConvTile&
     const int cg = nt * NT + c0 + sub * 4;             // GEMM column of this lane's float4
     const int phase = cg / ld, co = cg - phase * ld;   // transposed convs: column -> (output phase, channel)
     const float4 bias = *reinterpret_cast<const float4*>(a.bias + cg);
+    const float4 wsc = *reinterpret_cast<const float4*>(a.wscale + cg);
     float4 al[NACT > 0 ? NACT : 1], ia[NACT > 0 ? NACT : 1];
 #pragma unroll
     for (int s = 0; s < NACT; ++s) {
@@ -350,7 +352,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const ConvTile&
       const long long step = step0 + 4LL * i * a.out_mul;
       const long long idx = idx0 + i * istride;
       const float4 acc = *reinterpret_cast<const float4*>(stage + r * kStageLd + sub * 4);
-      float x[4] = {acc.x + bias.x, acc.y + bias.y, acc.z + bias.z, acc.w + bias.w};
+      float x[4] = {fmaf(acc.x, wsc.x, bias.x), fmaf(acc.y, wsc.y, bias.y), fmaf(acc.z, wsc.z, bias.z), fmaf(acc.w, wsc.w, bias.w)};
       if constexpr (kLoads) {
         x[0] += pre[i].x; x[1] += pre[i].y; x[2] += pre[i].z; x[3] += pre[i].w;
       }
