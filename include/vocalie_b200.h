@@ -148,6 +148,16 @@ int vt_pcm16_decode(const int16_t* in, float* out, int64_t n, void* stream);
 int vt_wav_pcm16_header(void* dst /* device, 44 bytes */, int sample_rate, const int64_t* n_samples_dev,
                         int64_t n_samples_host, void* stream);
 
+/* _resample_audio (backend/shared/tts_pipeline.py:100-111 -> librosa.resample), segment-batched rational-ratio polyphase
+ * resampler: segment i of `in` (seg_off_in) -> segment i of `out` (seg_off_out, lengths by librosa's rule
+ * int(ceil(n * target_sr / orig_sr)), computed by the caller), up / down = target_sr / orig_sr reduced.
+ * table: device float [up][ntaps] phase table (ntaps odd), y[m] = sum_j table[(m*down) % up][j] * x[(m*down)/up + (ntaps-1)/2 - j].
+ * The filter itself is the caller's (vocalie-tts_b200/post.py builds a 120 dB Kaiser sinc); sample values are NOT pinned
+ * to soxr, which the reference reaches through librosa and which is absent here (oracle/resample_oracle.py). */
+int vt_resample(const float* in, const int64_t* seg_off_in, const int64_t* seg_off_out, int n_seg,
+                int64_t max_out_len /* HOST */, int up, int down, const float* table, int ntaps, float* out,
+                void* stream);
+
 /* RMS helper the reference uses to validate clips (tts_backends/cosyvoice_backend.py:103,
  * tests/test_qwen3_runner.py:58): rms_out[i] = sqrt(mean(float64(x)^2)) over segment i, 0 for an empty
  * segment.  float64 accumulation in a fixed reduction order (deterministic; equal to numpy's pairwise

@@ -65,6 +65,7 @@ _SIGS = {
     "vt_hift_destroy": (None, [_P]),
     "vt_hift_workspace_bytes": (_I64, [_P, C.c_int, _I64, _I64]),
     "vt_hift_forward": (C.c_int, [_P, _P, C.POINTER(C.c_int32), C.c_int, _P, _P, _P, C.c_uint64, _P, _P, _I64, _P]),
+    "vt_resample": (C.c_int, [_P, _P, _P, C.c_int, _I64, C.c_int, C.c_int, _P, C.c_int, _P, _P]),
     "vt_rms": (C.c_int, [_P, _P, C.c_int, _P, _P, _I64, _P]),
     "vt_hift_set_profiling": (C.c_int, [_P, C.c_int]),
     "vt_hift_read_profile": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),

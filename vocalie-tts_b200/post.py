@@ -404,6 +404,89 @@ def apply_minimal_edit(raw_path: Path, output_path: Path, *, trim_enabled: bool,
     }
 
 
+# ------------------------------------------------------------------------- resampling
+RESAMPLE_ZEROS = 64        # zero crossings per side at the lower rate
+RESAMPLE_ATT_DB = 120.0    # Kaiser stop-band attenuation
+_resample_tables: dict = {}
+
+
+def resample_out_length(n: int, orig_sr: int, target_sr: int) -> int:
+    """librosa.resample's length rule (librosa/core/audio.py): ``int(np.ceil(n * (target_sr / orig_sr)))`` in float64 -
+    including its quirk (22 050 samples at 22 050 Hz -> 24 001 at 24 kHz, because the product is 24000.000000000004)."""
+    return int(np.ceil(int(n) * (float(target_sr) / orig_sr)))
+
+
+def _resample_table(torch, orig_sr: int, target_sr: int, device):
+    """Phase table of the Kaiser-windowed sinc (float64 design, fp32 table) - the numbers of oracle/resample_oracle.py
+    restated here: the product path does not import the oracle."""
+    import math
+    g = math.gcd(int(orig_sr), int(target_sr))
+    up, down = int(target_sr) // g, int(orig_sr) // g
+    key = (up, down, str(device))
+    if key not in _resample_tables:
+        r = max(up, down)
+        half = RESAMPLE_ZEROS * r
+        beta = 0.1102 * (RESAMPLE_ATT_DB - 8.7)
+        dw = (RESAMPLE_ATT_DB - 8.0) / (2.285 * (2 * half))
+        wc = math.pi / r - dw / 2.0
+        n = np.arange(-half, half + 1, dtype=np.float64)
+        h = (wc / math.pi) * np.sinc(wc / math.pi * n) * np.kaiser(2 * half + 1, beta)
+        h /= h.sum()
+        j0 = (half + up - 1) // up
+        tab = np.zeros((up, 2 * j0 + 1), dtype=np.float64)
+        idx = np.arange(up)[:, None] + (np.arange(-j0, j0 + 1) * up)[None, :]
+        ok = np.abs(idx) <= half
+        tab[ok] = up * h[(idx + half)[ok]]
+        _resample_tables[key] = (up, down, torch.from_numpy(np.ascontiguousarray(tab.astype(np.float32))).to(device))
+    return _resample_tables[key]
+
+
+def resample_device(audio, seg_off, orig_sr: int, target_sr: int):
+    """Resample every segment of a packed float32 CUDA buffer (segments ``seg_off``, host int64); returns the packed
+    output tensor and its int64 offsets (host) - segment i has ``resample_out_length(len_i)`` samples."""
+    torch = _torch()
+    lib = _lib.load_library()
+    if audio.dtype != torch.float32 or audio.dim() != 1 or not audio.is_cuda:
+        raise ValueError("audio must be a 1-D float32 CUDA tensor")
+    seg_np = np.ascontiguousarray(seg_off, dtype=np.int64)
+    if seg_np.ndim != 1 or seg_np.size < 1 or np.any(np.diff(seg_np) < 0) or int(seg_np[-1]) > audio.numel():
+        raise ValueError("seg_off must be non-decreasing and inside the audio buffer")
+    lens = np.diff(seg_np)
+    out_off = np.concatenate([[0], np.cumsum([resample_out_length(int(n), orig_sr, target_sr) for n in lens])]).astype(np.int64)
+    dev = audio.device
+    with torch.cuda.device(dev):
+        up, down, tab = _resample_table(torch, orig_sr, target_sr, dev)
+        out = torch.empty(max(int(out_off[-1]), 4), dtype=torch.float32, device=dev)
+        if len(lens):
+            src = audio.contiguous()
+            off_in_dev, off_out_dev = torch.from_numpy(seg_np).to(dev), torch.from_numpy(out_off).to(dev)   # named: they must outlive the call
+            check(lib.vt_resample(_ptr(src), _ptr(off_in_dev), _ptr(off_out_dev), len(lens), int(np.diff(out_off).max()),
+                                  up, down, _ptr(tab), int(tab.shape[1]), _ptr(out), _stream(torch)), "vt_resample")
+    return out, out_off
+
+
+def _resample_audio(audio: np.ndarray, orig_sr: int, target_sr: int) -> np.ndarray:
+    """GPU ``_resample_audio`` (reference tts_pipeline.py:100-111): same signature and shapes - 1-D mono, or
+    ``[n, channels]`` resampled per channel and cut to the shortest - with the output length of ``librosa.resample``.
+    The impulse response is this package's 120 dB Kaiser sinc, not soxr's (absent here): values are not bit-pinned."""
+    if orig_sr == target_sr:
+        return audio
+    torch = _torch()
+    a = np.asarray(audio, dtype=np.float32)
+    if a.ndim == 1:
+        if a.size == 0:
+            return np.zeros(0, dtype=np.float32)
+        out, off = resample_device(torch.from_numpy(np.ascontiguousarray(a)).cuda(), [0, a.size], orig_sr, target_sr)
+        return out[: int(off[-1])].cpu().numpy()
+    n, ch = a.shape[0], a.shape[1]
+    if ch == 0 or n == 0:
+        return np.zeros(0, dtype=np.float32)                                   # tts_pipeline.py:108-110
+    flat = np.ascontiguousarray(a.T).reshape(-1)                               # channel-major: one segment per channel
+    out, off = resample_device(torch.from_numpy(flat).cuda(), np.arange(ch + 1, dtype=np.int64) * n, orig_sr, target_sr)
+    y = out[: int(off[-1])].cpu().numpy().reshape(ch, -1)
+    return np.ascontiguousarray(y.T)
+
+
 def pcm16_encode(audio: np.ndarray) -> np.ndarray:
     """float32 -> PCM_16 codes on the GPU (``lrintf(x * 32767)``, the libsndfile default the
     reference writes with: tts_backends/chatterbox_runner.py:152, tts_pipeline.py:409)."""
