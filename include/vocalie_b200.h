@@ -187,6 +187,26 @@ typedef struct vt_tensor {
 
 int  vt_hift_create(const vt_tensor* tensors /* HOST */, int n_tensors, int operand_dtype,
                     vt_hift** out_handle);
+
+/* The constructor arguments of upstream HiFTGenerator that differ between its users (the module class is one and the
+ * same: Chatterbox's hifigan.py is CosyVoice's cosyvoice/hifigan/generator.py).  NULL / vt_hift_create = Chatterbox S3Gen
+ * (24 kHz, rates 8/5/3, kernels 16/11/7, source ResBlock kernels 7/7/11, trim_fade tail).  The second consumer behind the
+ * reference's plugin interface is CosyVoice (tts_backends/cosyvoice_runner.py:75-131, default rate 22 050 Hz :84,131):
+ * CosyVoice-300M = {22050, 2, {8, 8}, {16, 16}, {7, 11}, 0}.  Channels are 512 >> stage, n_fft 16 / hop 4, ResBlock
+ * kernels 3/7/11 with dilations 1/3/5, nine harmonics - as in every published instantiation of this generator.
+ * Layers whose shape has a tcgen05 instance run on it, the others on the fp32 CUDA-core kernels. */
+typedef struct vt_hift_config {
+  int32_t sampling_rate;
+  int32_t n_upsamples;                       /* 2 or 3 */
+  int32_t upsample_rates[4];
+  int32_t upsample_kernel_sizes[4];
+  int32_t source_resblock_kernel_sizes[4];   /* 3, 7 or 11 each */
+  int32_t trim_fade;                         /* 1: S3Token2Wav tail (first sr/50 samples zeroed, next sr/50 faded in) */
+} vt_hift_config;
+int  vt_hift_create_ex(const vt_tensor* tensors /* HOST */, int n_tensors, int operand_dtype,
+                       const vt_hift_config* config /* HOST, nullable */, vt_hift** out_handle);
+int  vt_hift_samples_per_frame(const vt_hift* h);   /* prod(upsample_rates) * hop: 480 (Chatterbox), 256 (CosyVoice-300M) */
+int  vt_hift_sampling_rate(const vt_hift* h);
 void vt_hift_destroy(vt_hift* h);
 
 /* Bytes of device workspace vt_hift_forward needs for a batch of B sequences whose mel lengths
@@ -199,7 +219,8 @@ int64_t vt_hift_workspace_bytes(const vt_hift* h, int B, int64_t total_T, int64_
  *   f0       : float32 [sum_T] Hz or NULL (run the ConvRNNF0Predictor)
  *   phase_vec: float32 [B, 9] or NULL;  noise: float32 [9, L] per sequence packed at 9*wav_off[b]
  *              or NULL.  NULL randomness -> counter-based generator seeded with `seed`.
- *   wav      : float32 out, sequence b at wav_off[b] = 480 * mel_off[b], length 480*T[b].
+ *   wav      : float32 out, sequence b at wav_off[b] = spf * mel_off[b], length spf*T[b]
+ *              (spf = vt_hift_samples_per_frame: 480 for Chatterbox).
  * Sequences are packed in order: mel_off[b] = sum_{i<b} T[i]. */
 int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T /* HOST */, int B,
                     const float* f0, const float* phase_vec, const float* noise, uint64_t seed,

@@ -60,39 +60,74 @@ UNIT_BRANCH_GAIN = 0.5
 UNIT_POST_GAIN = 0.25
 
 
+@dataclass(frozen=True)
+class HiftConfig:
+    """Constructor arguments of upstream ``HiFTGenerator`` that differ between its users (the module class is the same:
+    Chatterbox's hifigan.py is CosyVoice's cosyvoice/hifigan/generator.py)."""
+    name: str = "chatterbox_s3gen"
+    sampling_rate: int = SR
+    upsample_rates: tuple = UP_RATES
+    upsample_kernel_sizes: tuple = UP_KERNELS
+    source_resblock_kernel_sizes: tuple = SRC_RB_KERNELS
+    trim_fade: bool = True            # S3Token2Wav.inference tail (Chatterbox only)
+
+    @property
+    def n_levels(self) -> int:
+        return len(self.upsample_rates)
+
+    @property
+    def samples_per_frame(self) -> int:
+        return int(np.prod(self.upsample_rates)) * HOP
+
+    def source_downs(self):
+        """(k, stride, pad) per level - HiFTGenerator.__init__: downsample_rates = [1] + upsample_rates[::-1][:-1],
+        cumulative products reversed; u == 1 -> Conv1d(k=1) else Conv1d(k=2u, stride=u, padding=u//2)."""
+        rates = [1] + list(self.upsample_rates[::-1][:-1])
+        cum = list(np.cumprod(rates))[::-1]
+        return [(1, 1, 0) if u == 1 else (int(2 * u), int(u), int(u // 2)) for u in cum]
+
+
+CHATTERBOX = HiftConfig()
+# CosyVoice-300M (v1) HiFT: cosyvoice.yaml `hift:` block - 22.05 kHz, two upsampling stages, hop 256; the default rate of the
+# reference's CosyVoice runner (tts_backends/cosyvoice_runner.py:84,131)
+COSYVOICE_300M = HiftConfig(name="cosyvoice_300m", sampling_rate=22050, upsample_rates=(8, 8), upsample_kernel_sizes=(16, 16),
+                            source_resblock_kernel_sizes=(7, 11), trim_fade=False)
+CONFIGS = {c.name: c for c in (CHATTERBOX, COSYVOICE_300M)}
+
+
 # ----------------------------------------------------------------------------- weights
 def _wn_names(prefix):
     return prefix + ".parametrizations.weight.original0", prefix + ".parametrizations.weight.original1"
 
 
-def layer_table():
+def layer_table(cfg: "HiftConfig" = None):
     """(name, kind, C_in, C_out, k, weight_normed) for every conv, in upstream module naming."""
+    cfg = cfg or CHATTERBOX
     t = []
     t.append(("conv_pre", "conv", N_MEL, BASE_CH, 7, True))
-    for i, (u, k) in enumerate(zip(UP_RATES, UP_KERNELS)):
+    for i, (u, k) in enumerate(zip(cfg.upsample_rates, cfg.upsample_kernel_sizes)):
         t.append((f"ups.{i}", "convT", BASE_CH >> i, BASE_CH >> (i + 1), k, True))
-    down = [(30, 15, 7), (6, 3, 1), (1, 1, 0)]
-    for i, (k, s, p) in enumerate(down):
+    for i, (k, s, p) in enumerate(cfg.source_downs()):
         t.append((f"source_downs.{i}", "conv", N_FFT + 2, BASE_CH >> (i + 1), k, False))
-    for i in range(3):
+    for i in range(cfg.n_levels):
         ch = BASE_CH >> (i + 1)
         for j in range(3):
-            t.append((f"source_resblocks.{i}.convs1.{j}", "conv", ch, ch, SRC_RB_KERNELS[i], True))
-            t.append((f"source_resblocks.{i}.convs2.{j}", "conv", ch, ch, SRC_RB_KERNELS[i], True))
-    for i in range(3):
+            t.append((f"source_resblocks.{i}.convs1.{j}", "conv", ch, ch, cfg.source_resblock_kernel_sizes[i], True))
+            t.append((f"source_resblocks.{i}.convs2.{j}", "conv", ch, ch, cfg.source_resblock_kernel_sizes[i], True))
+    for i in range(cfg.n_levels):
         ch = BASE_CH >> (i + 1)
         for kk, k in enumerate(RB_KERNELS):
             r = i * 3 + kk
             for j in range(3):
                 t.append((f"resblocks.{r}.convs1.{j}", "conv", ch, ch, k, True))
                 t.append((f"resblocks.{r}.convs2.{j}", "conv", ch, ch, k, True))
-    t.append(("conv_post", "conv", BASE_CH >> 3, N_FFT + 2, 7, True))
+    t.append(("conv_post", "conv", BASE_CH >> cfg.n_levels, N_FFT + 2, 7, True))
     for i in range(5):
         t.append((f"f0_predictor.condnet.{2 * i}", "conv", N_MEL if i == 0 else F0_CH, F0_CH, 3, True))
     return t
 
 
-def make_state_dict(seed: int = 0, kind: str = "init") -> Dict[str, torch.Tensor]:
+def make_state_dict(seed: int = 0, kind: str = "init", cfg: "HiftConfig" = None) -> Dict[str, torch.Tensor]:
     """Random weights in upstream state-dict naming (weight-norm as original0=g, original1=v).
 
     kind="init": upstream initialisation - ``normal(0, 0.01)`` on the weight-normed convs of
@@ -107,15 +142,16 @@ def make_state_dict(seed: int = 0, kind: str = "init") -> Dict[str, torch.Tensor
       down to ~1e-6, fp16-subnormal) compensated by the matching input columns of conv2 - the function is (almost)
       unchanged, the operand ranges are not.
     """
+    cfg = cfg or CHATTERBOX
     if kind == "stress":
-        sd = make_state_dict(seed, "unit")
+        sd = make_state_dict(seed, "unit", cfg)
         g = torch.Generator().manual_seed(seed + 7919)
         for k in list(sd):
             if k.endswith(".alpha"):
                 sd[k] = torch.exp(torch.empty_like(sd[k]).uniform_(math.log(0.05), math.log(30.0), generator=g))
         for k in ("conv_pre.parametrizations.weight.original0", "conv_pre.bias"):
             sd[k] = sd[k] * 40.0
-        for i in range(3):
+        for i in range(cfg.n_levels):
             sd[f"source_downs.{i}.weight"] = sd[f"source_downs.{i}.weight"] * 40.0
             sd[f"source_downs.{i}.bias"] = sd[f"source_downs.{i}.bias"] * 40.0
         sd["conv_post.parametrizations.weight.original0"] = sd["conv_post.parametrizations.weight.original0"] / 40.0
@@ -141,12 +177,12 @@ def make_state_dict(seed: int = 0, kind: str = "init") -> Dict[str, torch.Tensor
     def uni(shape, bound):
         return (torch.rand(shape, generator=g) * 2 - 1) * bound
 
-    for name, kind_l, cin, cout, k, wn in layer_table():
+    for name, kind_l, cin, cout, k, wn in layer_table(cfg):
         shape = (cin, cout, k) if kind_l == "convT" else (cout, cin, k)
         fan_in = (cout if kind_l == "convT" else cin) * k  # torch's fan_in uses dim 1
         normal_init = name.startswith(("ups", "resblocks", "source_resblocks", "conv_post"))
         if kind == "unit":
-            eff = cin * k / (UP_RATES[int(name.split(".")[1])] if kind_l == "convT" else 1)
+            eff = cin * k / (cfg.upsample_rates[int(name.split(".")[1])] if kind_l == "convT" else 1)
             gain = 1.0
             if "resblocks" in name:
                 gain = UNIT_BRANCH_GAIN      # residual branches matter but do not blow up
@@ -168,7 +204,7 @@ def make_state_dict(seed: int = 0, kind: str = "init") -> Dict[str, torch.Tensor
         else:
             sd[name + ".weight"] = v
         sd[name + ".bias"] = b
-    for pre, nblk in (("resblocks", 9), ("source_resblocks", 3)):
+    for pre, nblk in (("resblocks", 3 * cfg.n_levels), ("source_resblocks", cfg.n_levels)):
         for r in range(nblk):
             ch = BASE_CH >> ((r // 3 if pre == "resblocks" else r) + 1)
             for j in range(3):
@@ -225,12 +261,12 @@ def synth_f0(T: int, seed: int, b: int = 0) -> torch.Tensor:
     return torch.where(voiced, f, torch.zeros_like(f)).to(torch.float32)
 
 
-def synth_noise(T: int, seed: int, b: int = 0):
-    """phase_vec ~ U(-pi, pi) [9] with [0]=0, noise ~ N(0,1) [9, 480T]."""
+def synth_noise(T: int, seed: int, b: int = 0, cfg: "HiftConfig" = None):
+    """phase_vec ~ U(-pi, pi) [9] with [0]=0, noise ~ N(0,1) [9, samples_per_frame * T]."""
     g = torch.Generator().manual_seed(seed * 1000 + 900 + b)
     pv = (torch.rand(NB_HARM + 1, generator=g) * 2 - 1) * math.pi
     pv[0] = 0.0
-    nz = torch.randn(NB_HARM + 1, SAMPLES_PER_FRAME * T, generator=g)
+    nz = torch.randn(NB_HARM + 1, (cfg or CHATTERBOX).samples_per_frame * T, generator=g)
     return pv.to(torch.float32), nz.to(torch.float32)
 
 
@@ -281,17 +317,18 @@ def f0_predictor(mel, W, q: Quant = None):
     return torch.abs(F.linear(x, W["f0_predictor.classifier.weight"], W["f0_predictor.classifier.bias"]).squeeze(-1))
 
 
-def sine_source(f0, W, phase_vec, noise):
+def sine_source(f0, W, phase_vec, noise, cfg: "HiftConfig" = None):
     """upstream SineGen.forward + SourceModuleHnNSF.forward with explicit randomness.
 
     f0 [B, T] (Hz) -> s [B, 1, 480T].  ``cumsum`` follows torch CPU semantics for fp32
     (accumulate in double, round each prefix to float).  phase_vec [B, 9], noise [B, 9, L].
     """
     dt = f0.dtype
-    f0u = f0.repeat_interleave(SAMPLES_PER_FRAME, dim=1).unsqueeze(1)          # nearest upsample [B,1,L]
+    cfg = cfg or CHATTERBOX
+    f0u = f0.repeat_interleave(cfg.samples_per_frame, dim=1).unsqueeze(1)      # nearest upsample [B,1,L]
     F_mat = torch.zeros(f0.size(0), NB_HARM + 1, f0u.size(-1), dtype=dt, device=f0.device)
     for i in range(NB_HARM + 1):
-        F_mat[:, i:i + 1, :] = f0u * (i + 1) / SR
+        F_mat[:, i:i + 1, :] = f0u * (i + 1) / cfg.sampling_rate
     theta = 2 * np.pi * (torch.cumsum(F_mat, dim=-1) % 1)
     sine = SINE_AMP * torch.sin(theta + phase_vec.reshape(f0.size(0), -1, 1).to(dt))
     uv = (f0u > VOICED_THR).to(dt)
@@ -318,36 +355,39 @@ def istft_head(mag, phase):
     return torch.istft(torch.complex(real, img), N_FFT, HOP, N_FFT, window=win)
 
 
-def trim_fade(dtype=torch.float32):
-    """upstream s3gen.py S3Token2Wav.__init__: 480 zeros then (cos(linspace(pi,0,480))+1)/2."""
-    n = SR // 50
+def trim_fade(dtype=torch.float32, sr: int = SR):
+    """upstream s3gen.py S3Token2Wav.__init__: n = sr // 50 (480) zeros then (cos(linspace(pi,0,n))+1)/2."""
+    n = sr // 50
     tf = torch.zeros(2 * n, dtype=dtype)
     tf[n:] = (torch.cos(torch.linspace(math.pi, 0, n, dtype=dtype)) + 1) / 2
     return tf
 
 
-def decode(mel, s, W, q: Quant = None, taps: Optional[dict] = None):
+def decode(mel, s, W, q: Quant = None, taps: Optional[dict] = None, cfg: "HiftConfig" = None):
     """upstream HiFTGenerator.decode."""
+    cfg = cfg or CHATTERBOX
+    NL = cfg.n_levels
+    downs = cfg.source_downs()
     s_stft = stft_source(s.squeeze(1))
     x = _conv(mel, W["conv_pre.weight"], W["conv_pre.bias"], q, padding=3)
     if taps is not None:
         taps["s_stft"] = s_stft
         taps["conv_pre"] = x
-    for i in range(3):
+    for i in range(NL):
         x = F.leaky_relu(x, LRELU)
         xi, wi = (q(x), q(W[f"ups.{i}.weight"])) if q is not None else (x, W[f"ups.{i}.weight"])
-        x = F.conv_transpose1d(xi, wi, W[f"ups.{i}.bias"], stride=UP_RATES[i],
-                               padding=(UP_KERNELS[i] - UP_RATES[i]) // 2)
-        if i == 2:
+        x = F.conv_transpose1d(xi, wi, W[f"ups.{i}.bias"], stride=cfg.upsample_rates[i],
+                               padding=(cfg.upsample_kernel_sizes[i] - cfg.upsample_rates[i]) // 2)
+        if i == NL - 1:
             x = F.pad(x, (1, 0), mode="reflect")
-        down = [(15, 7), (3, 1), (1, 0)][i]
+        down = downs[i][1:]
         # source_downs operate on the fp32 STFT on CUDA cores in the product (no operand rounding)
         si = F.conv1d(s_stft, W[f"source_downs.{i}.weight"], W[f"source_downs.{i}.bias"],
                       stride=down[0], padding=down[1])
         if taps is not None:
             taps[f"ups{i}"] = x
             taps[f"sd{i}"] = si
-        si = resblock(si, W, f"source_resblocks.{i}", SRC_RB_KERNELS[i], q)
+        si = resblock(si, W, f"source_resblocks.{i}", cfg.source_resblock_kernel_sizes[i], q)
         x = x + si
         if taps is not None:
             taps[f"si{i}"] = si
@@ -372,26 +412,28 @@ def decode(mel, s, W, q: Quant = None, taps: Optional[dict] = None):
 @torch.inference_mode()
 def hift_inference(mel: torch.Tensor, W: Dict[str, torch.Tensor], *, f0: Optional[torch.Tensor] = None,
                    phase_vec: torch.Tensor, noise: torch.Tensor, dtype=torch.float32,
-                   quant: Quant = None, apply_trim_fade: bool = True, taps: Optional[dict] = None):
+                   quant: Quant = None, apply_trim_fade: bool = True, taps: Optional[dict] = None,
+                   cfg: "HiftConfig" = None):
     """HiFTGenerator.inference + the S3Token2Wav tail, one sequence.
 
     mel [80, T]; f0 [T] or None (predict); phase_vec [9]; noise [9, 480T] -> wav [480T].
     ``quant`` rounds conv operands (activations and weights) to emulate the tensor-core
     operand dtype; it is None for the oracle proper.
     """
+    cfg = cfg or CHATTERBOX
     Wd = {k: v.to(dtype) for k, v in W.items()}
     mel = mel.to(dtype).unsqueeze(0)
     if f0 is None:
         f0 = f0_predictor(mel, Wd)
     else:
         f0 = f0.to(dtype).unsqueeze(0)
-    s = sine_source(f0, Wd, phase_vec.unsqueeze(0).to(mel.device), noise.unsqueeze(0).to(mel.device))
+    s = sine_source(f0, Wd, phase_vec.unsqueeze(0).to(mel.device), noise.unsqueeze(0).to(mel.device), cfg)
     if taps is not None:
         taps["f0"] = f0
         taps["s"] = s
-    y = decode(mel, s, Wd, quant, taps)
-    if apply_trim_fade:
-        tf = trim_fade(dtype).to(y.device)
+    y = decode(mel, s, Wd, quant, taps, cfg)
+    if apply_trim_fade and cfg.trim_fade:
+        tf = trim_fade(dtype, cfg.sampling_rate).to(y.device)
         n = min(tf.numel(), y.size(1))
         y[:, :n] *= tf[:n]
     return y.squeeze(0)

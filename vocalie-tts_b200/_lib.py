@@ -39,6 +39,12 @@ class PostParams(C.Structure):
     ]
 
 
+class HiftConfig(C.Structure):
+    """struct vt_hift_config."""
+    _fields_ = [("sampling_rate", C.c_int32), ("n_upsamples", C.c_int32), ("upsample_rates", C.c_int32 * 4),
+                ("upsample_kernel_sizes", C.c_int32 * 4), ("source_resblock_kernel_sizes", C.c_int32 * 4), ("trim_fade", C.c_int32)]
+
+
 class Tensor(C.Structure):
     """struct vt_tensor."""
     _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("ndim", C.c_int32), ("shape", C.c_int64 * 4)]
@@ -62,6 +68,9 @@ _SIGS = {
     "vt_pcm16_encode": (C.c_int, [_P, _P, _I64, _P]),
     "vt_pcm16_decode": (C.c_int, [_P, _P, _I64, _P]),
     "vt_hift_create": (C.c_int, [C.POINTER(Tensor), C.c_int, C.c_int, C.POINTER(_P)]),
+    "vt_hift_create_ex": (C.c_int, [C.POINTER(Tensor), C.c_int, C.c_int, C.POINTER(HiftConfig), C.POINTER(_P)]),
+    "vt_hift_samples_per_frame": (C.c_int, [_P]),
+    "vt_hift_sampling_rate": (C.c_int, [_P]),
     "vt_hift_destroy": (None, [_P]),
     "vt_hift_workspace_bytes": (_I64, [_P, C.c_int, _I64, _I64]),
     "vt_hift_forward": (C.c_int, [_P, _P, C.POINTER(C.c_int32), C.c_int, _P, _P, _P, C.c_uint64, _P, _P, _I64, _P]),

@@ -20,13 +20,14 @@ constexpr int kHeadFrames = kHeadSamples / kHop + 4;    // frames touching them 
 //   3. sample -> overlap-add of its <= 4 frames, divide by the overlap-added squared window, clamp, trim_fade
 __global__ void __launch_bounds__(256)
 k_istft_head(const float* __restrict__ post, const int* __restrict__ mel_off, const int* __restrict__ T,
-             const long long* __restrict__ off2, const float* __restrict__ trim_fade, float* __restrict__ wav) {
+             const long long* __restrict__ off2, const float* __restrict__ trim_fade, int trim_len, int spf,
+             float* __restrict__ wav) {
   __shared__ float sh_re[kHeadFrames][10];
   __shared__ float sh_im[kHeadFrames][10];
   __shared__ float sh_y[kHeadFrames][17];
   __shared__ float sh_w2[16];
   const int b = blockIdx.y;
-  const long long L = (long long)T[b] * kSPF;
+  const long long L = (long long)T[b] * spf;
   const long long frames = L / kHop + 1;
   const long long p0 = (long long)blockIdx.x * kHeadSamples;
   if (p0 >= L) return;
@@ -94,17 +95,17 @@ k_istft_head(const float* __restrict__ post, const int* __restrict__ mel_off, co
     }
     float y = num / den;
     y = fminf(fmaxf(y, -0.99f), 0.99f);
-    if (p < 2 * kSPF) y *= trim_fade[p];
-    wav[(long long)mel_off[b] * kSPF + p] = y;
+    if (p < trim_len) y *= trim_fade[p];
+    wav[(long long)mel_off[b] * spf + p] = y;
   }
 }
 
 int launch_istft_head(const float* post, const int* mel_off, const int* T, const long long* off2, int B,
-                      int T_max, const float* trim_fade, float* wav, cudaStream_t st) {
+                      int T_max, const float* trim_fade, int trim_len, int spf, float* wav, cudaStream_t st) {
   if (B == 0 || T_max == 0) return VT_OK;
-  const long long Lmax = (long long)T_max * kSPF;
+  const long long Lmax = (long long)T_max * spf;
   dim3 grid((unsigned)((Lmax + kHeadSamples - 1) / kHeadSamples), B);
-  k_istft_head<<<grid, 256, 0, st>>>(post, mel_off, T, off2, trim_fade, wav);
+  k_istft_head<<<grid, 256, 0, st>>>(post, mel_off, T, off2, trim_fade, trim_len, spf, wav);
   VT_LAUNCHED();
   return VT_OK;
 }

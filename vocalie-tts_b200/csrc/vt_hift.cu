@@ -30,13 +30,8 @@ int launch_pair_tc(const ConvArgs& a, const ConvLayer& c1, const ConvLayer& c2, 
 
 namespace {
 
-const int kUpRates[3] = {8, 5, 3};
-const int kUpKernels[3] = {16, 11, 7};
 const int kRbKernels[3] = {3, 7, 11};
 const int kRbDil[3] = {1, 3, 5};
-const int kSrcRbKernels[3] = {7, 7, 11};
-const int kSdK[3] = {30, 6, 1}, kSdS[3] = {15, 3, 1}, kSdP[3] = {7, 1, 0};
-const int kLevelMul[3] = {8, 40, 120};
 
 struct HostTensor {
   const float* data;
@@ -98,6 +93,7 @@ struct Workspace {
 using namespace vt;
 
 struct vt_hift {
+  HiftCfg cfg;
   int act_elem = ELEM_F32;
   bool use_tc = false;
   std::vector<void*> allocs;
@@ -308,8 +304,10 @@ int build_plan(vt_hift* h, const int32_t* T, int B, cudaStream_t st) {
   P.T_max = 0;
   P.h_mel_off.resize(B);
   std::vector<long long> melrow(B);
+  const HiftCfg& cfg = h->cfg;
+  const int NL = cfg.n_levels, LL = NL - 1;          // LL: the last (sample-rate / hop) level, one reflection-padded row longer
   std::vector<int> lenM(B), len[3];
-  for (int l = 0; l < 3; ++l) { len[l].resize(B); P.h_off[l].resize(B); }
+  for (int l = 0; l < NL; ++l) { len[l].resize(B); P.h_off[l].resize(B); }
   for (int b = 0; b < B; ++b) {
     P.h_mel_off[b] = (int)P.total_T;
     melrow[b] = P.total_T;
@@ -326,10 +324,10 @@ int build_plan(vt_hift* h, const int32_t* T, int B, cudaStream_t st) {
     }
     P.rowsM = o;
   }
-  for (int l = 0; l < 3; ++l) {
+  for (int l = 0; l < NL; ++l) {
     long long o = kGap;
     for (int b = 0; b < B; ++b) {
-      len[l][b] = kLevelMul[l] * T[b] + (l == 2 ? 1 : 0);
+      len[l][b] = cfg.level_mul[l] * T[b] + (l == LL ? 1 : 0);
       P.h_off[l][b] = o;
       o += len[l][b] + kGap;
     }
@@ -341,15 +339,15 @@ int build_plan(vt_hift* h, const int32_t* T, int B, cudaStream_t st) {
   add_tiles(tiles, P.pre, B, melrow.data(), lenM.data(), P.h_offM.data(), lenM.data(), kTileQ);
   add_tiles(tiles, P.up[0], B, P.h_offM.data(), lenM.data(), P.h_off[0].data(), lenM.data(), kTileQ);
   add_tiles(tiles, P.tcu[0], B, P.h_offM.data(), lenM.data(), P.h_off[0].data(), lenM.data(), 128);
-  add_tiles(tiles, P.tcu[1], B, P.h_off[0].data(), len[0].data(), P.h_off[1].data(), len[0].data(), 128);
-  add_tiles(tiles, P.tcu[2], B, P.h_off[1].data(), len[1].data(), P.h_off[2].data(), len[1].data(), 128);
-  add_tiles(tiles, P.up[1], B, P.h_off[0].data(), len[0].data(), P.h_off[1].data(), len[0].data(), kTileQ);
-  add_tiles(tiles, P.up[2], B, P.h_off[1].data(), len[1].data(), P.h_off[2].data(), len[1].data(), kTileQ);
+  for (int l = 1; l < NL; ++l) {
+    add_tiles(tiles, P.tcu[l], B, P.h_off[l - 1].data(), len[l - 1].data(), P.h_off[l].data(), len[l - 1].data(), 128);
+    add_tiles(tiles, P.up[l], B, P.h_off[l - 1].data(), len[l - 1].data(), P.h_off[l].data(), len[l - 1].data(), kTileQ);
+  }
   add_tiles(tiles, P.g_mel, B, P.h_offM.data(), lenM.data(), P.h_offM.data(), lenM.data(), 256);
   add_tiles(tiles, P.g_melu, B, P.h_offM.data(), lenM.data(), melrow.data(), lenM.data(), 256);
-  for (int l = 0; l < 3; ++l) {
-    add_tiles(tiles, P.g_sd[l], B, P.h_off[2].data(), len[2].data(), P.h_off[l].data(), len[l].data(), 256);
-    add_tiles(tiles, P.sd[l], B, P.h_off[2].data(), len[2].data(), P.h_off[l].data(), len[l].data(), kTileQ);
+  for (int l = 0; l < NL; ++l) {
+    add_tiles(tiles, P.g_sd[l], B, P.h_off[LL].data(), len[LL].data(), P.h_off[l].data(), len[l].data(), 256);
+    add_tiles(tiles, P.sd[l], B, P.h_off[LL].data(), len[LL].data(), P.h_off[l].data(), len[l].data(), kTileQ);
     add_tiles(tiles, P.lvl[l], B, P.h_off[l].data(), len[l].data(), P.h_off[l].data(), len[l].data(), kTileQ);
     add_tiles(tiles, P.tc[l][0], B, P.h_off[l].data(), len[l].data(), P.h_off[l].data(), len[l].data(), 128);
     add_tiles(tiles, P.tc[l][1], B, P.h_off[l].data(), len[l].data(), P.h_off[l].data(), len[l].data(), 256);
@@ -376,7 +374,7 @@ int build_plan(vt_hift* h, const int32_t* T, int B, cudaStream_t st) {
   char* dp = (char*)P.d_block;
   std::memcpy(hp, T, (size_t)B * 4); P.d_T = (int*)dp;
   std::memcpy(hp + nI, P.h_mel_off.data(), (size_t)B * 4); P.d_mel_off = (int*)(dp + nI);
-  for (int l = 0; l < 3; ++l) {
+  for (int l = 0; l < NL; ++l) {
     std::memcpy(hp + 2 * nI + l * nL, P.h_off[l].data(), (size_t)B * 8);
     P.d_off[l] = (long long*)(dp + 2 * nI + l * nL);
   }
@@ -399,12 +397,14 @@ Workspace carve_ws(const vt_hift* h, int B, long long total_T, void* base) {
     return p;
   };
   const size_t es = elem_size(h->act_elem);
+  const HiftCfg& cfg = h->cfg;
+  const int NL = cfg.n_levels;
   const long long rowsM = total_T + 64;
   w.f0a = (float*)take((size_t)rowsM * kF0Ch * 4);
   w.f0b = (float*)take((size_t)rowsM * kF0Ch * 4);
   w.f0 = (float*)take((size_t)rowsM * 4);
   w.phase_base = (double*)take((size_t)kHarm * rowsM * 16);   // phase prefix | increment, per (harmonic, frame)
-  w.s = (float*)take((size_t)total_T * kSPF * 4 + 64);
+  w.s = (float*)take((size_t)total_T * cfg.spf * 4 + 64);
   w.cap_rowsM = total_T + (long long)B * kGap + kGap + 512;
   w.xpre = (float*)take((size_t)w.cap_rowsM * kBase * 4);
   w.xpre_act = take((size_t)w.cap_rowsM * kBase * es);
@@ -412,8 +412,8 @@ Workspace carve_ws(const vt_hift* h, int B, long long total_T, void* base) {
   w.mel_lo = take((size_t)w.cap_rowsM * kMelOp * 2);
   for (int i = 0; i < 2; ++i)
     for (int j = 0; j < 2; ++j) w.fx[i][j] = take((size_t)w.cap_rowsM * kF0Ch * 2);
-  for (int l = 0; l < 3; ++l) {
-    const long long cap = (long long)kLevelMul[l] * total_T + (long long)B * (kGap + 1) + kGap + 512;
+  for (int l = 0; l < NL; ++l) {
+    const long long cap = (long long)cfg.level_mul[l] * total_T + (long long)B * (kGap + 1) + kGap + 512;
     w.cap_rows[l] = cap;
     const int C = kBase >> (l + 1);
     w.U[l] = (float*)take((size_t)cap * C * 4);
@@ -426,9 +426,9 @@ Workspace carve_ws(const vt_hift* h, int B, long long total_T, void* base) {
     for (int i = 0; i < 4; ++i) w.A[l][i] = take((size_t)cap * C * es);
     w.Yact[l] = take((size_t)cap * C * es);
   }
-  w.spec = (float*)take((size_t)w.cap_rows[2] * kSpecCh * 4);
-  w.post = (float*)take((size_t)w.cap_rows[2] * kSpecCh * 4);
-  w.spec_op = take((size_t)w.cap_rows[2] * kSpecOp * 2);
+  w.spec = (float*)take((size_t)w.cap_rows[NL - 1] * kSpecCh * 4);
+  w.post = (float*)take((size_t)w.cap_rows[NL - 1] * kSpecCh * 4);
+  w.spec_op = take((size_t)w.cap_rows[NL - 1] * kSpecOp * 2);
   w.bytes = off;
   return w;
 }
@@ -516,7 +516,43 @@ __global__ void k_tap(const T* src, long long row0, int ld, int ch, long long ro
 extern "C" {
 
 int vt_hift_create(const vt_tensor* tensors, int n_tensors, int operand_dtype, vt_hift** out_handle) {
+  return vt_hift_create_ex(tensors, n_tensors, operand_dtype, nullptr, out_handle);
+}
+
+int vt_hift_samples_per_frame(const vt_hift* h) { return h ? h->cfg.spf : VT_ERR_INVALID; }
+int vt_hift_sampling_rate(const vt_hift* h) { return h ? h->cfg.sr : VT_ERR_INVALID; }
+
+int vt_hift_create_ex(const vt_tensor* tensors, int n_tensors, int operand_dtype, const vt_hift_config* user_cfg,
+                      vt_hift** out_handle) {
   VT_REQUIRE(tensors && n_tensors > 0 && out_handle, "vt_hift_create: NULL argument");
+  HiftCfg cfg;                                   // defaults: Chatterbox S3Gen
+  if (user_cfg) {
+    VT_REQUIRE(user_cfg->n_upsamples == 2 || user_cfg->n_upsamples == 3, "vt_hift_create: 2 or 3 upsampling stages are supported (got %d)",
+               user_cfg->n_upsamples);
+    VT_REQUIRE(user_cfg->sampling_rate >= 8000 && user_cfg->sampling_rate <= 96000, "vt_hift_create: bad sampling rate %d", user_cfg->sampling_rate);
+    cfg.n_levels = user_cfg->n_upsamples;
+    cfg.sr = user_cfg->sampling_rate;
+    cfg.trim_fade = user_cfg->trim_fade ? 1 : 0;
+    int mul = 1;
+    for (int i = 0; i < cfg.n_levels; ++i) {
+      const int u = user_cfg->upsample_rates[i], k = user_cfg->upsample_kernel_sizes[i], sk = user_cfg->source_resblock_kernel_sizes[i];
+      VT_REQUIRE(u >= 1 && u <= 16 && k >= u && ((k - u) & 1) == 0, "vt_hift_create: unsupported upsampling stage %d (rate %d, kernel %d)", i, u, k);
+      VT_REQUIRE(sk == 3 || sk == 7 || sk == 11, "vt_hift_create: source ResBlock kernel size must be 3, 7 or 11 (got %d)", sk);
+      cfg.up_rate[i] = u; cfg.up_kernel[i] = k; cfg.src_rb_kernel[i] = sk;
+      mul *= u;
+      cfg.level_mul[i] = mul;
+    }
+    // source_downs (upstream HiFTGenerator.__init__): stride = product of the LATER upsampling rates; 1 -> k = 1,
+    // else k = 2 u, padding u / 2
+    for (int i = 0; i < cfg.n_levels; ++i) {
+      int u = 1;
+      for (int j = i + 1; j < cfg.n_levels; ++j) u *= cfg.up_rate[j];
+      cfg.sd_s[i] = u; cfg.sd_k[i] = u == 1 ? 1 : 2 * u; cfg.sd_p[i] = u == 1 ? 0 : u / 2;
+    }
+    cfg.spf = mul * kHop;
+    cfg.trim_n = cfg.sr / 50;
+  }
+  const int NL = cfg.n_levels;
   VT_REQUIRE(operand_dtype == VT_OPERAND_FP16 || operand_dtype == VT_OPERAND_BF16 || operand_dtype == VT_OPERAND_FP32,
              "vt_hift_create: unknown operand dtype %d", operand_dtype);
   std::map<std::string, HostTensor> tab;
@@ -529,21 +565,22 @@ int vt_hift_create(const vt_tensor* tensors, int n_tensors, int operand_dtype, v
     tab[tensors[i].name] = t;
   }
   vt_hift* h = new vt_hift();
+  h->cfg = cfg;
   h->act_elem = operand_dtype == VT_OPERAND_FP32 ? ELEM_F32 : (operand_dtype == VT_OPERAND_FP16 ? ELEM_F16 : ELEM_BF16);
   h->use_tc = operand_dtype != VT_OPERAND_FP32;
   int rc = VT_OK;
   auto fail = [&](int code) { vt_hift_destroy(h); return code; };
 #define TRY(expr) do { rc = (expr); if (rc) return fail(rc); } while (0)
   TRY(pack_conv(h, h->conv_pre, tab, "conv_pre", kMel, kBase, 7, 1, 1, 3, kMel, kBase, GEMM_SPLIT, kMelOp));
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < NL; ++i) {
     const int cin = kBase >> i, cout = kBase >> (i + 1);
-    TRY(pack_convT(h, h->ups[i], tab, "ups." + std::to_string(i), cin, cout, kUpKernels[i], kUpRates[i],
-                   (kUpKernels[i] - kUpRates[i]) / 2));
-    TRY(pack_conv(h, h->sdown[i], tab, "source_downs." + std::to_string(i), kNfft + 2, cout, kSdK[i], 1, kSdS[i],
-                  kSdP[i], kSpecCh, cout, GEMM_IM2COL, kSpecOp));
+    TRY(pack_convT(h, h->ups[i], tab, "ups." + std::to_string(i), cin, cout, cfg.up_kernel[i], cfg.up_rate[i],
+                   (cfg.up_kernel[i] - cfg.up_rate[i]) / 2));
+    TRY(pack_conv(h, h->sdown[i], tab, "source_downs." + std::to_string(i), kNfft + 2, cout, cfg.sd_k[i], 1, cfg.sd_s[i],
+                  cfg.sd_p[i], kSpecCh, cout, GEMM_IM2COL, kSpecOp));
     for (int j = 0; j < 3; ++j) {
       const std::string p = "source_resblocks." + std::to_string(i);
-      const int k = kSrcRbKernels[i];
+      const int k = cfg.src_rb_kernel[i];
       TRY(pack_conv(h, h->src_c1[i][j], tab, p + ".convs1." + std::to_string(j), cout, cout, k, kRbDil[j], 1,
                     (k * kRbDil[j] - kRbDil[j]) / 2, cout, cout));
       TRY(pack_conv(h, h->src_c2[i][j], tab, p + ".convs2." + std::to_string(j), cout, cout, k, 1, 1, (k - 1) / 2, cout, cout));
@@ -562,7 +599,7 @@ int vt_hift_create(const vt_tensor* tensors, int n_tensors, int operand_dtype, v
       }
     }
   }
-  for (int i = 0; i < 3 && h->use_tc; ++i) {
+  for (int i = 0; i < NL && h->use_tc; ++i) {
     const char* nf = getenv("VT_NO_FUSE");
     bool ok = !(nf && nf[0] == '1');
     for (int j = 0; j < 3 && ok; ++j) {
@@ -587,13 +624,13 @@ int vt_hift_create(const vt_tensor* tensors, int n_tensors, int operand_dtype, v
         bool p64 = e64 ? (e64[0] == 'a' || (e64[0] == '7' && kRbKernels[kk] >= 7)) : kRbKernels[kk] == 11;
         for (int j = 0; j < 3; ++j) {
           p64 = p64 && pair64_tc_supported(h->rb_c1[i * 3 + kk][j], h->rb_c2[i * 3 + kk][j]);
-          if (kSrcRbKernels[i] == kRbKernels[kk]) p64 = p64 && pair64_tc_supported(h->src_c1[i][j], h->src_c2[i][j]);
+          if (cfg.src_rb_kernel[i] == kRbKernels[kk]) p64 = p64 && pair64_tc_supported(h->src_c1[i][j], h->src_c2[i][j]);
         }
         h->pair64[kk] = p64;
       }
     }
   }
-  TRY(pack_conv(h, h->conv_post, tab, "conv_post", kBase >> 3, kNfft + 2, 7, 1, 1, 3, kBase >> 3, kSpecCh));
+  TRY(pack_conv(h, h->conv_post, tab, "conv_post", kBase >> NL, kNfft + 2, 7, 1, 1, 3, kBase >> NL, kSpecCh));
   for (int i = 0; i < 5; ++i)
     TRY(pack_conv(h, h->f0c[i], tab, "f0_predictor.condnet." + std::to_string(2 * i), i == 0 ? kMel : kF0Ch, kF0Ch, 3, 1, 1, 1,
                   i == 0 ? kMel : kF0Ch, kF0Ch, GEMM_SPLIT, i == 0 ? kMelOp : kF0Ch));
@@ -602,13 +639,14 @@ int vt_hift_create(const vt_tensor* tensors, int n_tensors, int operand_dtype, v
   TRY(upload_vec(h, tab, "m_source.l_linear.weight", kHarm, &h->lin_w));
   TRY(upload_vec(h, tab, "m_source.l_linear.bias", 1, &h->lin_b));
   {
-    // s3gen.py: trim_fade = zeros(2n); trim_fade[n:] = (cos(linspace(pi, 0, n)) + 1) / 2, n = 480 (fp32)
-    std::vector<float> tf(2 * kSPF, 0.0f);
-    const float step = (0.0f - 3.14159265358979323846f) / (float)(kSPF - 1);
-    for (int i = 0; i < kSPF; ++i) {
+    // s3gen.py: trim_fade = zeros(2n); trim_fade[n:] = (cos(linspace(pi, 0, n)) + 1) / 2, n = S3GEN_SR // 50 = 480 (fp32)
+    const int tn = cfg.trim_n;
+    std::vector<float> tf(2 * tn, 0.0f);
+    const float step = (0.0f - 3.14159265358979323846f) / (float)(tn - 1);
+    for (int i = 0; i < tn; ++i) {
       // torch.linspace (fp32): first half from the start, second half from the end
-      const float x = i < kSPF / 2 ? 3.14159265358979323846f + step * (float)i : 0.0f - step * (float)(kSPF - 1 - i);
-      tf[kSPF + i] = (cosf(x) + 1.0f) / 2.0f;
+      const float x = i < tn / 2 ? 3.14159265358979323846f + step * (float)i : 0.0f - step * (float)(tn - 1 - i);
+      tf[tn + i] = (cosf(x) + 1.0f) / 2.0f;
     }
     TRY(dev_upload(h, tf.data(), tf.size() * 4, (void**)&h->trim_fade));
   }
@@ -648,7 +686,9 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
     VT_REQUIRE(T[b] >= 1, "vt_hift_forward: every sequence needs at least one mel frame (T[%d]=%d)", b, T[b]);
     total_T += T[b];
   }
-  VT_REQUIRE(total_T * 121LL + B * 40LL < 2000000000LL, "vt_hift_forward: batch too large for 32-bit tile tables");
+  const HiftCfg& cfg = h->cfg;
+  const int NL = cfg.n_levels, LL = NL - 1;
+  VT_REQUIRE(total_T * (long long)(cfg.level_mul[LL] + 1) + B * 40LL < 2000000000LL, "vt_hift_forward: batch too large for 32-bit tile tables");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
   int rc = build_plan(h, T, B, st);
   if (rc) return rc;
@@ -672,9 +712,9 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
     GapTable gt{};
     int nb = 0;
     auto add = [&](void* p, int row_bytes, int level) { gt.b[nb++] = GapBuf{p, row_bytes, level}; };
-    for (int l = 0; l < 3; ++l) {
+    for (int l = 0; l < NL; ++l) {
       const int C = kBase >> (l + 1);
-      gt.off[l] = P.d_off[l]; gt.mul[l] = kLevelMul[l]; gt.plus[l] = l == 2 ? 1 : 0;
+      gt.off[l] = P.d_off[l]; gt.mul[l] = cfg.level_mul[l]; gt.plus[l] = l == LL ? 1 : 0;
       add(w.Yact[l], C * (int)elem_size(ae), l);
       if (h->fuse[l]) {
         // fused pairs read the fp32 streams with their halo
@@ -692,7 +732,7 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
     if (!f0_in)
       for (int i = 0; i < 2; ++i)
         for (int j = 0; j < 2; ++j) add(w.fx[i][j], kF0Ch * 2, 3);
-    add(w.spec_op, kSpecOp * 2, 2);
+    add(w.spec_op, kSpecOp * 2, LL);
     VT_REQUIRE(nb <= kMaxGapBufs, "gap table overflow");
     k_zero_gaps<<<dim3(B + 1, nb), 256, 0, st>>>(gt, P.d_T);
     VT_LAUNCHED();
@@ -740,9 +780,10 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
   mark(h, "f0_predictor", st);
   // ---- source: SineGen -> tanh(Linear) -> STFT
   rc = launch_sine_source(f0, P.d_mel_off, P.d_T, B, total_T, phase_vec, noise, seed, h->lin_w, h->lin_b,
-                          w.phase_base, w.s, st);
+                          w.phase_base, w.s, cfg.spf, cfg.sr, st);
   if (rc) return rc;
-  rc = launch_stft(w.s, P.d_mel_off, P.d_T, P.d_off[2], B, total_T, h->use_tc ? nullptr : w.spec, h->use_tc ? w.spec_op : nullptr, ae, st);
+  rc = launch_stft(w.s, P.d_mel_off, P.d_T, P.d_off[LL], B, total_T, h->use_tc ? nullptr : w.spec, h->use_tc ? w.spec_op : nullptr, ae,
+                   cfg.spf, st);
   if (rc) return rc;
   mark(h, "source_stft", st);
   // ---- conv_pre
@@ -761,13 +802,13 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
     if (rc) return rc;
   }
   mark(h, "conv_pre", st);
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < NL; ++i) {
     const std::string sfx = std::to_string(i);
     // ups[i]( leaky_relu(x, 0.1) ), reflection pad (1, 0) on the last stage
     {
       ConvArgs a = base_args(h->ups[i], P, P.up[i]);
       a.out = w.U[i];
-      if (i == 2) { a.out_shift = 1; a.dup_row2 = 1; }
+      if (i == LL) { a.out_shift = 1; a.dup_row2 = 1; }
       if (h->use_tc && h->ups[i].w_tc) {
         a.in_act = i == 0 ? w.xpre_act : w.Yact[i - 1];   // leaky_relu already applied by the producer
         rc = launch_conv_tc(a, h->ups[i], ae, P.d_tiles + P.tcu[i].off, P.tcu[i].n, 128, st);
@@ -797,19 +838,20 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
     // source_resblocks[i]; its last conv also adds the upsampled stream: x = ups + si
     if (prof) {
       VT_CUDA_OK(cudaEventRecord(h->ev_rb[i][0], st));
-      const double steps = (double)kLevelMul[i] * (double)total_T + (i == 2 ? B : 0);
+      const double steps = (double)cfg.level_mul[i] * (double)total_T + (i == LL ? B : 0);
       const double c = (double)(kBase >> (i + 1));
-      h->rb_flops += steps * 2.0 * c * c * 6.0 * (kSrcRbKernels[i] + kRbKernels[0] + kRbKernels[1] + kRbKernels[2]);
+      h->rb_flops += steps * 2.0 * c * c * 6.0 * (cfg.src_rb_kernel[i] + kRbKernels[0] + kRbKernels[1] + kRbKernels[2]);
       h->rb_launches += h->fuse[i] ? 12 : 24;
     }
     if (h->fuse[i]) {
       // fused pairs: fp32 stream in, fp32 stream out, no operand copies in HBM
       float* sbuf[2] = {w.S[i], w.S2[i]};
-      const int ksrc = kSrcRbKernels[i] == 3 ? 0 : (kSrcRbKernels[i] == 7 ? 1 : 2);
+      const int ksrc = cfg.src_rb_kernel[i] == 3 ? 0 : (cfg.src_rb_kernel[i] == 7 ? 1 : 2);
+      const bool c64 = (kBase >> (i + 1)) == 64;          // the tap-paired kernel is the C = 64 kernel
       for (int j = 0; j < 3; ++j) {
         // the tap-paired kernel takes the plain pairs; the last pair of a ResBlock (second residual / running mean /
         // operand copy: more streams in the fin epilogue) stays on the activation-major kernel - measured faster there
-        const bool p64 = i == 2 && h->pair64[ksrc] && (j < 2 || h->pair64_last);
+        const bool p64 = c64 && h->pair64[ksrc] && (j < 2 || h->pair64_last);
         ConvArgs c = base_args(h->src_c2[i][j], P, p64 ? P.pair64[ksrc] : P.pair[i][ksrc]);
         c.res1 = sbuf[j & 1];
         if (j < 2) c.out = sbuf[(j + 1) & 1];
@@ -823,7 +865,7 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
         const int R = i * 3 + r;
         float* xin[3] = {w.X[i], w.XR[i], w.XR2[i]};
         for (int j = 0; j < 3; ++j) {
-          const bool p64 = i == 2 && h->pair64[r] && (j < 2 || h->pair64_last);
+          const bool p64 = c64 && h->pair64[r] && (j < 2 || h->pair64_last);
           ConvArgs c = base_args(h->rb_c2[R][j], P, p64 ? P.pair64[r] : P.pair[i][r]);
           c.res1 = xin[j];
           if (j < 2) c.out = xin[j + 1];
@@ -832,7 +874,7 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
             c.out_accum = r > 0;
             c.out_scale = 1.0f / 3.0f;
             if (r == 2) {
-              c.act[0] = {w.Yact[i], nullptr, ACT_LRELU, i < 2 ? 0.1f : 0.01f};
+              c.act[0] = {w.Yact[i], nullptr, ACT_LRELU, i < LL ? 0.1f : 0.01f};
               c.act_from_out = 1;
             }
           }
@@ -883,7 +925,7 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
           c.out_accum = r > 0;
           c.out_scale = 1.0f / 3.0f;
           if (h->use_tc && r == 2) {   // the mean is complete: emit the next layer's leaky_relu operand copy
-            c.act[0] = {w.Yact[i], nullptr, ACT_LRELU, i < 2 ? 0.1f : 0.01f};
+            c.act[0] = {w.Yact[i], nullptr, ACT_LRELU, i < LL ? 0.1f : 0.01f};
             c.act_from_out = 1;
           }
         }
@@ -896,22 +938,22 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
   }
   // ---- conv_post( leaky_relu(x) ) with the default slope 0.01, then the spectral head
   {
-    ConvArgs a = base_args(h->conv_post, P, P.lvl[2]);
+    ConvArgs a = base_args(h->conv_post, P, P.lvl[LL]);
     a.out = w.post;
     if (h->use_tc && h->conv_post.w_tc) {
-      a.in_act = w.Yact[2];
+      a.in_act = w.Yact[LL];
       const int rows = conv_tc_tile_rows(h->conv_post);
-      const Plan::Seg& seg = P.tc[2][rows == 256 ? 1 : 0];
+      const Plan::Seg& seg = P.tc[LL][rows == 256 ? 1 : 0];
       rc = launch_conv_tc(a, h->conv_post, ae, P.d_tiles + seg.off, seg.n, rows, st);
     } else {
-      a.in = w.Y[2];
+      a.in = w.Y[LL];
       a.pro_act = ACT_LRELU; a.pro_slope = 0.01f;
       rc = launch_conv_ref(a, ae, st);
     }
     if (rc) return rc;
   }
   mark(h, "conv_post", st);
-  rc = launch_istft_head(w.post, P.d_mel_off, P.d_T, P.d_off[2], B, P.T_max, h->trim_fade, wav, st);
+  rc = launch_istft_head(w.post, P.d_mel_off, P.d_T, P.d_off[LL], B, P.T_max, h->trim_fade, cfg.trim_fade ? 2 * cfg.trim_n : 0, cfg.spf, wav, st);
   if (rc) return rc;
   mark(h, "istft_head", st);
   if (prof) VT_CUDA_OK(cudaEventRecord(h->ev_fwd[1], st));
@@ -937,7 +979,7 @@ int vt_hift_read_profile(vt_hift* h, double* total_ms, double* resblock_ms, doub
   VT_CUDA_OK(cudaEventElapsedTime(&ms, h->ev_fwd[0], h->ev_fwd[1]));
   if (total_ms) *total_ms = ms;
   double rb = 0;
-  for (int l = 0; l < 3; ++l) {
+  for (int l = 0; l < h->cfg.n_levels; ++l) {
     VT_CUDA_OK(cudaEventElapsedTime(&ms, h->ev_rb[l][0], h->ev_rb[l][1]));
     rb += ms;
   }
@@ -978,28 +1020,35 @@ int64_t vt_hift_read_tap(vt_hift* h, const char* tap, int seq, float* out, int64
   const void* src = nullptr;
   long long row0 = 0, rows = 0;
   int ld = 0, ch = 0, elem = ELEM_F32;
+  const HiftCfg& cfg = h->cfg;
+  const int LL = cfg.n_levels - 1;
+  const long long last_rows = (long long)cfg.level_mul[LL] * T + 1;
   auto level = [&](int l, const void* p, int e) {
-    src = p; row0 = P.h_off[l][seq]; rows = (long long)kLevelMul[l] * T + (l == 2 ? 1 : 0);
+    if (l < 0 || l > LL) { src = nullptr; return; }
+    src = p; row0 = P.h_off[l][seq]; rows = (long long)cfg.level_mul[l] * T + (l == LL ? 1 : 0);
     ld = ch = kBase >> (l + 1); elem = e;
   };
   if (name == "f0") { src = w.f0; row0 = P.h_mel_off[seq]; rows = T; ld = ch = 1; }
-  else if (name == "s") { src = w.s; row0 = (long long)P.h_mel_off[seq] * kSPF; rows = (long long)T * kSPF; ld = ch = 1; }
+  else if (name == "s") { src = w.s; row0 = (long long)P.h_mel_off[seq] * cfg.spf; rows = (long long)T * cfg.spf; ld = ch = 1; }
   else if (name == "s_stft") {
     // tensor-core modes keep only the operand-typed rows (kSpecOp wide)
-    src = h->use_tc ? w.spec_op : (const void*)w.spec; row0 = P.h_off[2][seq]; rows = 120LL * T + 1;
+    src = h->use_tc ? w.spec_op : (const void*)w.spec; row0 = P.h_off[LL][seq]; rows = last_rows;
     ld = h->use_tc ? kSpecOp : kSpecCh; ch = kNfft + 2; elem = h->use_tc ? h->act_elem : (int)ELEM_F32;
   }
-  else if (name == "conv_post") { src = w.post; row0 = P.h_off[2][seq]; rows = 120LL * T + 1; ld = kSpecCh; ch = kNfft + 2; }
+  else if (name == "conv_post") { src = w.post; row0 = P.h_off[LL][seq]; rows = last_rows; ld = kSpecCh; ch = kNfft + 2; }
   else if (name == "conv_pre") { src = w.xpre; row0 = P.h_offM[seq]; rows = T; ld = ch = kBase; }
-  else if (name.size() == 4 && name.compare(0, 3, "ups") == 0) level(name[3] - '0', w.U[name[3] - '0'], ELEM_F32);
-  else if (name.size() == 2 && name[0] == 'x') level(name[1] - '0', w.X[name[1] - '0'], ELEM_F32);
-  else if (name.size() == 6 && name.compare(0, 5, "stage") == 0) level(name[5] - '0', w.Y[name[5] - '0'], ELEM_F32);
-  else if (name.size() == 5 && name.compare(0, 4, "act0") == 0) level(name[4] - '0', w.A[name[4] - '0'][0], h->act_elem);
-  else { set_error("vt_hift_read_tap: unknown tap '%s'", tap); return VT_ERR_INVALID; }
-  if (name.size() >= 2 && (name[name.size() - 1] < '0' || name[name.size() - 1] > '2') &&
-      (name.compare(0, 3, "ups") == 0 || name[0] == 'x' || name.compare(0, 5, "stage") == 0)) {
-    set_error("vt_hift_read_tap: bad level in '%s'", tap);
-    return VT_ERR_INVALID;
+  else {
+    // per-level taps: ups<l>, x<l>, stage<l>, act0<l>
+    const int lv = name.empty() ? -1 : name[name.size() - 1] - '0';
+    const std::string stem = name.substr(0, name.size() ? name.size() - 1 : 0);
+    if (lv < 0 || lv > LL || (stem != "ups" && stem != "x" && stem != "stage" && stem != "act0")) {
+      set_error("vt_hift_read_tap: unknown tap '%s' (levels 0..%d)", tap, LL);
+      return VT_ERR_INVALID;
+    }
+    if (stem == "ups") level(lv, w.U[lv], ELEM_F32);
+    else if (stem == "x") level(lv, w.X[lv], ELEM_F32);
+    else if (stem == "stage") level(lv, w.Y[lv], ELEM_F32);
+    else level(lv, w.A[lv][0], h->act_elem);
   }
   const int64_t n = rows * ch;
   if (!out) return n;

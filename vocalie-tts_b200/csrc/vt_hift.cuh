@@ -26,13 +26,29 @@ constexpr int kMel = 80;
 constexpr int kBase = 512;
 constexpr int kF0Ch = 512;
 constexpr int kHarm = 9;           // nb_harmonics + 1
-constexpr int kSPF = 480;          // samples per mel frame
+constexpr int kMaxLevels = 3;      // upsampling stages of the generator (2 or 3)
 constexpr int kNfft = 16;
 constexpr int kHop = 4;
 constexpr int kSpecCh = 32;        // 18 STFT / conv_post channels padded to 32 (zeros)
 constexpr int kSpecOp = 24;        // STFT operand rows of the tensor-core source_downs: 18 channels + 6 zeros (48 B)
 constexpr int kMelOp = 128;        // mel operand rows: 80 channels + 48 zeros
 constexpr int kTileQ = 64;         // output steps per tile of the CUDA-core conv kernel
+
+// Constructor arguments of upstream HiFTGenerator that differ between its users (Chatterbox S3Gen: rates 8/5/3 at 24 kHz,
+// tts_backends/chatterbox_impl.py:189; CosyVoice-300M: rates 8/8 at 22.05 kHz, tts_backends/cosyvoice_runner.py:75-131).
+struct HiftCfg {
+  int n_levels = 3;
+  int sr = 24000;
+  int up_rate[kMaxLevels] = {8, 5, 3};
+  int up_kernel[kMaxLevels] = {16, 11, 7};
+  int src_rb_kernel[kMaxLevels] = {7, 7, 11};
+  int trim_fade = 1;                  // S3Token2Wav tail (Chatterbox): first sr/50 samples zeroed, next sr/50 faded in
+  // derived
+  int level_mul[kMaxLevels] = {8, 40, 120};   // steps per mel frame at each level
+  int sd_k[kMaxLevels] = {30, 6, 1}, sd_s[kMaxLevels] = {15, 3, 1}, sd_p[kMaxLevels] = {7, 1, 0};   // source_downs
+  int spf = 480;                      // samples per mel frame = level_mul[last] * hop
+  int trim_n = 480;                   // sr / 50
+};
 
 enum ActKind : int { ACT_NONE = 0, ACT_SNAKE = 1, ACT_LRELU = 2, ACT_ELU = 3 };
 enum ElemKind : int { ELEM_F32 = 0, ELEM_F16 = 1, ELEM_BF16 = 2 };
@@ -119,14 +135,14 @@ int launch_gemm_tc(const ConvArgs& a, const ConvLayer& L, int act_elem, cudaStre
 int launch_f0_head(const float* h, const float* w, const float* b, float* f0, long long rows, cudaStream_t st);
 int launch_sine_source(const float* f0, const int* mel_off, const int* T, int B, long long total_T,
                        const float* phase_vec, const float* noise, unsigned long long seed,
-                       const float* lin_w, const float* lin_b, double* phase_base, float* s, cudaStream_t st);
+                       const float* lin_w, const float* lin_b, double* phase_base, float* s, int spf, int sr, cudaStream_t st);
 int launch_stft(const float* s, const int* mel_off, const int* T, const long long* off2, int B, long long total_T,
-                float* spec, void* spec_op, int op_elem, cudaStream_t st);
+                float* spec, void* spec_op, int op_elem, int spf, cudaStream_t st);
 // mel fp32 [total_T][80] -> two fp16 terms [gapped rows][128] (hi, lo), channels 80..127 zero
 int launch_pack_mel(const float* mel, const int* mel_off, const int* T, const long long* offM, int B, long long total_T,
                     void* mel_hi, void* mel_lo, cudaStream_t st);
 // Spectral head (vt_head.cu): conv_post output -> exp/sin -> iSTFT -> clamp -> trim_fade
 int launch_istft_head(const float* post, const int* mel_off, const int* T, const long long* off2, int B,
-                      int T_max, const float* trim_fade, float* wav, cudaStream_t st);
+                      int T_max, const float* trim_fade, int trim_len, int spf, float* wav, cudaStream_t st);
 
 }  // namespace vt

@@ -41,13 +41,13 @@ int launch_f0_head(const float* h, const float* w, const float* b, float* f0, lo
 // (SURVEY A.4 [probe]).  F is constant inside a mel frame, so the fp64 prefix at sample j of
 // frame t is base[t] + (j+1)*F with base[t] = sum_{t'<t} 480*F(t') (exact products in fp64);
 // it is rounded to fp32 *before* the mod-1 exactly like the reference.
-__device__ __forceinline__ float harmonic_inc(float f0, int h) {
+__device__ __forceinline__ float harmonic_inc(float f0, int h, float sr) {
   // upstream: F_mat = f0 * (i + 1) / sampling_rate   (fp32 mul, then fp32 div)
-  return __fdiv_rn(__fmul_rn(f0, (float)(h + 1)), 24000.0f);
+  return __fdiv_rn(__fmul_rn(f0, (float)(h + 1)), sr);
 }
 
 __global__ void k_phase_base(const float* __restrict__ f0, const int* __restrict__ mel_off,
-                             const int* __restrict__ T, int B, long long total_T, double* __restrict__ base) {
+                             const int* __restrict__ T, int B, long long total_T, double* __restrict__ base, int spf, float sr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * kHarm) return;
   const int b = i / kHarm, h = i % kHarm;
@@ -56,10 +56,10 @@ __global__ void k_phase_base(const float* __restrict__ f0, const int* __restrict
   double* dst = base + (long long)h * total_T + o;
   double* inc = dst + (long long)kHarm * total_T;      // second half of the buffer: the per-frame increment itself
   for (int t = 0; t < T[b]; ++t) {
-    const double d = (double)harmonic_inc(f0[o + t], h);
+    const double d = (double)harmonic_inc(f0[o + t], h, sr);
     dst[t] = acc;
     inc[t] = d;                                          // (k_sine_source: no IEEE division per sample and harmonic)
-    acc += (double)kSPF * d;
+    acc += (double)spf * d;
   }
 }
 
@@ -99,11 +99,10 @@ __global__ void __launch_bounds__(256)
 k_sine_source(const float* __restrict__ f0, const int* __restrict__ mel_off, const int* __restrict__ T, int B,
               long long total_T, const float* __restrict__ phase_vec, const float* __restrict__ noise,
               unsigned long long seed, const float* __restrict__ lin_w, const float* __restrict__ lin_b,
-              const double* __restrict__ base, float* __restrict__ s) {
-  static_assert(kSPF % 4 == 0, "a sample quad must not straddle a frame");
+              const double* __restrict__ base, float* __restrict__ s, int spf) {
   const int b = blockIdx.y;
   const long long o = mel_off[b];
-  const long long L = (long long)T[b] * kSPF;
+  const long long L = (long long)T[b] * spf;
   const float lb = lin_b[0];
   float lw[kHarm], pv[kHarm];
 #pragma unroll
@@ -121,20 +120,20 @@ k_sine_source(const float* __restrict__ f0, const int* __restrict__ mel_off, con
     for (int h = 1; h < kHarm; ++h) pv[h] = ((float)rr[h - 1] * 2.3283064365386963e-10f * 2.0f - 1.0f) * 3.14159265358979f;
   }
   for (long long n = 4 * ((long long)blockIdx.x * blockDim.x + threadIdx.x); n < L; n += 4 * (long long)gridDim.x * blockDim.x) {
-    const int t = (int)(n / kSPF), j = (int)(n - (long long)t * kSPF);
+    const int t = (int)(n / spf), j = (int)(n - (long long)t * spf);
     const float f = f0[o + t];
     const bool voiced = f > 10.0f;
     const float uv = voiced ? 1.0f : 0.0f;
     // upstream: noise_amp = uv * noise_std + (1 - uv) * sine_amp / 3
     // (uv in {0, 1}: both values are exact compile-time constants of the same fp32 expression)
     const float namp = voiced ? 0.003f : 0.1f / 3.0f;
-    const unsigned long long gi = (unsigned long long)(o * kSPF + n) >> 2;      // global index of the quad
+    const unsigned long long gi = (unsigned long long)(o * spf + n) >> 2;      // global index of the quad
     float acc[4] = {lb, lb, lb, lb};
 #pragma unroll
     for (int h = 0; h < kHarm; ++h) {
       float z[4];
       if (noise) {
-        const float4 zz = *reinterpret_cast<const float4*>(noise + (o * kSPF) * kHarm + (long long)h * L + n);
+        const float4 zz = *reinterpret_cast<const float4*>(noise + (o * spf) * kHarm + (long long)h * L + n);
         z[0] = zz.x; z[1] = zz.y; z[2] = zz.z; z[3] = zz.w;
       } else {
         const uint4 r = philox4x32(make_uint4((unsigned)gi, (unsigned)(gi >> 32), (unsigned)h, 0xA5u), key);
@@ -154,22 +153,23 @@ k_sine_source(const float* __restrict__ f0, const int* __restrict__ mel_off, con
         acc[q] = fmaf(v, lw[h], acc[q]);
       }
     }
-    *reinterpret_cast<float4*>(s + o * kSPF + n) = make_float4(tanhf(acc[0]), tanhf(acc[1]), tanhf(acc[2]), tanhf(acc[3]));
+    *reinterpret_cast<float4*>(s + o * spf + n) = make_float4(tanhf(acc[0]), tanhf(acc[1]), tanhf(acc[2]), tanhf(acc[3]));
   }
 }
 
 int launch_sine_source(const float* f0, const int* mel_off, const int* T, int B, long long total_T,
                        const float* phase_vec, const float* noise, unsigned long long seed,
-                       const float* lin_w, const float* lin_b, double* phase_base, float* s, cudaStream_t st) {
+                       const float* lin_w, const float* lin_b, double* phase_base, float* s, int spf, int sr, cudaStream_t st) {
   if (B == 0 || total_T == 0) return VT_OK;
-  k_phase_base<<<(B * kHarm + 63) / 64, 64, 0, st>>>(f0, mel_off, T, B, total_T, phase_base);
+  VT_REQUIRE(spf % 4 == 0, "samples per frame must be a multiple of 4 (a sample quad must not straddle a frame)");
+  k_phase_base<<<(B * kHarm + 63) / 64, 64, 0, st>>>(f0, mel_off, T, B, total_T, phase_base, spf, (float)sr);
   VT_LAUNCHED();
   // grid.x sized for the longest sequence (grid-stride inside, four samples per thread): aim at ~148*8 blocks in total
   int gx = (148 * 8 + B - 1) / B;
   if (gx < 1) gx = 1;
   dim3 grid(gx, B);
   k_sine_source<<<grid, 256, 0, st>>>(f0, mel_off, T, B, total_T, phase_vec, noise, seed, lin_w, lin_b,
-                                      phase_base, s);
+                                      phase_base, s, spf);
   VT_LAUNCHED();
   return VT_OK;
 }
@@ -193,11 +193,11 @@ template <> __device__ __forceinline__ unsigned pack2_op<__nv_bfloat16>(float a,
 template <typename OpT>
 __global__ void __launch_bounds__(256)
 k_stft(const float* __restrict__ s, const int* __restrict__ mel_off, const int* __restrict__ T,
-       const long long* __restrict__ off2, int B, float* __restrict__ spec, OpT* __restrict__ spec_op) {
+       const long long* __restrict__ off2, int B, float* __restrict__ spec, OpT* __restrict__ spec_op, int spf) {
   const int b = blockIdx.y;
-  const long long L = (long long)T[b] * kSPF;
+  const long long L = (long long)T[b] * spf;
   const long long frames = L / kHop + 1;
-  const float* sb = s + (long long)mel_off[b] * kSPF;
+  const float* sb = s + (long long)mel_off[b] * spf;
   for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < frames; f += (long long)gridDim.x * blockDim.x) {
     float x[kNfft];
 #pragma unroll
@@ -239,14 +239,14 @@ k_stft(const float* __restrict__ s, const int* __restrict__ mel_off, const int* 
 }
 
 int launch_stft(const float* s, const int* mel_off, const int* T, const long long* off2, int B, long long total_T,
-                float* spec, void* spec_op, int op_elem, cudaStream_t st) {
+                float* spec, void* spec_op, int op_elem, int spf, cudaStream_t st) {
   if (B == 0 || total_T == 0) return VT_OK;
   int gx = (148 * 8 + B - 1) / B;
   dim3 grid(gx < 1 ? 1 : gx, B);
   if (spec_op && op_elem == ELEM_BF16)
-    k_stft<__nv_bfloat16><<<grid, 256, 0, st>>>(s, mel_off, T, off2, B, spec, reinterpret_cast<__nv_bfloat16*>(spec_op));
+    k_stft<__nv_bfloat16><<<grid, 256, 0, st>>>(s, mel_off, T, off2, B, spec, reinterpret_cast<__nv_bfloat16*>(spec_op), spf);
   else
-    k_stft<__half><<<grid, 256, 0, st>>>(s, mel_off, T, off2, B, spec, reinterpret_cast<__half*>(spec_op));
+    k_stft<__half><<<grid, 256, 0, st>>>(s, mel_off, T, off2, B, spec, reinterpret_cast<__half*>(spec_op), spf);
   VT_LAUNCHED();
   return VT_OK;
 }

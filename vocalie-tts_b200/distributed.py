@@ -184,7 +184,6 @@ class ShardedJob:
 
     def __init__(self, pipe, T_all: Sequence[int], shards: Sequence[Sequence[int]], *, group=None):
         import torch.distributed as dist
-        from .hift import SAMPLES_PER_FRAME
         from . import post as _post
         if pipe.granularity != "job":
             raise ValueError("ShardedJob runs the reference order: build the pipeline with granularity='job'")
@@ -202,7 +201,7 @@ class ShardedJob:
         if not gap_on:
             pipe.stitch_head = pipe.stitch_tail = 1          # plain concatenate: no fades anywhere (tts_pipeline.py:171-172)
             pipe.opts = dict(o, chunk_gap_ms=0)
-        self.lens = self.T_all * SAMPLES_PER_FRAME
+        self.lens = self.T_all * pipe.spf
         self.n_raw = final_length(self.lens, self.gap)
         self.raw_pieces = stitched_pieces(self.lens, self.gap, self.shards)
         self.local_T = self.T_all[np.asarray(self.shards[self.rank], dtype=np.int64)].astype(np.int32)
@@ -215,15 +214,14 @@ class ShardedJob:
         """``mel``: this rank's chunks, float32 CUDA [sum(local_T), 80].  ``max_frames`` bounds the mel frames per
         vocoder call (length bucketing of long jobs, HiFTVocoder.forward_bucketed)."""
         import torch
-        from .hift import SAMPLES_PER_FRAME
         pipe = self.pipe
         T = self.local_T
-        n = int(T.astype(np.int64).sum()) * SAMPLES_PER_FRAME
+        n = int(T.astype(np.int64).sum()) * pipe.spf
         with torch.cuda.device(pipe.voc.device):
             wav = pipe._buf("_wav", n + 4, torch.float32)
             if T.size:
                 pipe.voc.forward_bucketed(mel, T, f0=f0, phase_vec=phase_vec, noise=noise, seed=seed, out=wav, max_frames=max_frames)
-            seg_off = np.concatenate([[0], np.cumsum(T.astype(np.int64) * SAMPLES_PER_FRAME)])
+            seg_off = np.concatenate([[0], np.cumsum(T.astype(np.int64) * pipe.spf)])
             res = self.post_device(wav, seg_off, out=out)
             from . import post as _post
             pipe.last_launches = (pipe.voc.last_launches + _post.last_launch_count() - pipe.voc._last_call_launches) if T.size \

@@ -25,6 +25,41 @@ N_HARMONICS = 9
 
 OPERANDS = {"fp16": _lib.VT_OPERAND_FP16, "bf16": _lib.VT_OPERAND_BF16, "fp32": _lib.VT_OPERAND_FP32}
 
+# Constructor arguments of upstream HiFTGenerator per consumer (the module class is the same: Chatterbox's hifigan.py is
+# CosyVoice's cosyvoice/hifigan/generator.py).  "chatterbox_s3gen": S3Token2Wav.__init__.  "cosyvoice_300m":
+# the `hift:` block of CosyVoice-300M's cosyvoice.yaml - the engine behind tts_backends/cosyvoice_runner.py:75-131 at its
+# default 22 050 Hz (:84,131).
+GENERATOR_CONFIGS = {
+    "chatterbox_s3gen": dict(sampling_rate=24000, upsample_rates=(8, 5, 3), upsample_kernel_sizes=(16, 11, 7),
+                             source_resblock_kernel_sizes=(7, 7, 11), trim_fade=True),
+    "cosyvoice_300m": dict(sampling_rate=22050, upsample_rates=(8, 8), upsample_kernel_sizes=(16, 16),
+                           source_resblock_kernel_sizes=(7, 11), trim_fade=False),
+}
+
+
+def resolve_config(config) -> dict:
+    if config is None:
+        config = "chatterbox_s3gen"
+    if isinstance(config, str):
+        if config not in GENERATOR_CONFIGS:
+            raise ValueError(f"unknown generator config {config!r} (known: {sorted(GENERATOR_CONFIGS)})")
+        config = GENERATOR_CONFIGS[config]
+    cfg = dict(GENERATOR_CONFIGS["chatterbox_s3gen"], **{k: config[k] for k in config})
+    n = len(cfg["upsample_rates"])
+    if n not in (2, 3) or len(cfg["upsample_kernel_sizes"]) != n or len(cfg["source_resblock_kernel_sizes"]) != n:
+        raise ValueError("generator config: 2 or 3 upsampling stages with matching kernel-size lists are supported")
+    return cfg
+
+
+def source_down_shapes(upsample_rates):
+    """(k, stride, pad) of source_downs[i] - upstream HiFTGenerator.__init__: stride = product of the later rates;
+    1 -> Conv1d(k=1), else Conv1d(k=2u, stride=u, padding=u//2)."""
+    out = []
+    for i in range(len(upsample_rates)):
+        u = int(np.prod(upsample_rates[i + 1:])) if i + 1 < len(upsample_rates) else 1
+        out.append((1, 1, 0) if u == 1 else (2 * u, u, u // 2))
+    return out
+
 
 def _torch():
     import torch
@@ -62,22 +97,25 @@ def fold_weight_norm(state_dict: Dict[str, "object"]) -> Dict[str, np.ndarray]:
     return out
 
 
-def algorithmic_flops_per_frame(include_f0: bool = True) -> float:
-    """2*MAC of every conv of the path per mel frame (612.45 MFLOP with the F0 predictor)."""
+def algorithmic_flops_per_frame(include_f0: bool = True, config=None) -> float:
+    """2*MAC of every conv of the path per mel frame (612.45 MFLOP with the F0 predictor for Chatterbox)."""
+    cfg = resolve_config(config)
+    rates, kernels, src_k = cfg["upsample_rates"], cfg["upsample_kernel_sizes"], cfg["source_resblock_kernel_sizes"]
     f = 0.0
     if include_f0:
         f += 2 * (80 * 512 * 3 + 4 * 512 * 512 * 3 + 512)
     f += 2 * 80 * 512 * 7
-    ups = [(512, 256, 16, 1), (256, 128, 11, 8), (128, 64, 7, 40)]      # (cin, cout, k, input steps per frame)
-    for cin, cout, k, steps in ups:
-        f += 2 * cin * cout * k * steps
-    for (k, cout, steps) in ((30, 256, 8), (6, 128, 40), (1, 64, 120)):
-        f += 2 * 18 * cout * k * steps
-    for stage, (c, steps) in enumerate(((256, 8), (128, 40), (64, 120))):
-        f += 6 * 2 * c * c * (7, 7, 11)[stage] * steps
-        for k in (3, 7, 11):
-            f += 6 * 2 * c * c * k * steps
-    f += 2 * 64 * 18 * 7 * 120
+    steps = 1                                   # input steps per frame of the stage's transposed conv
+    sds = source_down_shapes(rates)
+    for i, (u, k) in enumerate(zip(rates, kernels)):
+        cin, c = 512 >> i, 512 >> (i + 1)
+        f += 2 * cin * c * k * steps
+        steps *= u
+        f += 2 * 18 * c * sds[i][0] * steps
+        f += 6 * 2 * c * c * src_k[i] * steps
+        for rk in (3, 7, 11):
+            f += 6 * 2 * c * c * rk * steps
+    f += 2 * (512 >> len(rates)) * 18 * 7 * steps
     return f
 
 
@@ -89,11 +127,14 @@ class HiFTVocoder:
     parity bar), "bf16", or "fp32" (exact CUDA-core path).
     """
 
-    def __init__(self, state_dict, operand: str = "fp16"):
+    def __init__(self, state_dict, operand: str = "fp16", config=None):
+        """``config``: a name of ``GENERATOR_CONFIGS`` or a dict of HiFTGenerator constructor arguments
+        (default: Chatterbox S3Gen)."""
         torch = _torch()
         if operand not in OPERANDS:
             raise ValueError(f"operand must be one of {sorted(OPERANDS)}")
         self.operand = operand
+        self.config = resolve_config(config)
         self._lib = _lib.load_library()
         sm, major, minor = C.c_int(), C.c_int(), C.c_int()
         check(self._lib.vt_device_check(C.byref(sm), C.byref(major), C.byref(minor)), "vt_device_check")
@@ -115,8 +156,18 @@ class HiFTVocoder:
             for d in range(a.ndim):
                 arr[i].shape[d] = a.shape[d]
         h = C.c_void_p()
-        check(self._lib.vt_hift_create(arr, len(names), OPERANDS[operand], C.byref(h)), "vt_hift_create")
+        cc = _lib.HiftConfig()
+        cc.sampling_rate = int(self.config["sampling_rate"])
+        cc.n_upsamples = len(self.config["upsample_rates"])
+        for i in range(cc.n_upsamples):
+            cc.upsample_rates[i] = int(self.config["upsample_rates"][i])
+            cc.upsample_kernel_sizes[i] = int(self.config["upsample_kernel_sizes"][i])
+            cc.source_resblock_kernel_sizes[i] = int(self.config["source_resblock_kernel_sizes"][i])
+        cc.trim_fade = 1 if self.config["trim_fade"] else 0
+        check(self._lib.vt_hift_create_ex(arr, len(names), OPERANDS[operand], C.byref(cc), C.byref(h)), "vt_hift_create_ex")
         self._h = h
+        self.samples_per_frame = int(self._lib.vt_hift_samples_per_frame(h))
+        self.sr = int(self._lib.vt_hift_sampling_rate(h))
         self._ws = None
         self._lock = threading.Lock()   # reference jobs run on up to 2 threads (backend/config.py:11)
         self.device = torch.device("cuda", torch.cuda.current_device())
@@ -170,12 +221,12 @@ class HiFTVocoder:
             raise ValueError("mel must be a float32 CUDA tensor of shape [sum(T), 80]")
         mel = mel.contiguous()
         for name, t, n in (("f0", f0, total_T), ("phase_vec", phase_vec, B * N_HARMONICS),
-                           ("noise", noise, total_T * SAMPLES_PER_FRAME * N_HARMONICS)):
+                           ("noise", noise, total_T * self.samples_per_frame * N_HARMONICS)):
             if t is not None and (t.dtype != torch.float32 or not t.is_cuda or t.numel() != n or not t.is_contiguous()):
                 raise ValueError(f"{name} must be a contiguous float32 CUDA tensor with {n} elements")
         if out is None:
-            out = torch.empty(total_T * SAMPLES_PER_FRAME, dtype=torch.float32, device=self.device)
-        elif out.numel() < total_T * SAMPLES_PER_FRAME or out.dtype != torch.float32 or not out.is_cuda:
+            out = torch.empty(total_T * self.samples_per_frame, dtype=torch.float32, device=self.device)
+        elif out.numel() < total_T * self.samples_per_frame or out.dtype != torch.float32 or not out.is_cuda:
             raise ValueError("out must be a float32 CUDA tensor with 480*sum(T) elements")
         with self._lock:
             ws = self._workspace(torch, self.workspace_bytes(B, total_T, int(T.max()) if B else 0))
@@ -201,7 +252,7 @@ class HiFTVocoder:
         if max_frames is None or total_T <= max_frames or T.size <= 1:
             return self.forward_packed(mel, T, f0=f0, phase_vec=phase_vec, noise=noise, seed=seed, out=out)
         if out is None:
-            out = torch.empty(total_T * SAMPLES_PER_FRAME, dtype=torch.float32, device=self.device)
+            out = torch.empty(total_T * self.samples_per_frame, dtype=torch.float32, device=self.device)
         off = np.concatenate([[0], np.cumsum(T.astype(np.int64))])
         b0 = 0
         launches = 0
@@ -212,9 +263,9 @@ class HiFTVocoder:
             f_lo, f_hi = int(off[b0]), int(off[b1])
             self.forward_packed(mel[f_lo:f_hi], T[b0:b1], f0=None if f0 is None else f0[f_lo:f_hi],
                                 phase_vec=None if phase_vec is None else phase_vec.reshape(-1, N_HARMONICS)[b0:b1].contiguous(),
-                                noise=None if noise is None else noise.reshape(-1)[f_lo * SAMPLES_PER_FRAME * N_HARMONICS:
-                                                                                  f_hi * SAMPLES_PER_FRAME * N_HARMONICS],
-                                seed=seed + b0, out=out[f_lo * SAMPLES_PER_FRAME:f_hi * SAMPLES_PER_FRAME])
+                                noise=None if noise is None else noise.reshape(-1)[f_lo * self.samples_per_frame * N_HARMONICS:
+                                                                                  f_hi * self.samples_per_frame * N_HARMONICS],
+                                seed=seed + b0, out=out[f_lo * self.samples_per_frame:f_hi * self.samples_per_frame])
             launches += self.last_launches
             b0 = b1
         self.last_launches = launches          # all buckets (the library's own counter restarts with every call)
@@ -229,7 +280,7 @@ class HiFTVocoder:
         pv = None if phase_vec is None else torch.stack([p.reshape(-1) for p in phase_vec]).to(self.device, torch.float32).contiguous()
         nz = None if noise is None else torch.cat([n.reshape(-1).to(self.device, torch.float32) for n in noise]).contiguous()
         wav = self.forward_packed(mel, T, f0=f0p, phase_vec=pv, noise=nz, seed=seed)
-        off = np.concatenate([[0], np.cumsum(T.astype(np.int64) * SAMPLES_PER_FRAME)])
+        off = np.concatenate([[0], np.cumsum(T.astype(np.int64) * self.samples_per_frame)])
         return [wav[off[i]:off[i + 1]] for i in range(len(T))]
 
     def set_profiling(self, enable: bool = True):
@@ -265,7 +316,7 @@ class HiFTVocoder:
         return out[:n].view(-1, channels)
 
 
-def random_state_dict(seed: int = 0) -> Dict[str, np.ndarray]:
+def random_state_dict(seed: int = 0, config=None) -> Dict[str, np.ndarray]:
     """Random-init HiFT weights in upstream state-dict naming (benchmarks and smoke tests - there
     is no network to fetch ``ResembleAI/chatterbox``'s ``s3gen`` checkpoint).  Follows upstream
     initialisation (SURVEY 8(d) W_init): ``normal(0, 0.01)`` on the weight-normed convs of ups /
@@ -273,6 +324,9 @@ def random_state_dict(seed: int = 0) -> Dict[str, np.ndarray]:
     weight-norm gain ``g = ||v||``."""
     rng = np.random.default_rng(seed)
     sd: Dict[str, np.ndarray] = {}
+    cfg = resolve_config(config)
+    rates, up_k, src_k = cfg["upsample_rates"], cfg["upsample_kernel_sizes"], cfg["source_resblock_kernel_sizes"]
+    sds = source_down_shapes(rates)
 
     def conv(name, cout, cin, k, normal, wn=True, transposed=False):
         shape = (cin, cout, k) if transposed else (cout, cin, k)
@@ -289,12 +343,13 @@ def random_state_dict(seed: int = 0) -> Dict[str, np.ndarray]:
         sd[name + ".bias"] = (rng.uniform(-1, 1, cout).astype(np.float32) / np.float32(np.sqrt(fan_in)))
 
     conv("conv_pre", 512, 80, 7, False)
-    for i, (k, (sk, cout)) in enumerate(zip((16, 11, 7), ((30, 256), (6, 128), (1, 64)))):
+    for i, k in enumerate(up_k):
+        cout = 512 >> (i + 1)
         conv(f"ups.{i}", cout, 512 >> i, k, True, transposed=True)
-        conv(f"source_downs.{i}", cout, 18, sk, False, wn=False)
+        conv(f"source_downs.{i}", cout, 18, sds[i][0], False, wn=False)
         for j in range(3):
             for c12 in ("convs1", "convs2"):
-                conv(f"source_resblocks.{i}.{c12}.{j}", cout, cout, (7, 7, 11)[i], True)
+                conv(f"source_resblocks.{i}.{c12}.{j}", cout, cout, src_k[i], True)
             for a in ("activations1", "activations2"):
                 sd[f"source_resblocks.{i}.{a}.{j}.alpha"] = np.ones(cout, np.float32)
         for kk, rk in enumerate((3, 7, 11)):
@@ -304,7 +359,7 @@ def random_state_dict(seed: int = 0) -> Dict[str, np.ndarray]:
                     conv(f"resblocks.{r}.{c12}.{j}", cout, cout, rk, True)
                 for a in ("activations1", "activations2"):
                     sd[f"resblocks.{r}.{a}.{j}.alpha"] = np.ones(cout, np.float32)
-    conv("conv_post", 18, 64, 7, True)
+    conv("conv_post", 18, 512 >> len(rates), 7, True)
     for i in range(5):
         conv(f"f0_predictor.condnet.{2 * i}", 512, 80 if i == 0 else 512, 3, False)
     sd["f0_predictor.classifier.weight"] = rng.uniform(-1, 1, (1, 512)).astype(np.float32) / np.float32(np.sqrt(512))

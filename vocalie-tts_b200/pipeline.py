@@ -59,7 +59,8 @@ class VocoderPipeline:
         if edit not in ("minimal_edit", "minimal_post_process"):
             raise ValueError("edit must be 'minimal_edit' or 'minimal_post_process'")
         self.voc = vocoder
-        self.sr = S3GEN_SR
+        self.sr = int(getattr(vocoder, "sr", S3GEN_SR))                       # 24 000 for Chatterbox, 22 050 for CosyVoice-300M
+        self.spf = int(getattr(vocoder, "samples_per_frame", SAMPLES_PER_FRAME))
         self.granularity = granularity
         self.edit = edit
         self.opts = dict(chunk_gap_ms=int(chunk_gap_ms), trim_silence=bool(trim_silence), normalize=bool(normalize),
@@ -146,7 +147,7 @@ class VocoderPipeline:
         """Worst-case output samples of a job with mel lengths ``T`` (what submit() stages)."""
         T = np.asarray(T)
         gap = _post._ms_to_frames(self.sr, self.opts["chunk_gap_ms"])
-        return int(T.astype(np.int64).sum()) * SAMPLES_PER_FRAME + len(T) * gap
+        return int(T.astype(np.int64).sum()) * self.spf + len(T) * gap
 
     # ------------------------------------------------------------------ device path
     def _buf(self, name, n, dtype):
@@ -163,11 +164,11 @@ class VocoderPipeline:
         frames per vocoder call (length bucketing of long jobs, HiFTVocoder.forward_bucketed)."""
         torch = _torch()
         T = np.ascontiguousarray(T, dtype=np.int32)
-        n = int(T.astype(np.int64).sum()) * SAMPLES_PER_FRAME
+        n = int(T.astype(np.int64).sum()) * self.spf
         with torch.cuda.device(self.voc.device):
             wav = self.voc.forward_bucketed(mel, T, f0=f0, phase_vec=phase_vec, noise=noise, seed=seed,
                                             out=self._buf("_wav", n + 4, torch.float32), max_frames=max_frames)
-            seg_off = np.concatenate([[0], np.cumsum(T.astype(np.int64) * SAMPLES_PER_FRAME)])
+            seg_off = np.concatenate([[0], np.cumsum(T.astype(np.int64) * self.spf)])
             res = self.post_device(wav, seg_off, read_back=read_back)
             # the library's per-thread launch counter restarts with every vt_hift_forward and keeps counting through the
             # post calls: kernels of this job = all vocoder buckets + what the post calls added to the last one
