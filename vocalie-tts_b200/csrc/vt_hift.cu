@@ -134,16 +134,28 @@ int dev_upload(vt_hift* h, const void* src, size_t bytes, void** out) {
 
 // Per-output-channel power-of-two scaling of the tensor-core weight images.  fp16 operands lose precision below
 // 6.1e-5 (subnormals) and a trained checkpoint's weight-normed rows can sit orders of magnitude apart (w = g v / ||v||
-// with a per-row gain g), so row c of the packed weights holds s_c * w with s_c = 2^-e the power of two that brings
-// max|row| into [0.5, 1): exact in every format, the accumulators come out as s_c * (W a) and the epilogues undo it for
-// free in the FMA that adds the bias (ConvArgs::wscale = 1 / s_c).  `w` is [k][cin_pad][ncol] and is scaled IN PLACE
-// (callers pass a copy: the fp32 CUDA-core path keeps the unscaled weights).
+// with a per-row gain g).  A LAYER is scaled only if one of its rows needs it - max|row| below 2^-8 (its typical elements
+// then approach the subnormal range) or above 2^10: then every row c holds s_c * w with s_c = 2^-e the power of two that
+// brings max|row| into [0.5, 1) - exact in every format - the accumulators come out as s_c * (W a) and the epilogues undo
+// it in the FMA that adds the bias (ConvArgs::wscale = 1 / s_c).  Layers inside the comfortable range keep s = 1 and their
+// kernels' unscaled instances.  `w` is [k][cin_pad][ncol] and is scaled IN PLACE (callers pass a copy: the fp32 CUDA-core
+// path keeps the plain weights).
 int scale_weight_rows(vt_hift* h, ConvLayer& L, std::vector<float>& w, int k, int cin_pad, int ncol) {
-  std::vector<float> inv(ncol, 1.0f);
+  std::vector<float> inv(ncol, 1.0f), rowmax(ncol, 0.0f);
+  bool need = false;
   for (int co = 0; co < ncol; ++co) {
     float m = 0.0f;
     for (int j = 0; j < k; ++j)
       for (int ci = 0; ci < cin_pad; ++ci) m = std::max(m, std::fabs(w[((size_t)j * cin_pad + ci) * ncol + co]));
+    rowmax[co] = m;
+    if (m > 0.0f && std::isfinite(m) && (m < 0.00390625f || m > 1024.0f)) need = true;
+  }
+  static const char* force = getenv("VT_WSCALE");               // VT_WSCALE=1: scale every layer (tests), 0: never
+  if (force && force[0] == '1') need = true;
+  if (force && force[0] == '0') need = false;
+  L.scaled = need;
+  for (int co = 0; co < ncol && need; ++co) {
+    const float m = rowmax[co];
     if (!(m > 0.0f) || !std::isfinite(m)) continue;
     int e = 0;
     std::frexp(m, &e);                       // m = f * 2^e, f in [0.5, 1)

@@ -116,7 +116,8 @@ struct ConvLayer {
   int out_mul = 1, phase_c = 0;     // transposed convs run as a k'=3 conv with cout = s*C_out
   float* w = nullptr;               // device [k][cin][cout] fp32
   float* bias = nullptr;            // device [cout]
-  float* wscale = nullptr;          // device [cout]: 1 / (power-of-two row scale of the tensor-core weight images)
+  float* wscale = nullptr;          // device [cout]: 1 / (power-of-two row scale of the tensor-core weight images); ones if !scaled
+  bool scaled = false;              // some row of this layer needed a scale (fp16-subnormal or near-overflow weights)
   void* w_tp = nullptr;             // device, tap-pair image for the C = 64 pair kernel (vt_pair64_tc.cu)
   void* w_tc = nullptr;             // device, tensor-core operand packing (vt_conv_tc.cu)
   unsigned long long tap_skip = 0;  // all-zero (column tile, tap) pairs of a phase-decomposed transposed conv

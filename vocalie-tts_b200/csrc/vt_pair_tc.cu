@@ -93,7 +93,12 @@ template <> __device__ __forceinline__ unsigned short to_op_bits<__nv_bfloat16>(
   return __bfloat16_as_ushort(__float2bfloat16_rn(v));
 }
 
-template <int C, int NBUF, int NA1, int NA2, int W_ST, int NEPI, int NPROD, int NSLAB, int EM, bool kPreload, bool TR, typename ActT>
+// WS: the packed weights of this pair carry per-output-channel power-of-two scales (ConvArgs::wscale / PairArgs::wscale1)
+// that the epilogues undo.  A layer only gets scaled rows when it needs them (vt_hift.cu scale_weight_rows), so the
+// common instance (WS = false) pays nothing: the activation-major epilogues fetch per-channel constants from shared memory
+// for every element group, and one more vector there costs 6-9 % of a C = 64 launch (and 40-70 % on the accumulate
+// variants, whose fin passes run at the register cap).
+template <int C, int NBUF, int NA1, int NA2, int W_ST, int NEPI, int NPROD, int NSLAB, int EM, bool kPreload, bool TR, bool WS, typename ActT>
 __global__ void __launch_bounds__(PairCfg<C, NBUF, NEPI, NPROD, TR>::WARPS * 32, 1)
 k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
   using PC = PairCfg<C, NBUF, NEPI, NPROD, TR>;
@@ -128,9 +133,9 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
   uint64_t* w_full = d2i_full + NBUF;
   uint64_t* w_empty = w_full + W_ST;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_empty + W_ST);
-  float* prm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(tmem_slot) + 16);   // al1 | ia1 | b1 | al2 | ia2 | ws1
+  float* prm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(tmem_slot) + 16);   // al1 | ia1 | b1 | al2 | ia2 | ws1 | ws2 | 1 / ws2
   // fin staging (32 x kStageLd floats per warp): its own region, or the idle A2 tile in combined mode
-  float* stage_all = kCombined ? reinterpret_cast<float*>(sA2) : prm + 6 * C;
+  float* stage_all = kCombined ? reinterpret_cast<float*>(sA2) : prm + 8 * C;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -149,7 +154,11 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
     const float a1 = p.alpha1[c], a2 = p.alpha2[c];
     prm[c] = a1; prm[C + c] = __fdividef(1.0f, a1 + 1e-9f); prm[2 * C + c] = p.bias1[c];
     prm[3 * C + c] = a2; prm[4 * C + c] = __fdividef(1.0f, a2 + 1e-9f);
-    prm[5 * C + c] = p.wscale1[c];
+    if constexpr (WS) {
+      prm[5 * C + c] = p.wscale1[c];
+      const float w2 = a.wscale[c];
+      prm[6 * C + c] = w2; prm[7 * C + c] = __frcp_rn(w2);     // shared memory: the fin passes must not wait on global loads
+    }
   }
   if (warp == W_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
@@ -397,7 +406,7 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
     const int c = quarter * 32 + lane;                                   // this thread's channel
     const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
     if (!is_fin) {
-      const float b1 = prm[2 * C + c], al2 = prm[3 * C + c], ia2 = prm[4 * C + c], ws1 = prm[5 * C + c];
+      const float b1 = prm[2 * C + c], al2 = prm[3 * C + c], ia2 = prm[4 * C + c], ws1 = WS ? prm[5 * C + c] : 1.0f;
       // A2 element (row r, channel c): 64-channel block, 16-byte chunk XOR-swizzled by the row, 2 bytes inside
       const uint32_t coff = (uint32_t)(c >> 6) * (uint32_t)(kPairRA2 * 128) + (uint32_t)((c & 7) * 2);
       const uint32_t chunk = (uint32_t)((c & 63) >> 3);
@@ -432,7 +441,7 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
       }
     } else {
       constexpr bool kRes2 = (EM & EM_RES2) != 0, kAccum = (EM & EM_ACCUM) != 0;
-      const float b2 = a.bias[c], ws2 = a.wscale[c];
+      const float b2 = a.bias[c], ws2 = WS ? a.wscale[c] : 1.0f;
       const bool accum = kAccum && a.out_accum;
       const float inv = 1.0f / a.out_scale;
       const uint32_t d2 = tmem_base + lane_sel + (uint32_t)ACC_COLS;
@@ -543,8 +552,8 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
       blk_geom(tl, blk, mb, c0, idx0, nvalid);
       const float4 bias = *reinterpret_cast<const float4*>(a.bias + c0 + sub * 4);
       // conv2 accumulates s_c * (W2 a) on top of the preload, so the preload is s_c * (x + b2 + ...): exact (power of two)
-      const float4 wsq = *reinterpret_cast<const float4*>(a.wscale + c0 + sub * 4);
-      const float4 sc = make_float4(__frcp_rn(wsq.x), __frcp_rn(wsq.y), __frcp_rn(wsq.z), __frcp_rn(wsq.w));
+      float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
+      if constexpr (WS) sc = *reinterpret_cast<const float4*>(prm + 7 * C + c0 + sub * 4);
       const bool accum = kAccum && a.out_accum;
       const float inv = 1.0f / a.out_scale;
 #pragma unroll
@@ -561,7 +570,7 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
             const float4 pv = *reinterpret_cast<const float4*>(a.out + idx);
             t.x = fmaf(pv.x, inv, t.x); t.y = fmaf(pv.y, inv, t.y); t.z = fmaf(pv.z, inv, t.z); t.w = fmaf(pv.w, inv, t.w);
           }
-          t.x *= sc.x; t.y *= sc.y; t.z *= sc.z; t.w *= sc.w;
+          if constexpr (WS) { t.x *= sc.x; t.y *= sc.y; t.z *= sc.z; t.w *= sc.w; }
         }
         *reinterpret_cast<float4*>(stage + (q * 4 + rsub) * kStageLd + sub * 4) = t;
       }
@@ -594,8 +603,11 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
       }
       __syncwarp();
       if (!(a.dbg & 8)) {
-        const float4 wsq = *reinterpret_cast<const float4*>(a.wscale + c0 + sub * 4);
-        const float4 osc = make_float4(wsq.x * a.out_scale, wsq.y * a.out_scale, wsq.z * a.out_scale, wsq.w * a.out_scale);
+        float4 osc = make_float4(a.out_scale, a.out_scale, a.out_scale, a.out_scale);
+        if constexpr (WS) {
+          const float4 wsq = *reinterpret_cast<const float4*>(prm + 6 * C + c0 + sub * 4);
+          osc = make_float4(wsq.x * a.out_scale, wsq.y * a.out_scale, wsq.z * a.out_scale, wsq.w * a.out_scale);
+        }
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           if (4 * q >= nvalid) continue;
@@ -646,7 +658,7 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
       __syncwarp();
       if (!(a.dbg & 8)) {
         const float4 bias = *reinterpret_cast<const float4*>(a.bias + c0 + sub * 4);
-        const float4 wsq = *reinterpret_cast<const float4*>(a.wscale + c0 + sub * 4);
+        const float4 wsq = WS ? *reinterpret_cast<const float4*>(prm + 6 * C + c0 + sub * 4) : make_float4(1.f, 1.f, 1.f, 1.f);
         const bool accum = kAccum && a.out_accum;
         const float inv = 1.0f / a.out_scale;
 #pragma unroll
@@ -726,7 +738,7 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
               const float4 bb = *reinterpret_cast<const float4*>(prm + 2 * C + c);
               const float4 aa = *reinterpret_cast<const float4*>(prm + 3 * C + c);
               const float4 ii = *reinterpret_cast<const float4*>(prm + 4 * C + c);
-              const float4 ww = *reinterpret_cast<const float4*>(prm + 5 * C + c);
+              const float4 ww = WS ? *reinterpret_cast<const float4*>(prm + 5 * C + c) : make_float4(1.f, 1.f, 1.f, 1.f);
               y[hh * 4 + 0] = snake_f(fmaf(__uint_as_float(v[g * 8 + hh * 4 + 0]), ww.x, bb.x), aa.x, ii.x);
               y[hh * 4 + 1] = snake_f(fmaf(__uint_as_float(v[g * 8 + hh * 4 + 1]), ww.y, bb.y), aa.y, ii.y);
               y[hh * 4 + 2] = snake_f(fmaf(__uint_as_float(v[g * 8 + hh * 4 + 2]), ww.z, bb.z), aa.z, ii.z);
@@ -787,18 +799,18 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
   }
 }
 
-template <int C, int NBUF, int NA1, int NA2, int W_ST, int NEPI, int NPROD, int NSLAB, int EM, bool kPreload, bool TR, typename ActT>
-int launch_pair_em(const ConvArgs& a, const PairArgs& p, uint32_t idesc, int grid, cudaStream_t st) {
+template <int C, int NBUF, int NA1, int NA2, int W_ST, int NEPI, int NPROD, int NSLAB, int EM, bool kPreload, bool TR, bool WS, typename ActT>
+int launch_pair_ws(const ConvArgs& a, const PairArgs& p, uint32_t idesc, int grid, cudaStream_t st) {
   constexpr int CB = C / 64;
   using PC = PairCfg<C, NBUF, NEPI, NPROD, TR>;
   constexpr int smem = CB * (NA1 * kPairRA1 + NA2 * kPairRA2) * 128 + W_ST * C * 128 + NSLAB * 8192 +
-                       (2 * NA1 + 2 * NA2 + 2 * NSLAB + 4 * NBUF + 2 * W_ST) * 8 + 16 + 6 * C * 4 +
+                       (2 * NA1 + 2 * NA2 + 2 * NSLAB + 4 * NBUF + 2 * W_ST) * 8 + 16 + 8 * C * 4 +
                        ((PC::kCombined || TR) ? 0 : NEPI * 32 * kStageLd * 4);
   static_assert(smem <= 232448, "shared memory budget exceeded");
   static_assert(!PC::kCombined || NEPI * 32 * kStageLd * 4 <= CB * kPairRA2 * 128, "fin staging must fit the A2 tile");
   static bool configured = false;
   if (!configured) {
-    VT_CUDA_OK(cudaFuncSetAttribute(k_pair_tc<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, kPreload, TR, ActT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    VT_CUDA_OK(cudaFuncSetAttribute(k_pair_tc<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, kPreload, TR, WS, ActT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   if (a.mc) {
@@ -808,12 +820,20 @@ int launch_pair_em(const ConvArgs& a, const PairArgs& p, uint32_t idesc, int gri
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    VT_CUDA_OK(cudaLaunchKernelEx(&cfg, k_pair_tc<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, kPreload, TR, ActT>, a, p, idesc));
+    VT_CUDA_OK(cudaLaunchKernelEx(&cfg, k_pair_tc<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, kPreload, TR, WS, ActT>, a, p, idesc));
   } else {
-    k_pair_tc<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, kPreload, TR, ActT><<<grid, PC::WARPS * 32, smem, st>>>(a, p, idesc);
+    k_pair_tc<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, kPreload, TR, WS, ActT><<<grid, PC::WARPS * 32, smem, st>>>(a, p, idesc);
   }
   VT_LAUNCHED();
   return VT_OK;
+}
+
+template <int C, int NBUF, int NA1, int NA2, int W_ST, int NEPI, int NPROD, int NSLAB, int EM, bool kPreload, bool TR, typename ActT>
+int launch_pair_em(const ConvArgs& a, const PairArgs& p, uint32_t idesc, int grid, cudaStream_t st) {
+  // a.wscale / p.wscale1 are null when neither conv of the pair has scaled weight rows
+  if (a.wscale && p.wscale1)
+    return launch_pair_ws<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, kPreload, TR, true, ActT>(a, p, idesc, grid, st);
+  return launch_pair_ws<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, kPreload, TR, false, ActT>(a, p, idesc, grid, st);
 }
 
 template <int C, int NBUF, int NA1, int NA2, int W_ST, int NEPI, int NPROD, int NSLAB, int EM, typename ActT>
@@ -875,8 +895,11 @@ int launch_pair_tc(const ConvArgs& a_in, const ConvLayer& c1, const ConvLayer& c
   a.cout = c2.cout; a.phase_c = c2.cout; a.out_mul = 1; a.out_shift = 0; a.dup_row2 = 0;
   PairArgs p{};
   p.x_in = a.res1;
-  p.alpha1 = alpha1; p.alpha2 = alpha2; p.bias1 = c1.bias; p.wscale1 = c1.wscale;
-  a.wscale = c2.wscale;
+  p.alpha1 = alpha1; p.alpha2 = alpha2; p.bias1 = c1.bias;
+  // scaled weight rows in either conv -> the WS instance (an unscaled partner carries a vector of ones)
+  const bool ws = c1.scaled || c2.scaled;
+  p.wscale1 = ws ? c1.wscale : nullptr;
+  a.wscale = ws ? c2.wscale : nullptr;
   p.w1 = reinterpret_cast<const uint8_t*>(c1.w_tc);
   p.w2 = reinterpret_cast<const uint8_t*>(c2.w_tc);
   p.k = c1.k; p.dil = c1.dil;
