@@ -68,6 +68,8 @@ k_convT_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ide
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();                             // dependents may be scheduled (they take an SM when its CTA of this grid exits)
+  if (warp != W_WP) pdl_wait();                // everything but the (static) weight stream waits for the previous kernel
   const int n_tiles = a.n_tiles;
 
   if (warp >= W_AP) {
@@ -273,7 +275,7 @@ int launch_convT_em(const ConvArgs& a, const void* wtc, uint32_t idesc, int grid
     VT_CUDA_OK(cudaFuncSetAttribute(k_convT_tc<C, EM, ActT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  k_convT_tc<C, EM, ActT><<<grid, (kTEpi + 2 + kProdWarps) * 32, smem, st>>>(a, reinterpret_cast<const uint8_t*>(wtc), idesc);
+  VT_CUDA_OK(launch_pdl(k_convT_tc<C, EM, ActT>, dim3((unsigned)grid), dim3((kTEpi + 2 + kProdWarps) * 32), (size_t)smem, st, a, reinterpret_cast<const uint8_t*>(wtc), idesc));
   VT_LAUNCHED();
   return VT_OK;
 }

@@ -76,6 +76,8 @@ k_conv_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ides
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();                             // dependents may be scheduled (they take an SM when its CTA of this grid exits)
+  if (warp != W_WP) pdl_wait();                // everything but the (static) weight stream waits for the previous kernel
 
   const int nchunks = a.k * CB;                 // weight chunks per tile
   const int n_nt = a.cout / NT;                 // column tiles
@@ -253,8 +255,8 @@ int launch_em(const ConvArgs& a, const void* wtc, uint32_t idesc, int grid, cuda
                                     cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     configured = true;
   }
-  k_conv_tc<CIN, NT, MB, A_ST, W_ST, NEPI, HALO, EM, ActT><<<grid, (NEPI + 2 + kProdWarps) * 32, smem, st>>>(
-      a, reinterpret_cast<const uint8_t*>(wtc), idesc);
+  VT_CUDA_OK(launch_pdl(k_conv_tc<CIN, NT, MB, A_ST, W_ST, NEPI, HALO, EM, ActT>, dim3((unsigned)grid), dim3((NEPI + 2 + kProdWarps) * 32),
+                        (size_t)smem, st, a, reinterpret_cast<const uint8_t*>(wtc), idesc));
   VT_LAUNCHED();
   return VT_OK;
 }

@@ -64,6 +64,8 @@ k_gemm_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const KBlock* __res
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();                             // dependents may be scheduled (they take an SM when its CTA of this grid exits)
+  if (warp != W_WP) pdl_wait();                // everything but the (static) weight stream waits for the previous kernel
 
   const int n_nt = a.cout / NT;
   const int n_tiles = a.n_tiles * n_nt;            // (row tile, column tile), column tile fastest
@@ -184,8 +186,8 @@ int launch_gemm_em(const ConvArgs& a, const ConvLayer& L, uint32_t idesc, int gr
     VT_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc<NT, MB, ST, NEPI, EM, ActT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  k_gemm_tc<NT, MB, ST, NEPI, EM, ActT><<<grid, (NEPI + 2 + kProdWarps) * 32, smem, st>>>(
-      a, reinterpret_cast<const uint8_t*>(L.w_gemm), reinterpret_cast<const KBlock*>(L.d_kb), L.n_kb, idesc);
+  VT_CUDA_OK(launch_pdl(k_gemm_tc<NT, MB, ST, NEPI, EM, ActT>, dim3((unsigned)grid), dim3((NEPI + 2 + kProdWarps) * 32), (size_t)smem, st,
+                        a, reinterpret_cast<const uint8_t*>(L.w_gemm), reinterpret_cast<const KBlock*>(L.d_kb), L.n_kb, idesc));
   VT_LAUNCHED();
   return VT_OK;
 }

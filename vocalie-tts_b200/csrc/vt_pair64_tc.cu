@@ -120,6 +120,8 @@ __global__ void __launch_bounds__(kP64Warps * 32, 1) k_pair64_tc(const ConvArgs 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();                             // dependents may be scheduled (they take an SM when its CTA of this grid exits)
+  if (warp != kP64W_LD) pdl_wait();                // everything but the (static) weight stream waits for the previous kernel
 
   const int n_tiles = a.n_tiles;
   const int n_my = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -511,7 +513,7 @@ int launch_pair64_na(const ConvArgs& a, const PairArgs& p, uint32_t idesc, int g
     VT_CUDA_OK(cudaFuncSetAttribute(k_pair64_tc<EM, NA1, ActT>, cudaFuncAttributeMaxDynamicSharedMemorySize, P64Cfg<NA1>::kSmem));
     configured = true;
   }
-  k_pair64_tc<EM, NA1, ActT><<<grid, kP64Warps * 32, P64Cfg<NA1>::kSmem, st>>>(a, p, idesc);
+  VT_CUDA_OK(launch_pdl(k_pair64_tc<EM, NA1, ActT>, dim3((unsigned)grid), dim3(kP64Warps * 32), (size_t)P64Cfg<NA1>::kSmem, st, a, p, idesc));
   VT_LAUNCHED();
   return VT_OK;
 }

@@ -169,6 +169,9 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();                             // dependents may be scheduled (they take an SM when its CTA of this grid exits)
+  if (!(warp == W_WP && lane == 0)) pdl_wait();   // everything but the (static) weight stream waits for the previous kernel
+                                                  // (at C = 64 the x loader is lane 1 of the weight loader's warp: it waits)
   // Weight multicast (a.mc): the two CTAs of a cluster walk the same weight sequence in lockstep, each fetching half
   // of every ring slot for both.  They must run the same number of tiles: an odd tile count is padded with a dummy
   // (the last tile again with n = 0: every store of the epilogues is masked by n).
@@ -822,7 +825,7 @@ int launch_pair_ws(const ConvArgs& a, const PairArgs& p, uint32_t idesc, int gri
     cfg.attrs = at; cfg.numAttrs = 1;
     VT_CUDA_OK(cudaLaunchKernelEx(&cfg, k_pair_tc<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, kPreload, TR, WS, ActT>, a, p, idesc));
   } else {
-    k_pair_tc<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, kPreload, TR, WS, ActT><<<grid, PC::WARPS * 32, smem, st>>>(a, p, idesc);
+    VT_CUDA_OK(launch_pdl(k_pair_tc<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, kPreload, TR, WS, ActT>, dim3((unsigned)grid), dim3(PC::WARPS * 32), smem, st, a, p, idesc));
   }
   VT_LAUNCHED();
   return VT_OK;

@@ -4,6 +4,9 @@
 #pragma once
 #include "vt_hift.cuh"
 
+#include <cstdlib>
+#include <utility>
+
 namespace vt {
 
 // One ResBlock iteration run as a fused pair (vt_pair_tc.cu, vt_pair64_tc.cu)
@@ -118,6 +121,15 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Programmatic dependent launch: consecutive tensor-core kernels of a forward are launched with programmatic stream
+// serialisation, every CTA signals at once that its dependents may be scheduled, and every role that reads what the
+// previous kernel wrote waits for that kernel's completion - AFTER barrier initialisation, TMEM allocation and parameter
+// staging, while the weight loader (static data) already fills its ring.  The persistent kernels hold an SM each, so the
+// next kernel's CTA starts on an SM the moment this kernel's CTA leaves it: launch latency, prologue and the tail of the
+// slowest SMs overlap (measured gap between dependent launches: ~12 us x 68 launches per forward).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -224,6 +236,19 @@ template <> struct Pack4<__nv_bfloat16> {
     return make_uint2(*reinterpret_cast<unsigned*>(&a), *reinterpret_cast<unsigned*>(&b));
   }
 };
+
+// Host side: launch with the programmatic-serialisation attribute (VT_PDL=0 restores plain launches for A/B timing).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  static const bool on = !(getenv("VT_PDL") && getenv("VT_PDL")[0] == '0');
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = on ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 constexpr int kStageLd = 36;   // floats per staged row (32 + 4 pad: conflict-free 16-byte accesses both ways)
 
