@@ -326,7 +326,10 @@ def run_ours(args, rank, world, local_rank):
     job = D.ShardedJob(pipe, T_all, shards) if world > 1 else None
     n_raw = D.final_length(T_all * SPF, GAP_MS * SR // 1000)
     finals = [torch.empty(n_raw + 8, dtype=torch.int16, device=dev) for _ in range(2)] if (world > 1 and rank == 0) else [None, None]
-    host_finals = [torch.empty(n_raw + 8, dtype=torch.int16).pin_memory() for _ in range(2)] if (world > 1 and rank == 0) else None
+    # e2e at N > 1: two host buffers shared by the ranks of the node (/dev/shm, page-locked in every process): every rank
+    # copies its own part of the file over its own PCIe link, nothing crosses NVLink and rank 0 reads nothing back
+    host_files = [D.SharedHostBuffer(f"vocalie_b200_bench_{os.environ.get('MASTER_PORT', '0')}_{i}", n_raw + 8, torch.int16)
+                  for i in range(2)] if world > 1 else None
 
     def step_device(seed, slot=0):
         if world == 1:
@@ -335,13 +338,13 @@ def run_ours(args, rank, world, local_rank):
         r = job.run_device(mel_dev, seed=seed, out=finals[slot], max_frames=max_frames)
         return r, r.total_samples
 
-    copy_stream = torch.cuda.Stream(device=dev)
-    copied = [torch.cuda.Event(), torch.cuda.Event()]
+    e2e_jobs = [0]
 
     def e2e_loop(steps, seed0):
         """Host mels in, host PCM_16 audio out, `steps` jobs back to back.  One GPU: the public VocoderPipeline.submit()
-        / collect().  Several GPUs: every rank uploads its mels, the sharded job runs, rank 0 reads the assembled file
-        back on a second stream while the next job computes (two output slots)."""
+        / collect().  Several GPUs: every rank uploads its mels, the sharded job runs, and every rank copies ITS pieces of
+        the finished PCM_16 file device -> host into a buffer shared by the ranks (asynchronously, on a side stream, while
+        the next job computes; two buffers).  `d2h_bytes_per_step` is the whole file (the sum over ranks)."""
         if world == 1:
             pending = None
             for i in range(steps):
@@ -356,25 +359,23 @@ def run_ours(args, rank, world, local_rank):
                 pipe.collect(pending)
                 return pipe.last_d2h_bytes
             return n_raw * 2
-        cur = torch.cuda.current_stream()
-        d2h = 0
+        base = e2e_jobs[0]
         for i in range(steps):
-            slot = i & 1
-            if rank == 0:
-                cur.wait_event(copied[slot])          # the slot's previous file has left the device
             mel_dev.copy_(mel_host, non_blocking=True)
-            _, total = step_device(seed0 + i, slot)
-            if rank == 0:
-                ready = torch.cuda.Event()
-                ready.record(cur)
-                with torch.cuda.stream(copy_stream):
-                    copy_stream.wait_event(ready)
-                    host_finals[slot][:total].copy_(finals[slot][:total], non_blocking=True)
-                    copied[slot].record(copy_stream)
-                d2h = total * 2
-        copy_stream.synchronize()
-        cur.synchronize()
-        return d2h
+            r = job.run_device(mel_dev, seed=seed0 + i, max_frames=max_frames, host_out=host_files[(base + i) & 1].tensor)
+            if i > 0:
+                # job i-1: this rank's copies have landed long ago (they ran under job i's... predecessor's compute); tell
+                # the others, and let rank 0 - the consumer of the file - see it complete before its buffer is reused
+                job.wait_host(previous=True)
+                host_files[(base + i - 1) & 1].publish(base + i - 1)
+                if rank == 0:
+                    host_files[(base + i - 1) & 1].wait_complete(base + i - 1)
+        job.wait_host()
+        host_files[(base + steps - 1) & 1].publish(base + steps - 1)
+        host_files[(base + steps - 1) & 1].wait_complete(base + steps - 1)
+        e2e_jobs[0] = base + steps
+        torch.cuda.current_stream().synchronize()
+        return r.total_samples * 2
 
     def barrier():
         if world > 1:
@@ -432,6 +433,9 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = audio_s_job / (float(te.item()) * 1e-3)
 
+    if host_files:
+        for hf in host_files:
+            hf.close()
     if rank != 0:
         return
     hbm, tf_sus, tf_burst, how = peaks()
@@ -467,7 +471,8 @@ def run_ours(args, rank, world, local_rank):
                    "f0": "predicted (ConvRNNF0Predictor)", "noise": "in-kernel Philox", "output": "PCM_16",
                    "l2": "flushed between timed steps (256 MB write); per-step activations >> L2",
                    "exchange": "int64[3] all-reduce (file trim range + peak), then grouped ncclSend/ncclRecv of every rank's part "
-                               "straight into its place on rank 0" if world > 1 else "none"},
+                               "straight into its place on rank 0 (value); e2e: every rank copies its part device->host into "
+                               "a host buffer shared by the ranks" if world > 1 else "none"},
         "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(mel_host.numel() * 4 * world),
                 "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),

@@ -57,6 +57,18 @@ def main():
                         and res.edit["end_sample"] == ref.edit["end_sample"]
                 ok_all = ok_all and ok
                 print(f"sharded-check world={world} {mode} {kw or 'trim+normalise'}: {'OK' if ok else 'MISMATCH'} ({got.numel()} samples)", flush=True)
+            # the same job assembled on the HOST: every rank copies its own pieces into a buffer shared by the ranks
+            shared = D.SharedHostBuffer(f"vocalie_b200_check_{os.environ.get('MASTER_PORT', '0')}", job.n_raw + 8, torch.int16)
+            res_h = job.run_device(mel, host_out=shared.tensor, **loc)
+            job.wait_host()
+            shared.publish(0)
+            shared.wait_complete(0)
+            if rank == 0:
+                got_h = shared.tensor[: res_h.total_samples].clone()
+                ok = res_h.total_samples == want.numel() and bool(torch.equal(got_h, want.cpu()))
+                ok_all = ok_all and ok
+                print(f"sharded-check world={world} {mode} {kw or 'trim+normalise'} host-assembled: {'OK' if ok else 'MISMATCH'}", flush=True)
+            shared.close()
     if rank == 0:
         print("SHARDED-CHECK", "PASS" if ok_all else "FAIL", flush=True)
     dist.barrier()

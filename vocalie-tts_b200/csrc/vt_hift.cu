@@ -71,6 +71,10 @@ struct Plan {
   std::vector<int> h_mel_off;
   void* d_block = nullptr;
   size_t d_block_bytes = 0;
+  void* h_block = nullptr;                  // pinned staging of d_block (the upload is asynchronous)
+  size_t h_block_bytes = 0;
+  cudaEvent_t done = nullptr;               // recorded after the last forward that used this plan
+  unsigned long long last_use = 0;
 };
 
 struct Workspace {
@@ -100,7 +104,9 @@ struct vt_hift {
   ConvLayer conv_pre, ups[3], sdown[3], src_c1[3][3], src_c2[3][3], rb_c1[9][3], rb_c2[9][3], conv_post, f0c[5];
   float *src_a1[3][3], *src_a2[3][3], *rb_a1[9][3], *rb_a2[9][3];
   float *f0_w = nullptr, *f0_b = nullptr, *lin_w = nullptr, *lin_b = nullptr, *trim_fade = nullptr;
-  Plan plan;
+  Plan plan;                                // the plan of the current / last forward
+  std::vector<Plan> plan_cache;             // recently used plans (a long job runs a handful of bucket shapes over and over)
+  unsigned long long plan_tick = 0;
   Workspace ws{};
   bool fuse[3] = {false, false, false};     // level runs its ResBlock pairs on the fused kernel (vt_pair_tc.cu)
   bool pair64_last = false;                 // VT_PAIR64=all: also the last pair of each ResBlock
@@ -307,9 +313,36 @@ void add_tiles(std::vector<ConvTile>& v, Plan::Seg& seg, int B, const long long*
   seg.n = (int)v.size() - seg.off;
 }
 
+void free_plan(Plan& P) {
+  if (P.d_block) cudaFree(P.d_block);
+  if (P.h_block) cudaFreeHost(P.h_block);
+  if (P.done) cudaEventDestroy(P.done);
+  P = Plan();
+}
+
+constexpr size_t kPlanCache = 7;            // + the current one: 8 batch shapes stay resident
+
 int build_plan(vt_hift* h, const int32_t* T, int B, cudaStream_t st) {
+  auto matches = [&](const Plan& q) { return q.B == B && (int)q.T.size() == B && std::equal(q.T.begin(), q.T.end(), T); };
+  if (matches(h->plan)) { h->plan.last_use = ++h->plan_tick; return VT_OK; }
+  for (auto& c : h->plan_cache)
+    if (matches(c)) { std::swap(h->plan, c); h->plan.last_use = ++h->plan_tick; return VT_OK; }
+  // miss: the current plan retires into the cache; the least recently used one gives its blocks to the new plan
+  if (h->plan.B > 0) h->plan_cache.push_back(std::move(h->plan));
+  h->plan = Plan();
+  if (h->plan_cache.size() > kPlanCache) {
+    size_t lru = 0;
+    for (size_t i = 1; i < h->plan_cache.size(); ++i)
+      if (h->plan_cache[i].last_use < h->plan_cache[lru].last_use) lru = i;
+    Plan old = std::move(h->plan_cache[lru]);
+    h->plan_cache.erase(h->plan_cache.begin() + lru);
+    if (old.done) VT_CUDA_OK(cudaEventSynchronize(old.done));      // kernels and the upload that used its blocks are finished
+    h->plan.d_block = old.d_block; h->plan.d_block_bytes = old.d_block_bytes;
+    h->plan.h_block = old.h_block; h->plan.h_block_bytes = old.h_block_bytes;
+    h->plan.done = old.done;
+  }
   Plan& P = h->plan;
-  if (P.B == B && (int)P.T.size() == B && std::equal(P.T.begin(), P.T.end(), T)) return VT_OK;
+  P.last_use = ++h->plan_tick;
   P.B = B;
   P.T.assign(T, T + B);
   P.total_T = 0;
@@ -374,15 +407,25 @@ int build_plan(vt_hift* h, const int32_t* T, int B, cudaStream_t st) {
   // one device block: T | mel_off | off[3] | tiles
   const size_t nI = align_up((size_t)B * 4, 256), nL = align_up((size_t)B * 8, 256);
   const size_t bytes = 2 * nI + 4 * nL + align_up(tiles.size() * sizeof(ConvTile), 256);
+  // blocks grow geometrically (a recycled plan rarely needs a new allocation: cudaFree / cudaMalloc synchronise the device)
+  const size_t cap = align_up(bytes + bytes / 2, (size_t)1 << 20);
   if (bytes > P.d_block_bytes) {
     if (P.d_block) cudaFree(P.d_block);
     P.d_block = nullptr;
     P.d_block_bytes = 0;
-    VT_CUDA_OK(cudaMalloc(&P.d_block, bytes));
-    P.d_block_bytes = bytes;
+    VT_CUDA_OK(cudaMalloc(&P.d_block, cap));
+    P.d_block_bytes = cap;
   }
-  std::vector<char> host(bytes, 0);
-  char* hp = host.data();
+  if (bytes > P.h_block_bytes) {
+    if (P.h_block) cudaFreeHost(P.h_block);
+    P.h_block = nullptr;
+    P.h_block_bytes = 0;
+    VT_CUDA_OK(cudaMallocHost(&P.h_block, cap));
+    P.h_block_bytes = cap;
+  }
+  if (!P.done) VT_CUDA_OK(cudaEventCreateWithFlags(&P.done, cudaEventDisableTiming));
+  char* hp = (char*)P.h_block;
+  std::memset(hp, 0, bytes);
   char* dp = (char*)P.d_block;
   std::memcpy(hp, T, (size_t)B * 4); P.d_T = (int*)dp;
   std::memcpy(hp + nI, P.h_mel_off.data(), (size_t)B * 4); P.d_mel_off = (int*)(dp + nI);
@@ -394,9 +437,9 @@ int build_plan(vt_hift* h, const int32_t* T, int B, cudaStream_t st) {
   P.d_offM = (long long*)(dp + 2 * nI + 3 * nL);
   std::memcpy(hp + 2 * nI + 4 * nL, tiles.data(), tiles.size() * sizeof(ConvTile));
   P.d_tiles = (ConvTile*)(dp + 2 * nI + 4 * nL);
-  // synchronous copy: `host` dies at scope exit; plans are cached per shape so this is off the steady state
-  VT_CUDA_OK(cudaStreamSynchronize(st));
-  VT_CUDA_OK(cudaMemcpy(P.d_block, host.data(), bytes, cudaMemcpyHostToDevice));
+  // asynchronous upload from the plan's own pinned staging block: a new batch shape costs host time only, no stream
+  // synchronisation (a long job alternates between bucket shapes; `done` guards the blocks when a plan is recycled)
+  VT_CUDA_OK(cudaMemcpyAsync(P.d_block, P.h_block, bytes, cudaMemcpyHostToDevice, st));
   return VT_OK;
 }
 
@@ -670,7 +713,8 @@ int vt_hift_create_ex(const vt_tensor* tensors, int n_tensors, int operand_dtype
 void vt_hift_destroy(vt_hift* h) {
   if (!h) return;
   for (void* p : h->allocs) cudaFree(p);
-  if (h->plan.d_block) cudaFree(h->plan.d_block);
+  free_plan(h->plan);
+  for (auto& c : h->plan_cache) free_plan(c);
   for (int i = 0; i < 2; ++i) if (h->ev_fwd[i]) cudaEventDestroy(h->ev_fwd[i]);
   for (int l = 0; l < 3; ++l)
     for (int i = 0; i < 2; ++i) if (h->ev_rb[l][i]) cudaEventDestroy(h->ev_rb[l][i]);
@@ -969,6 +1013,7 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
   if (rc) return rc;
   mark(h, "istft_head", st);
   if (prof) VT_CUDA_OK(cudaEventRecord(h->ev_fwd[1], st));
+  VT_CUDA_OK(cudaEventRecord(h->plan.done, st));
   return VT_OK;
 }
 

@@ -153,6 +153,76 @@ def assemble_on_rank0(local_audio, local_lens: Sequence[int], chunk_ids: Sequenc
     return out, total
 
 
+class SharedHostBuffer:
+    """Host memory mapped by every rank of the node (a file under /dev/shm) and page-locked in each process
+    (cudaHostRegister): every rank copies ITS pieces of the finished file device -> host over its own PCIe link,
+    straight into place - no gather to rank 0, no single-link read-back of the whole job.  Rank 0 creates the file,
+    the others map it after a barrier; ``close`` unregisters and (rank 0) unlinks."""
+
+    def __init__(self, name: str, numel: int, dtype, *, group=None):
+        import os
+        import torch
+        import torch.distributed as dist
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.group = group
+        self.path = os.path.join("/dev/shm", name)
+        self.numel, self.dtype = int(numel), dtype
+        nbytes = self.numel * torch.empty(0, dtype=dtype).element_size()
+        if self.rank == 0:
+            with open(self.path, "wb") as f:
+                f.truncate(nbytes)
+        if dist.is_initialized():
+            dist.barrier(group)
+        self.tensor = torch.from_file(self.path, shared=True, size=self.numel, dtype=dtype)
+        # completion flags, one int64 per rank, in the same kind of mapping (plain host stores: no GPU synchronisation):
+        # flags[r] = index of the last job whose pieces rank r has finished copying
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if self.rank == 0:
+            with open(self.path + ".flags", "wb") as f:
+                f.write((-1).to_bytes(8, "little", signed=True) * self.world)
+        if dist.is_initialized():
+            dist.barrier(group)
+        self.flags = torch.from_file(self.path + ".flags", shared=True, size=self.world, dtype=torch.int64)
+        self._registered = False
+        if torch.cuda.is_available():
+            rc = torch.cuda.cudart().cudaHostRegister(self.tensor.data_ptr(), nbytes, 0)
+            if int(rc) != 0:
+                raise RuntimeError(f"cudaHostRegister failed with status {int(rc)}")
+            self._registered = True
+
+    def publish(self, job_index: int) -> None:
+        """This rank's pieces of job ``job_index`` are in the buffer (call after ShardedJob.wait_host())."""
+        self.flags[self.rank] = int(job_index)
+
+    def wait_complete(self, job_index: int, timeout_s: float = 60.0) -> None:
+        """Block (host-side polling of the shared flags) until EVERY rank has published ``job_index``."""
+        import time
+        t0 = time.monotonic()
+        while int(self.flags.min()) < int(job_index):
+            if time.monotonic() - t0 > timeout_s:
+                raise TimeoutError(f"host assembly of job {job_index} incomplete: flags {self.flags.tolist()}")
+            time.sleep(0.0002)
+
+    def close(self):
+        import os
+        import torch
+        import torch.distributed as dist
+        if self._registered:
+            torch.cuda.synchronize()
+            torch.cuda.cudart().cudaHostUnregister(self.tensor.data_ptr())
+            self._registered = False
+        self.tensor = None
+        self.flags = None
+        if dist.is_initialized():
+            dist.barrier(self.group)
+        if self.rank == 0:
+            for pth in (self.path, self.path + ".flags"):
+                try:
+                    os.unlink(pth)
+                except OSError:
+                    pass
+
+
 # ------------------------------------------------------------------------------------ reference order, sharded
 def merge_file_range(first_g: int, last_g: int, n_file: int, *, trim: bool, min_silence_frames: int) -> Tuple[int, int]:
     """``_find_active_range`` on the whole file from the merged extremes (tts_pipeline.py:192-209) followed by
@@ -210,7 +280,7 @@ class ShardedJob:
         self.min_sil = int(pipe.sr * (int(o["silence_min_ms"]) / 1000.0))
 
     def run_device(self, mel, *, f0=None, phase_vec=None, noise=None, seed: int = 0, out=None,
-                   max_frames: Optional[int] = None) -> ShardedJobResult:
+                   max_frames: Optional[int] = None, host_out=None) -> ShardedJobResult:
         """``mel``: this rank's chunks, float32 CUDA [sum(local_T), 80].  ``max_frames`` bounds the mel frames per
         vocoder call (length bucketing of long jobs, HiFTVocoder.forward_bucketed)."""
         import torch
@@ -222,16 +292,18 @@ class ShardedJob:
             if T.size:
                 pipe.voc.forward_bucketed(mel, T, f0=f0, phase_vec=phase_vec, noise=noise, seed=seed, out=wav, max_frames=max_frames)
             seg_off = np.concatenate([[0], np.cumsum(T.astype(np.int64) * pipe.spf)])
-            res = self.post_device(wav, seg_off, out=out)
+            res = self.post_device(wav, seg_off, out=out, host_out=host_out)
             from . import post as _post
             pipe.last_launches = (pipe.voc.last_launches + _post.last_launch_count() - pipe.voc._last_call_launches) if T.size \
                 else _post.last_launch_count()
         return res
 
-    def post_device(self, wav, seg_off, *, out=None, ops=None) -> ShardedJobResult:
+    def post_device(self, wav, seg_off, *, out=None, ops=None, host_out=None) -> ShardedJobResult:
         """Stitch -> (all-reduce -> whole-file edit) -> assembly, from this rank's packed raw chunks.  ``ops`` are the
         four device passes (default: the CUDA kernels; the gloo CPU tests inject the numpy oracle to exercise this
-        host logic without a GPU)."""
+        host logic without a GPU).  ``host_out`` (a 1-D host tensor every rank can write, e.g. SharedHostBuffer.tensor):
+        the file is assembled on the HOST instead - every rank copies its own pieces device -> host into place on a side
+        stream (asynchronously: ``wait_host()`` before reading) and nothing is gathered to rank 0."""
         import torch
         import torch.distributed as dist
         pipe = self.pipe
@@ -242,7 +314,11 @@ class ShardedJob:
         n_chunks = seg_off.size - 1
         n_local_raw = int(self.runs_off[-1])
         if not pipe.editing:
+            self._before_overwrite()
             local = ops.stitch(wav, seg_off, n_local_raw, final=True) if n_chunks else torch.zeros(0, device=dev)
+            if host_out is not None:
+                self._to_host(local, self.raw_pieces[self.rank], host_out)
+                return ShardedJobResult(None, self.n_raw, self.n_raw, None)
             final = assemble_pieces(local, self.raw_pieces, self.n_raw, group=self.group, out=out)
             return ShardedJobResult(final, self.n_raw, self.n_raw, None)
         stats = torch.tensor([-(1 << 62), -1, 0], dtype=torch.int64, device=dev)     # [-first, last, peak bits]
@@ -277,8 +353,13 @@ class ShardedJob:
             for i, (_, nrun, d0) in enumerate(self.raw_pieces[self.rank]):
                 s = min(max(start_g - d0, 0), nrun)
                 rng[i] = (s, min(max(end_g - d0, s), nrun))
+            self._before_overwrite()
             local = ops.edit(x, self.runs_off, rng, peak if o["normalize"] else 0.0)
-        final = assemble_pieces(local, pieces, total, group=self.group, out=out)
+        if host_out is not None:
+            self._to_host(local, pieces[self.rank], host_out)
+            final = None
+        else:
+            final = assemble_pieces(local, pieces, total, group=self.group, out=out)
         target_peak = 10 ** (o["target_dbfs"] / 20.0)
         normalized = bool(o["normalize"] and peak > 0.0 and target_peak > 0.0)
         edit = {"start_sample": start_g, "end_sample": end_g, "peak_before": peak,
@@ -286,6 +367,42 @@ class ShardedJob:
                 "trimmed": bool(o["trim_silence"] and 0 <= start_g < end_g <= self.n_raw), "normalized": normalized,
                 "target_dbfs": o["target_dbfs"], "edit": pipe.edit}
         return ShardedJobResult(final, total, self.n_raw, edit)
+
+
+    # ---- host assembly: this rank's pieces -> their place in a host buffer shared by the ranks, on a side stream
+    def _before_overwrite(self):
+        """The previous job's device->host copies read the buffer the next pass is about to overwrite."""
+        import torch
+        ev = getattr(self, "_copied", None)
+        if ev is not None and torch.cuda.is_available():
+            torch.cuda.current_stream().wait_event(ev)
+
+    def _to_host(self, local, pieces, host_out):
+        import torch
+        if not local.is_cuda:                                   # CPU tests
+            for src0, n, d0 in pieces:
+                if n > 0:
+                    host_out[d0:d0 + n].copy_(local[src0:src0 + n])
+            return
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=local.device)
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(ready)
+            for src0, n, d0 in pieces:
+                if n > 0:
+                    host_out[d0:d0 + n].copy_(local[src0:src0 + n], non_blocking=True)
+            self._copied_prev = getattr(self, "_copied", None)
+            self._copied = torch.cuda.Event()
+            self._copied.record(self._copy_stream)
+
+    def wait_host(self, previous: bool = False):
+        """Block until this rank's pieces of the last (``previous``: the one before the last) host-assembled job have
+        landed; then ``SharedHostBuffer.publish`` / ``wait_complete`` tell the ranks apart."""
+        ev = getattr(self, "_copied_prev" if previous else "_copied", None)
+        if ev is not None:
+            ev.synchronize()
 
 
 class _CudaOps:
