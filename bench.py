@@ -259,12 +259,39 @@ def run_torch_eager(args, rank, world):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / args.steps
         out[name] = {"value": n_chunks * T * SPF / SR / (ms * 1e-3), "ms_per_step": ms}
+    # the best the stock path can do: one batched call (equal-length chunks stack; the reference itself never batches)
+    Bn = 16
+    melB = torch.stack([H.synth_mel(T, 3, b) for b in range(Bn)]).to(dev)
+    pvB = torch.stack([H.synth_noise(T, 3, b)[0] for b in range(Bn)]).to(dev)
+    nzB = torch.randn(Bn, 9, T * SPF, device=dev)
+    tf = H.trim_fade(torch.float32).to(dev)
+    for name, ctx in (("fp32_batch16", None), ("bf16_autocast_batch16", torch.autocast("cuda", dtype=torch.bfloat16))):
+        def stepB():
+            import contextlib
+            with torch.inference_mode(), (ctx or contextlib.nullcontext()):
+                f0 = H.f0_predictor(melB, W)
+                s_ = H.sine_source(f0.float(), W, pvB, nzB)
+                y = H.decode(melB, s_, W).float()
+                y[:, : tf.numel()] *= tf
+                x = y.reshape(-1)
+                return (x * (10 ** (-1 / 20) / x.abs().max())).clamp_(-1, 1)
+        for _ in range(max(args.warmup, 2)):
+            stepB()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            stepB()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        out[name] = {"value": Bn * T * SPF / SR / (ms * 1e-3), "ms_per_step": ms}
     best = max(out.values(), key=lambda d: d["value"])
     print(json.dumps({"impl": "torch_eager", "metric": METRIC, "value": best["value"], "unit": "audio-s/s", "n_gpus": 1,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": best["ms_per_step"], "higher_is_better": True,
                       "data": "synthetic", "dtype": "f32 / bf16 autocast",
-                      "config": {"workload": f"stock PyTorch eager (cuDNN/cuFFT) HiFT restatement on cuda:0, {n_chunks} chunks x 10 s, "
-                                             "batch 1 per call like the reference"},
+                      "config": {"workload": f"stock PyTorch eager (cuDNN/cuFFT) HiFT restatement on cuda:0, 10 s chunks: {n_chunks} chunks at batch 1 per "
+                                             f"call like the reference, and one batched call of {Bn} chunks (value = the best variant)"},
                       "variants": out, "gpu_launches": 0}), flush=True)
 
 

@@ -341,6 +341,8 @@ def sine_source(f0, W, phase_vec, noise, cfg: "HiftConfig" = None):
 
 def stft_source(s):
     """upstream HiFTGenerator._stft: [B, L] -> real||imag [B, 18, L/4+1]."""
+    if s.dtype in (torch.bfloat16, torch.float16):
+        s = s.float()              # only under autocast (bench.py's stock-PyTorch GPU arm): cuFFT has no bf16
     win = torch.hann_window(N_FFT, periodic=True, dtype=s.dtype, device=s.device)
     spec = torch.stft(s, N_FFT, HOP, N_FFT, window=win, return_complex=True)
     return torch.cat([spec.real, spec.imag], dim=1)
@@ -348,6 +350,8 @@ def stft_source(s):
 
 def istft_head(mag, phase):
     """upstream HiFTGenerator._istft: clip(mag, max=100); mag*cos/sin(phase); torch.istft."""
+    if mag.dtype in (torch.bfloat16, torch.float16):
+        mag, phase = mag.float(), phase.float()          # autocast arm only (see stft_source)
     mag = torch.clip(mag, max=1e2)
     real = mag * torch.cos(phase)
     img = mag * torch.sin(phase)
