@@ -355,8 +355,23 @@ def run_ours(args, rank, world, local_rank):
     finals = [torch.empty(n_raw + 8, dtype=torch.int16, device=dev) for _ in range(2)] if (world > 1 and rank == 0) else [None, None]
     # e2e at N > 1: two host buffers shared by the ranks of the node (/dev/shm, page-locked in every process): every rank
     # copies its own part of the file over its own PCIe link, nothing crosses NVLink and rank 0 reads nothing back
-    host_files = [D.SharedHostBuffer(f"vocalie_b200_bench_{os.environ.get('MASTER_PORT', '0')}_{i}", n_raw + 8, torch.int16)
-                  for i in range(2)] if world > 1 else None
+    host_files, host_mode = None, "none"
+    if world > 1:
+        ok = 1
+        try:
+            host_files = [D.SharedHostBuffer(f"vocalie_b200_bench_{os.environ.get('MASTER_PORT', '0')}_{i}", n_raw + 8, torch.int16)
+                          for i in range(2)]
+        except Exception as exc:  # noqa: BLE001  (no /dev/shm or page-locking refused: fall back to the gather + rank-0 read-back)
+            print(f"[bench] rank {rank}: shared host buffer unavailable ({exc}); e2e uses the NCCL gather", file=sys.stderr, flush=True)
+            ok = 0
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            host_files = None
+        host_mode = "shared" if host_files else "gather"
+    gather_host = [torch.empty(n_raw + 8, dtype=torch.int16).pin_memory() for _ in range(2)] if (host_mode == "gather" and rank == 0) else None
+    gather_copied = [torch.cuda.Event(), torch.cuda.Event()]
+    gather_stream = torch.cuda.Stream(device=dev) if host_mode == "gather" else None
 
     def step_device(seed, slot=0):
         if world == 1:
@@ -386,6 +401,28 @@ def run_ours(args, rank, world, local_rank):
                 pipe.collect(pending)
                 return pipe.last_d2h_bytes
             return n_raw * 2
+        if host_mode == "gather":
+            # fallback: device assembly on rank 0 (grouped send / recv), rank 0 reads the file back on a second stream
+            cur = torch.cuda.current_stream()
+            total = 0
+            for i in range(steps):
+                slot = i & 1
+                if rank == 0:
+                    cur.wait_event(gather_copied[slot])
+                mel_dev.copy_(mel_host, non_blocking=True)
+                r = job.run_device(mel_dev, seed=seed0 + i, out=finals[slot], max_frames=max_frames)
+                total = r.total_samples
+                if rank == 0:
+                    ready = torch.cuda.Event()
+                    ready.record(cur)
+                    with torch.cuda.stream(gather_stream):
+                        gather_stream.wait_event(ready)
+                        gather_host[slot][:total].copy_(finals[slot][:total], non_blocking=True)
+                        gather_copied[slot].record(gather_stream)
+            if gather_stream is not None:
+                gather_stream.synchronize()
+            cur.synchronize()
+            return total * 2
         base = e2e_jobs[0]
         for i in range(steps):
             mel_dev.copy_(mel_host, non_blocking=True)
@@ -499,7 +536,7 @@ def run_ours(args, rank, world, local_rank):
                    "l2": "flushed between timed steps (256 MB write); per-step activations >> L2",
                    "exchange": "int64[3] all-reduce (file trim range + peak), then grouped ncclSend/ncclRecv of every rank's part "
                                "straight into its place on rank 0 (value); e2e: every rank copies its part device->host into "
-                               "a host buffer shared by the ranks" if world > 1 else "none"},
+                               "a host buffer shared by the ranks" + ("" if host_mode == "shared" else " [unavailable here: gather + rank-0 read-back]") if world > 1 else "none"},
         "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(mel_host.numel() * 4 * world),
                 "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),

@@ -200,7 +200,7 @@ k_convT_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ide
           }
         };
         if constexpr (kLoads) issue(0);
-        mbar_wait_relaxed(&acc_full[buf], (uint32_t)(seq >> 1) & 1u);
+        mbar_wait(&acc_full[buf], (uint32_t)(seq >> 1) & 1u);
         tc_fence_after();
 #pragma unroll 1
         for (int cc = 0; cc < 4; ++cc) {

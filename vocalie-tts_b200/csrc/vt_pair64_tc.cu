@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(kP64Warps * 32, 1) k_pair64_tc(const ConvArgs 
         }
       }
     };
-    auto ewait = [&](uint64_t* bar, uint32_t parity) { mbar_wait_relaxed(bar, parity); };
+    auto ewait = [&](uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); };
     int n_next = 1;
     long long base_next = n_my > 0 ? tile_base(0, n_next) : 0;
     if (n_my > 0) issue_x(base_next, n_next);

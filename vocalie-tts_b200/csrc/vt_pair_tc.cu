@@ -220,17 +220,17 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
     uint32_t xs = 0, xph = 0;
     for (int i = 0; i < n_my; ++i) {
       const int b1 = i % NA1;
-      mbar_wait_relaxed(&a1_empty[b1], ((uint32_t)(i / NA1) & 1u) ^ 1u);
+      mbar_wait(&a1_empty[b1], ((uint32_t)(i / NA1) & 1u) ^ 1u);
       if (pt == 0) trace_ev(a.trace, i, 0);
       const uint32_t a1 = a1_base + (uint32_t)(b1 * A1_BYTES);
       long long x_wait = 0;
       for (int sl = 0; sl < n_slab; ++sl) {
         if (a.trace) {
           const long long tw = clock64();
-          mbar_wait_relaxed(&x_full[xs], xph);
+          mbar_wait(&x_full[xs], xph);
           x_wait += clock64() - tw;
         } else {
-          mbar_wait_relaxed(&x_full[xs], xph);
+          mbar_wait(&x_full[xs], xph);
         }
         const uint32_t xsrc = smem_u32(sX + xs * kSlabBytes);
         // all shared-memory reads of this slab first (the volatile asm statements keep program order, so
@@ -415,8 +415,8 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
       const uint32_t chunk = (uint32_t)((c & 63) >> 3);
       for (int i = 0; i < n_my; ++i) {
         const ConvTile tile = get_tile(i);
-        mbar_wait_relaxed(&d1_full[0], (uint32_t)i & 1u);
-        mbar_wait_relaxed(&a2_empty[0], ((uint32_t)i & 1u) ^ 1u);
+        mbar_wait(&d1_full[0], (uint32_t)i & 1u);
+        mbar_wait(&a2_empty[0], ((uint32_t)i & 1u) ^ 1u);
         tc_fence_after();
         if (ew == 0 && lane == 0) trace_ev(a.trace, i, 2);
         const uint32_t dst0 = smem_u32(sA2) + coff;
@@ -469,7 +469,7 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
       long long obase = n_my > 0 ? tile_base(0, n_cur) : 0;
       if (n_my > 0) issue(obase, n_cur, 0);
       for (int i = 0; i < n_my; ++i) {
-        mbar_wait_relaxed(&d2_full[0], (uint32_t)i & 1u);
+        mbar_wait(&d2_full[0], (uint32_t)i & 1u);
         tc_fence_after();
         if (warp == 0 && lane == 0) trace_ev(a.trace, i, 4);
         struct { int n; } tile{n_cur};
@@ -717,8 +717,8 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
       const ConvTile tile = get_tile(i);
       if (do_mid) {
         const int b2 = i % NA2;
-        mbar_wait_relaxed(&d1_full[b], u & 1u);
-        mbar_wait_relaxed(&a2_empty[b2], ((uint32_t)(i / NA2) & 1u) ^ 1u);
+        mbar_wait(&d1_full[b], u & 1u);
+        mbar_wait(&a2_empty[b2], ((uint32_t)(i / NA2) & 1u) ^ 1u);
         tc_fence_after();
         if (ew == 0 && lane == 0 && (kCombined || warp == W_MID)) trace_ev(a.trace, i, 2);
         const uint32_t dst0 = smem_u32(sA2 + b2 * A2_BYTES);
@@ -760,7 +760,7 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
         mbar_arrive_warp(&a2_full[b2]);
       }
       if (do_fin) {
-        mbar_wait_relaxed(&d2_full[b], u & 1u);
+        mbar_wait(&d2_full[b], u & 1u);
         tc_fence_after();
         if (warp == 0 && lane == 0) trace_ev(a.trace, i, 4);
         if constexpr (kPreload) {

@@ -83,9 +83,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   if (!mbar_try(addr, parity)) mbar_wait_slow(addr, parity);
 }
-// Waits of the roles whose waits are long (epilogues, producers).  Formerly a __nanosleep back-off between probes;
-// with the suspend hint the plain wait is already idle.
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
@@ -258,26 +255,6 @@ constexpr int kStageLd = 36;   // floats per staged row (32 + 4 pad: conflict-fr
 __device__ __forceinline__ float snake_f(float v, float alpha, float inv_alpha) {
   const float s = __sinf(v * alpha);
   return fmaf(inv_alpha, s * s, v);
-}
-
-// The same function on the FMA pipe only.  MUFU.SIN issues one warp instruction per ~32 cycles per scheduler on
-// sm_100a (measured: a producer warp alone needs 32 cycles per Snake), i.e. 4 sines per clock per SM - a fused
-// ResBlock pair at C = 64 needs 35 k of them per tile, more time than its MMAs.  Here: u = v*alpha/pi rounded to the
-// nearest integer by the 1.5*2^23 trick, r = u - rint(u) in [-0.5, 0.5], sin^2(pi r) = t*P(t) with t = r^2 and a
-// degree-4 minimax P (absolute error 1.3e-6 in fp32 Horner - the class of sin.approx squared).  10 FMA-pipe
-// instructions against 4 + 1 MUFU: kernels split their elements between the two forms so that both pipes are busy.
-// alpha / pi is loop-invariant per channel and hoisted by the compiler.  |v*alpha| < 2^22 * pi is assumed.
-__device__ __forceinline__ float snake_poly(float v, float alpha, float inv_alpha) {
-  const float a_pi = alpha * 0.318309886f;
-  const float m = fmaf(v, a_pi, 12582912.0f);
-  const float rn = m - 12582912.0f;
-  const float r = fmaf(v, a_pi, -rn);
-  const float t = r * r;
-  float p = fmaf(t, 10.603050f, -29.434399f);
-  p = fmaf(t, p, 42.643887f);
-  p = fmaf(t, p, -32.465050f);
-  p = fmaf(t, p, 9.8695183f);
-  return fmaf(inv_alpha * t, p, v);
 }
 
 // Debug timeline (VT_TC_TRACE): CTA 0 records clock64 at role events of its first kTraceTiles tiles.

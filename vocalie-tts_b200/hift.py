@@ -228,7 +228,9 @@ class HiFTVocoder:
             out = torch.empty(total_T * self.samples_per_frame, dtype=torch.float32, device=self.device)
         elif out.numel() < total_T * self.samples_per_frame or out.dtype != torch.float32 or not out.is_cuda:
             raise ValueError("out must be a float32 CUDA tensor with 480*sum(T) elements")
-        with self._lock:
+        # launch on the vocoder's device and on the calling thread's current stream FOR THAT DEVICE (reference job threads
+        # default to device 0 whatever device the vocoder lives on)
+        with self._lock, torch.cuda.device(self.device):
             ws = self._workspace(torch, self.workspace_bytes(B, total_T, int(T.max()) if B else 0))
             ptr = lambda t: 0 if t is None else int(t.data_ptr())
             rc = self._lib.vt_hift_forward(self._h, ptr(mel), T.ctypes.data_as(C.POINTER(C.c_int32)), B, ptr(f0),
