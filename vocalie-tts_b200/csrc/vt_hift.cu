@@ -20,6 +20,9 @@ bool convT_tc_supported(const ConvLayer& L);
 int launch_convT_tc(const ConvArgs& a, const ConvLayer& L, int act_elem, const void* tiles, int n_tiles, cudaStream_t st);
 bool pair_tc_supported(const ConvLayer& c1, const ConvLayer& c2);
 int pair_tc_tile_rows(int k);
+bool pair3_tc_supported(const ConvLayer* const c1[3], const ConvLayer* const c2[3], int act_elem);
+int launch_pair3_tc(const ConvArgs& a, const ConvLayer* const c1[3], const ConvLayer* const c2[3], const float* const alpha1[3],
+                    const float* const alpha2[3], const float* const x_in[3], int act_elem, cudaStream_t st);
 bool pair64_tc_supported(const ConvLayer& c1, const ConvLayer& c2);
 int pair64_tc_tile_rows(int k);
 int pack_pair64(ConvLayer& L, std::vector<void*>& allocs);
@@ -82,6 +85,7 @@ struct Workspace {
   double* phase_base;
   float *U[3], *S[3], *X[3], *XR[3], *Y[3];
   float *S2[3], *XR2[3];                    // ping-pong partners of S / XR for the fused pairs (no in-place update)
+  float *XR3[3], *XR4[3];                   // with XR2: the inputs of the three ResBlocks' last pairs (mean-fused launch)
   void *A[3][4];                            // activation copies A0, A1, A2, Q per level
   void *Yact[3];                            // leaky_relu(stage output) operand copies (next ups / conv_post)
   void *xpre_act;                           // leaky_relu(conv_pre) operand copy, gapped mel-rate layout
@@ -478,6 +482,8 @@ Workspace carve_ws(const vt_hift* h, int B, long long total_T, void* base) {
     w.Y[l] = (float*)take((size_t)cap * C * 4);
     w.S2[l] = (float*)take((size_t)cap * C * 4);
     w.XR2[l] = (float*)take((size_t)cap * C * 4);
+    w.XR3[l] = (float*)take((size_t)cap * C * 4);
+    w.XR4[l] = (float*)take((size_t)cap * C * 4);
     for (int i = 0; i < 4; ++i) w.A[l][i] = take((size_t)cap * C * es);
     w.Yact[l] = take((size_t)cap * C * es);
   }
@@ -774,8 +780,8 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
       add(w.Yact[l], C * (int)elem_size(ae), l);
       if (h->fuse[l]) {
         // fused pairs read the fp32 streams with their halo
-        float* fb[5] = {w.S[l], w.S2[l], w.X[l], w.XR[l], w.XR2[l]};
-        for (int i = 0; i < 5; ++i) add(fb[i], C * 4, l);
+        float* fb[7] = {w.S[l], w.S2[l], w.X[l], w.XR[l], w.XR2[l], w.XR3[l], w.XR4[l]};
+        for (int i = 0; i < 7; ++i) add(fb[i], C * 4, l);
       } else {
         for (int i = 0; i < 4; ++i) add(w.A[l][i], C * (int)elem_size(ae), l);
       }
@@ -917,10 +923,15 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
         if (rc) return rc;
       }
       mark(h, ("source_resblock" + sfx).c_str(), st);
+      // the last pairs of the three ResBlocks as ONE mean-fused launch when their weights allow it (no scaled rows)
+      const ConvLayer* l1[3] = {&h->rb_c1[i * 3][2], &h->rb_c1[i * 3 + 1][2], &h->rb_c1[i * 3 + 2][2]};
+      const ConvLayer* l2[3] = {&h->rb_c2[i * 3][2], &h->rb_c2[i * 3 + 1][2], &h->rb_c2[i * 3 + 2][2]};
+      const bool tri = pair3_tc_supported(l1, l2, ae);
+      float* ylast[3] = {w.XR2[i], w.XR3[i], w.XR4[i]};
       for (int r = 0; r < 3; ++r) {
         const int R = i * 3 + r;
-        float* xin[3] = {w.X[i], w.XR[i], w.XR2[i]};
-        for (int j = 0; j < 3; ++j) {
+        float* xin[3] = {w.X[i], w.XR[i], tri ? ylast[r] : w.XR2[i]};
+        for (int j = 0; j < (tri ? 2 : 3); ++j) {
           const bool p64 = c64 && h->pair64[r] && (j < 2 || h->pair64_last);
           ConvArgs c = base_args(h->rb_c2[R][j], P, p64 ? P.pair64[r] : P.pair[i][r]);
           c.res1 = xin[j];
@@ -938,6 +949,18 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
                                      : launch_pair_tc(c, h->rb_c1[R][j], h->rb_c2[R][j], h->rb_a1[R][j], h->rb_a2[R][j], ae, st);
           if (rc) return rc;
         }
+      }
+      if (tri) {
+        if (prof) h->rb_launches -= 2;            // three last pairs in one launch
+        ConvArgs c = base_args(h->rb_c2[i * 3 + 2][2], P, P.pair[i][2]);     // tiles of the largest kernel size
+        c.out = w.Y[i];
+        c.out_scale = 1.0f / 3.0f;
+        c.act[0] = {w.Yact[i], nullptr, ACT_LRELU, i < LL ? 0.1f : 0.01f};
+        c.act_from_out = 1;
+        const float* a1[3] = {h->rb_a1[i * 3][2], h->rb_a1[i * 3 + 1][2], h->rb_a1[i * 3 + 2][2]};
+        const float* a2[3] = {h->rb_a2[i * 3][2], h->rb_a2[i * 3 + 1][2], h->rb_a2[i * 3 + 2][2]};
+        rc = launch_pair3_tc(c, l1, l2, a1, a2, ylast, ae, st);
+        if (rc) return rc;
       }
     }
     for (int j = 0; j < 3 && !h->fuse[i]; ++j) {

@@ -98,10 +98,25 @@ template <> __device__ __forceinline__ unsigned short to_op_bits<__nv_bfloat16>(
 // common instance (WS = false) pays nothing: the activation-major epilogues fetch per-channel constants from shared memory
 // for every element group, and one more vector there costs 6-9 % of a C = 64 launch (and 40-70 % on the accumulate
 // variants, whose fin passes run at the register cap).
-template <int C, int NBUF, int NA1, int NA2, int W_ST, int NEPI, int NPROD, int NSLAB, int EM, bool kPreload, bool TR, bool WS, typename ActT>
+//
+// NS = 3 ("mean-fused"): the last pairs of the three ResBlocks of a stage as three sub-iterations per tile.  Every role
+// but the fin epilogue simply runs NS iterations per tile with the sub's parameters (input stream, weights, Snake
+// parameters, kernel size, dilation); conv2 of all subs accumulates in the tile's D2 buffer, the fin epilogue runs once
+// per tile with the sum of the residual inputs and biases.  The partial mean (one fp32 stream written and one read per
+// ResBlock, loaded synchronously by fin passes on the critical path: +0.15 .. 0.55 ms per launch) never exists.
+template <int C, int NBUF, int NA1, int NA2, int W_ST, int NEPI, int NPROD, int NSLAB, int EM, bool kPreload, bool TR, bool WS, typename ActT, int NS = 1>
 __global__ void __launch_bounds__(PairCfg<C, NBUF, NEPI, NPROD, TR>::WARPS * 32, 1)
 k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
   using PC = PairCfg<C, NBUF, NEPI, NPROD, TR>;
+  static_assert(NS == 1 || (NS == 3 && !WS && !PC::kCombined && (TR || kPreload) && !(EM & (EM_RES2 | EM_ACCUM))),
+                "mean-fused launches: unscaled weights, separate mid / fin warps, no other extra stream");
+  constexpr int PRM_SUB = 5 * C;                         // al1 | ia1 | b1 | al2 | ia2 of one sub
+  constexpr int PRM_FLOATS = NS == 1 ? 8 * C : NS * PRM_SUB;
+  auto sub_k = [&](int r) { return (NS == 1 || r == 0) ? p.k : p.more[r - 1].k; };
+  auto sub_dil = [&](int r) { return (NS == 1 || r == 0) ? p.dil : p.more[r - 1].dil; };
+  auto sub_x = [&](int r) { return (NS == 1 || r == 0) ? p.x_in : p.more[r - 1].x_in; };
+  auto sub_h2 = [&](int r) { return (sub_k(r) - 1) / 2; };
+  auto sub_h1 = [&](int r) { return (sub_k(r) - 1) * sub_dil(r) / 2; };
   static_assert(!TR || (C == 128 && NBUF == 1 && !kPreload && NEPI == 8), "the transposed variant is built for C = 128");
   constexpr bool kCombined = PC::kCombined;
   constexpr int NMID = NEPI, kFin = NEPI, kProdT = NPROD * 32;
@@ -135,7 +150,7 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_empty + W_ST);
   float* prm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(tmem_slot) + 16);   // al1 | ia1 | b1 | al2 | ia2 | ws1 | ws2 | 1 / ws2
   // fin staging (32 x kStageLd floats per warp): its own region, or the idle A2 tile in combined mode
-  float* stage_all = kCombined ? reinterpret_cast<float*>(sA2) : prm + 8 * C;
+  float* stage_all = kCombined ? reinterpret_cast<float*>(sA2) : prm + PRM_FLOATS;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -150,10 +165,12 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
     for (int i = 0; i < W_ST; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], a.mc ? 2 : 1); }
     fence_barrier_init();
   }
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float a1 = p.alpha1[c], a2 = p.alpha2[c];
-    prm[c] = a1; prm[C + c] = __fdividef(1.0f, a1 + 1e-9f); prm[2 * C + c] = p.bias1[c];
-    prm[3 * C + c] = a2; prm[4 * C + c] = __fdividef(1.0f, a2 + 1e-9f);
+  for (int cr = threadIdx.x; cr < C * NS; cr += blockDim.x) {
+    const int r = cr / C, c = cr - r * C;
+    const float a1 = (r == 0 ? p.alpha1 : p.more[r - 1].alpha1)[c], a2 = (r == 0 ? p.alpha2 : p.more[r - 1].alpha2)[c];
+    float* q = prm + r * PRM_SUB;
+    q[c] = a1; q[C + c] = __fdividef(1.0f, a1 + 1e-9f); q[2 * C + c] = (r == 0 ? p.bias1 : p.more[r - 1].bias1)[c];
+    q[3 * C + c] = a2; q[4 * C + c] = __fdividef(1.0f, a2 + 1e-9f);
     if constexpr (WS) {
       prm[5 * C + c] = p.wscale1[c];
       const float w2 = a.wscale[c];
@@ -185,8 +202,7 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
     if (t >= a.n_tiles) tl.n = 0;
     return tl;
   };
-  const int H2 = (p.k - 1) / 2, H1 = (p.k - 1) * p.dil / 2;
-  const int nchunks = p.k * CB;
+  const int n_it = n_my * NS;                  // iterations of every role but fin: (tile, sub) pairs, sub fastest
 
   constexpr bool kSplitLoader = PC::kSplitLoader;
   constexpr int W_XL = kSplitLoader ? W_AP + NPROD : W_WP;    // x loader: its own warp, or lane 1 of the weight loader's
@@ -205,21 +221,26 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
     const int r_in = (r_raw & ~6) | ((r_raw & 2) << 1) | ((r_raw & 4) >> 1);
     const int cA = 4 * ch, cB = C / 2 + 4 * ch;    // first channel of the two pieces
     float alA[4], iaA[4], alB[4], iaB[4];
+    auto load_snake1 = [&](int r) {
+      const float* q = prm + r * PRM_SUB;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      alA[e] = prm[cA + e]; iaA[e] = prm[C + cA + e];
-      alB[e] = prm[cB + e]; iaB[e] = prm[C + cB + e];
-    }
-    const int R1 = 256 + 2 * H1;
-    const int n_slab = (R1 + SLAB_ROWS - 1) / SLAB_ROWS;
+      for (int e = 0; e < 4; ++e) {
+        alA[e] = q[cA + e]; iaA[e] = q[C + cA + e];
+        alB[e] = q[cB + e]; iaB[e] = q[C + cB + e];
+      }
+    };
+    load_snake1(0);
     // byte offsets of the two pieces inside an A1 row block: 64-channel block, 16-byte chunk, 8-byte half
     const uint32_t blkA = (uint32_t)(cA >> 6) * (uint32_t)(kPairRA1 * 128), blkB = (uint32_t)(cB >> 6) * (uint32_t)(kPairRA1 * 128);
     const uint32_t chkA = (uint32_t)((cA & 63) >> 3), chkB = (uint32_t)((cB & 63) >> 3);
     const uint32_t halfA = (uint32_t)((cA & 7) >> 2) * 8u, halfB = (uint32_t)((cB & 7) >> 2) * 8u;
     const uint32_t a1_base = smem_u32(sA1);
     uint32_t xs = 0, xph = 0;
-    for (int i = 0; i < n_my; ++i) {
+    for (int i = 0; i < n_it; ++i) {
       const int b1 = i % NA1;
+      if constexpr (NS > 1) load_snake1(i % NS);
+      const int R1 = 256 + 2 * sub_h1(i % NS);
+      const int n_slab = (R1 + SLAB_ROWS - 1) / SLAB_ROWS;
       mbar_wait(&a1_empty[b1], ((uint32_t)(i / NA1) & 1u) ^ 1u);
       if (pt == 0) trace_ev(a.trace, i, 0);
       const uint32_t a1 = a1_base + (uint32_t)(b1 * A1_BYTES);
@@ -274,12 +295,13 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
     // C = 64 (20 warps exactly) it is lane 1 of the weight loader's warp - diverged lanes make progress independently.
     if (warp == W_XL && lane == kXlLane) {
       // x ring: the tiles' fp32 rows (with halo), slab by slab (whole rows are contiguous in HBM -> 1-D bulk copies)
-      const int R1 = 256 + 2 * H1;
       uint32_t xs = 0, xph = 0;
       ConvTile tl = n_my > 0 ? get_tile(0) : ConvTile{};
-      for (int xi = 0; xi < n_my; ++xi) {
-        const float* xsrc = p.x_in + (tl.in_row0 + tl.q0 - H1 - H2) * (long long)C;
-        if (xi + 1 < n_my) tl = get_tile(xi + 1);          // next tile's entry: off the critical path
+      for (int xi = 0; xi < n_it; ++xi) {
+        const int r = xi % NS, H1 = sub_h1(r), H2 = sub_h2(r);
+        const int R1 = 256 + 2 * H1;
+        const float* xsrc = sub_x(r) + (tl.in_row0 + tl.q0 - H1 - H2) * (long long)C;
+        if (r == NS - 1 && xi + 1 < n_it) tl = get_tile(xi / NS + 1);   // next tile's entry: off the critical path
         for (int xr = 0; xr < R1; xr += SLAB_ROWS) {
           const int rows = R1 - xr < SLAB_ROWS ? R1 - xr : SLAB_ROWS;
           mbar_wait(&x_empty[xs], xph ^ 1u);
@@ -295,10 +317,12 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
       // weight ring: chunk order mirrors the MMA issue order
       const uint32_t mc_rank = a.mc ? cluster_ctarank() : 0u;
       uint32_t ws = 0, wph = 0;
-      for (int s = 0; s < n_my + SKEW; ++s)
+      for (int s = 0; s < n_it + SKEW; ++s)
         for (int pass = 0; pass < 2; ++pass) {
-          if (pass == 0 ? s >= n_my : s < SKEW) continue;
-          const uint8_t* wsrc = pass == 0 ? p.w1 : p.w2;
+          if (pass == 0 ? s >= n_it : s < SKEW) continue;
+          const int r = (pass == 0 ? s : s - SKEW) % NS;
+          const uint8_t* wsrc = (NS == 1 || r == 0) ? (pass == 0 ? p.w1 : p.w2) : (pass == 0 ? p.more[r - 1].w1 : p.more[r - 1].w2);
+          const int nchunks = sub_k(r) * CB;
           for (int w_c = 0; w_c < nchunks; ++w_c) {
             mbar_wait(&w_empty[ws], wph ^ 1u);
             if (a.dbg & 1) mbar_arrive(&w_full[ws]);
@@ -330,12 +354,15 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
     const uint32_t w_lo0 = ((smem_u32(sW) >> 4) & 0x3FFFu) | (1u << 16);
     const bool mma_on = !(a.dbg & 16);
     uint32_t ws = 0, wph = 0;
-    for (int s = 0; s < n_my + SKEW; ++s)
+    for (int s = 0; s < n_it + SKEW; ++s)
       for (int pass = 0; pass < 2; ++pass) {
-        if (pass == 0 ? s >= n_my : s < SKEW) continue;
+        if (pass == 0 ? s >= n_it : s < SKEW) continue;
         const int i = pass == 0 ? s : s - SKEW;
-        const int b = i % NBUF;
-        const uint32_t u = (uint32_t)(i / NBUF);
+        const int r = i % NS;                                       // sub-pair of the tile
+        // D1 is double buffered by iteration; D2 belongs to the TILE: conv2 of every sub accumulates in it
+        const int ib = pass == 0 ? i : i / NS;
+        const int b = ib % NBUF;
+        const uint32_t u = (uint32_t)(ib / NBUF);
         const int bs = pass == 0 ? i % NA1 : i % NA2;                         // shared-memory operand buffer
         const uint32_t us = (uint32_t)(pass == 0 ? i / NA1 : i / NA2);
         uint64_t* src_full = pass == 0 ? &a1_full[bs] : &a2_full[bs];
@@ -343,18 +370,21 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
         uint64_t* dst_full = pass == 0 ? &d1_full[b] : &d2_full[b];
         // conv1 needs D1 drained by the mid epilogue; conv2 needs D2 preloaded by the fin warps (x + b2 + ...)
         if (pass == 0) mbar_wait(&d1_empty[b], (u & 1u) ^ 1u);
-        else if (kPreload) mbar_wait(&d2i_full[b], u & 1u);
-        else mbar_wait(&d2i_full[b], (u & 1u) ^ 1u);       // plain "D2 drained" barrier in register-prefetch mode
+        else if (r == 0) {
+          if (kPreload) mbar_wait(&d2i_full[b], u & 1u);
+          else mbar_wait(&d2i_full[b], (u & 1u) ^ 1u);     // plain "D2 drained" barrier in register-prefetch mode
+        }
         mbar_wait(src_full, us & 1u);
         tc_fence_after();
         if (lane == 0) trace_ev(a.trace, i, 6 + 2 * pass);
         const uint32_t d0 = tmem_base + (uint32_t)((pass * NBUF + b) * ACC_COLS);
         const uint32_t a_tile = pass == 0 ? a1_lo0 + (uint32_t)bs * (uint32_t)(A1_BYTES >> 4) : a2_lo0 + (uint32_t)bs * (uint32_t)(A2_BYTES >> 4);
         const uint32_t blk16 = (uint32_t)(pass == 0 ? kPairRA1 : kPairRA2) * 8u;   // 64-channel block stride, 16-byte units
-        const uint32_t tap16 = (uint32_t)(pass == 0 ? p.dil : 1) * 8u;              // one tap = dil rows of 128 B
-        uint32_t acc = (pass == 1 && kPreload) ? 1u : 0u;
+        const uint32_t tap16 = (uint32_t)(pass == 0 ? sub_dil(r) : 1) * 8u;         // one tap = dil rows of 128 B
+        uint32_t acc = (pass == 1 && (kPreload || r > 0)) ? 1u : 0u;
         long long w_wait = 0;
-        for (int j = 0; j < p.k; ++j) {
+        const int k_r = sub_k(r);
+        for (int j = 0; j < k_r; ++j) {
           uint32_t a_chunk = a_tile + (uint32_t)j * tap16;
 #pragma unroll 1
           for (int cb = 0; cb < CB; ++cb, a_chunk += blk16) {
@@ -393,7 +423,7 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
         }
         if (elect_one()) {
           umma_commit(src_empty);
-          umma_commit(dst_full);
+          if (pass == 0 || r == NS - 1) umma_commit(dst_full);      // D2 is complete after the last sub's conv2
         }
         __syncwarp();
         if (lane == 0) trace_ev(a.trace, i, 7 + 2 * pass);
@@ -409,12 +439,20 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
     const int c = quarter * 32 + lane;                                   // this thread's channel
     const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
     if (!is_fin) {
-      const float b1 = prm[2 * C + c], al2 = prm[3 * C + c], ia2 = prm[4 * C + c], ws1 = WS ? prm[5 * C + c] : 1.0f;
+      float b1 = prm[2 * C + c], al2 = prm[3 * C + c], ia2 = prm[4 * C + c];
+      const float ws1 = WS ? prm[5 * C + c] : 1.0f;
       // A2 element (row r, channel c): 64-channel block, 16-byte chunk XOR-swizzled by the row, 2 bytes inside
       const uint32_t coff = (uint32_t)(c >> 6) * (uint32_t)(kPairRA2 * 128) + (uint32_t)((c & 7) * 2);
       const uint32_t chunk = (uint32_t)((c & 63) >> 3);
-      for (int i = 0; i < n_my; ++i) {
-        const ConvTile tile = get_tile(i);
+      ConvTile tile = n_my > 0 ? get_tile(0) : ConvTile{};
+      for (int i = 0; i < n_it; ++i) {
+        const int r = i % NS;
+        if (NS == 1 || r == 0) tile = get_tile(i / NS);
+        if constexpr (NS > 1) {
+          const float* q = prm + r * PRM_SUB;
+          b1 = q[2 * C + c]; al2 = q[3 * C + c]; ia2 = q[4 * C + c];
+        }
+        const int H2 = sub_h2(r);
         mbar_wait(&d1_full[0], (uint32_t)i & 1u);
         mbar_wait(&a2_empty[0], ((uint32_t)i & 1u) ^ 1u);
         tc_fence_after();
@@ -444,7 +482,9 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
       }
     } else {
       constexpr bool kRes2 = (EM & EM_RES2) != 0, kAccum = (EM & EM_ACCUM) != 0;
-      const float b2 = a.bias[c], ws2 = WS ? a.wscale[c] : 1.0f;
+      float b2 = a.bias[c];
+      if constexpr (NS > 1) b2 += p.more[0].bias2[c] + p.more[1].bias2[c];
+      const float ws2 = WS ? a.wscale[c] : 1.0f;
       const bool accum = kAccum && a.out_accum;
       const float inv = 1.0f / a.out_scale;
       const uint32_t d2 = tmem_base + lane_sel + (uint32_t)ACC_COLS;
@@ -471,7 +511,7 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
       for (int i = 0; i < n_my; ++i) {
         mbar_wait(&d2_full[0], (uint32_t)i & 1u);
         tc_fence_after();
-        if (warp == 0 && lane == 0) trace_ev(a.trace, i, 4);
+        if (warp == 0 && lane == 0) trace_ev(a.trace, i * NS + NS - 1, 4);
         struct { int n; } tile{n_cur};
 #pragma unroll 1
         for (int cc = 0; cc < 4; ++cc) {
@@ -485,6 +525,14 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
 #pragma unroll
               for (int t = 0; t < 32; ++t)
                 x[t] = fmaf(__ldg(a.out + obase + (long long)(col0 + t < last ? col0 + t : last) * C), inv, x[t]);
+            }
+            if constexpr (NS > 1) {                          // the other subs' residual inputs (pair inputs share the row map)
+#pragma unroll
+              for (int q = 0; q < NS - 1; ++q) {
+                const float* xq = p.more[q].x_in + obase;
+#pragma unroll
+                for (int t = 0; t < 32; ++t) x[t] += __ldg(xq + (long long)(col0 + t < last ? col0 + t : last) * C);
+              }
             }
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {                 // 16 accumulator columns at a time: x[32] stays live
@@ -514,7 +562,7 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
           }
         }
         tc_fence_before();
-        if (warp == 0 && lane == 0) trace_ev(a.trace, i, 5);
+        if (warp == 0 && lane == 0) trace_ev(a.trace, i * NS + NS - 1, 5);
         mbar_arrive_warp(&d2i_full[0]);
       }
     }
@@ -553,7 +601,14 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
     auto fin_store = [&](const ConvTile& tl, int blk, int b, float4 (&pre)[8]) {
       int mb, c0, nvalid; long long idx0;
       blk_geom(tl, blk, mb, c0, idx0, nvalid);
-      const float4 bias = *reinterpret_cast<const float4*>(a.bias + c0 + sub * 4);
+      float4 bias = *reinterpret_cast<const float4*>(a.bias + c0 + sub * 4);
+      if constexpr (NS > 1) {
+#pragma unroll
+        for (int q = 0; q < NS - 1; ++q) {
+          const float4 bq = *reinterpret_cast<const float4*>(p.more[q].bias2 + c0 + sub * 4);
+          bias.x += bq.x; bias.y += bq.y; bias.z += bq.z; bias.w += bq.w;
+        }
+      }
       // conv2 accumulates s_c * (W2 a) on top of the preload, so the preload is s_c * (x + b2 + ...): exact (power of two)
       float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
       if constexpr (WS) sc = *reinterpret_cast<const float4*>(prm + 7 * C + c0 + sub * 4);
@@ -572,6 +627,13 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
           if (accum) {
             const float4 pv = *reinterpret_cast<const float4*>(a.out + idx);
             t.x = fmaf(pv.x, inv, t.x); t.y = fmaf(pv.y, inv, t.y); t.z = fmaf(pv.z, inv, t.z); t.w = fmaf(pv.w, inv, t.w);
+          }
+          if constexpr (NS > 1) {                            // the other subs' residual inputs
+#pragma unroll
+            for (int m = 0; m < NS - 1; ++m) {
+              const float4 xm = ldg_f4(p.more[m].x_in + idx);
+              t.x += xm.x; t.y += xm.y; t.z += xm.z; t.w += xm.w;
+            }
           }
           if constexpr (WS) { t.x *= sc.x; t.y *= sc.y; t.z *= sc.z; t.w *= sc.w; }
         }
@@ -711,11 +773,15 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
         mbar_arrive_warp(&d2i_full[j]);
       }
     }
-    for (int i = 0; i < n_my; ++i) {
-      const int b = i % NBUF;
-      const uint32_t u = (uint32_t)(i / NBUF);
-      const ConvTile tile = get_tile(i);
+    // one loop over (tile, sub) iterations: the mid part runs every iteration, the fin part once per tile (after the
+    // last sub); NS > 1 has separate mid and fin warps, so each warp only sees its own part
+    for (int it = 0; it < n_it; ++it) {
+      const int sr = it % NS;                              // sub-pair
+      const ConvTile tile = get_tile(it / NS);
       if (do_mid) {
+        const int i = it, b = i % NBUF, H2 = sub_h2(sr);
+        const uint32_t u = (uint32_t)(i / NBUF);
+        const float* prs = prm + sr * PRM_SUB;
         const int b2 = i % NA2;
         mbar_wait(&d1_full[b], u & 1u);
         mbar_wait(&a2_empty[b2], ((uint32_t)(i / NA2) & 1u) ^ 1u);
@@ -738,9 +804,9 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
               const int c = c0 + g * 8 + hh * 4;
-              const float4 bb = *reinterpret_cast<const float4*>(prm + 2 * C + c);
-              const float4 aa = *reinterpret_cast<const float4*>(prm + 3 * C + c);
-              const float4 ii = *reinterpret_cast<const float4*>(prm + 4 * C + c);
+              const float4 bb = *reinterpret_cast<const float4*>(prs + 2 * C + c);
+              const float4 aa = *reinterpret_cast<const float4*>(prs + 3 * C + c);
+              const float4 ii = *reinterpret_cast<const float4*>(prs + 4 * C + c);
               const float4 ww = WS ? *reinterpret_cast<const float4*>(prm + 5 * C + c) : make_float4(1.f, 1.f, 1.f, 1.f);
               y[hh * 4 + 0] = snake_f(fmaf(__uint_as_float(v[g * 8 + hh * 4 + 0]), ww.x, bb.x), aa.x, ii.x);
               y[hh * 4 + 1] = snake_f(fmaf(__uint_as_float(v[g * 8 + hh * 4 + 1]), ww.y, bb.y), aa.y, ii.y);
@@ -759,10 +825,12 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
         mbar_arrive_warp(&d1_empty[b]);
         mbar_arrive_warp(&a2_full[b2]);
       }
-      if (do_fin) {
+      if (do_fin && sr == NS - 1) {
+        const int i = it / NS, b = i % NBUF;               // tile index: D2 and its barriers belong to the tile
+        const uint32_t u = (uint32_t)(i / NBUF);
         mbar_wait(&d2_full[b], u & 1u);
         tc_fence_after();
-        if (warp == 0 && lane == 0) trace_ev(a.trace, i, 4);
+        if (warp == 0 && lane == 0) trace_ev(a.trace, it, 4);
         if constexpr (kPreload) {
           const bool has_next = i + NBUF < n_my;
           const ConvTile tnext = has_next ? get_tile(i + NBUF) : tile;
@@ -775,7 +843,7 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
           }
           if (has_next) tmem_st_wait();
           tc_fence_before();
-          if (warp == 0 && lane == 0) trace_ev(a.trace, i, 5);
+          if (warp == 0 && lane == 0) trace_ev(a.trace, it, 5);
           if (has_next) mbar_arrive_warp(&d2i_full[b]);
         } else {
 #pragma unroll
@@ -784,7 +852,7 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
             pf_issue(i * BPW + k + PF, pfr[k % PF]);
           }
           tc_fence_before();
-          if (warp == 0 && lane == 0) trace_ev(a.trace, i, 5);
+          if (warp == 0 && lane == 0) trace_ev(a.trace, it, 5);
           mbar_arrive_warp(&d2i_full[b]);
         }
         // combined mode: the staging lives in the A2 tile; nobody may start mid(i+1) before everyone left fin(i)
@@ -802,18 +870,18 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
   }
 }
 
-template <int C, int NBUF, int NA1, int NA2, int W_ST, int NEPI, int NPROD, int NSLAB, int EM, bool kPreload, bool TR, bool WS, typename ActT>
+template <int C, int NBUF, int NA1, int NA2, int W_ST, int NEPI, int NPROD, int NSLAB, int EM, bool kPreload, bool TR, bool WS, typename ActT, int NS = 1>
 int launch_pair_ws(const ConvArgs& a, const PairArgs& p, uint32_t idesc, int grid, cudaStream_t st) {
   constexpr int CB = C / 64;
   using PC = PairCfg<C, NBUF, NEPI, NPROD, TR>;
   constexpr int smem = CB * (NA1 * kPairRA1 + NA2 * kPairRA2) * 128 + W_ST * C * 128 + NSLAB * 8192 +
-                       (2 * NA1 + 2 * NA2 + 2 * NSLAB + 4 * NBUF + 2 * W_ST) * 8 + 16 + 8 * C * 4 +
+                       (2 * NA1 + 2 * NA2 + 2 * NSLAB + 4 * NBUF + 2 * W_ST) * 8 + 16 + (NS == 1 ? 8 : 5 * NS) * C * 4 +
                        ((PC::kCombined || TR) ? 0 : NEPI * 32 * kStageLd * 4);
   static_assert(smem <= 232448, "shared memory budget exceeded");
   static_assert(!PC::kCombined || NEPI * 32 * kStageLd * 4 <= CB * kPairRA2 * 128, "fin staging must fit the A2 tile");
   static bool configured = false;
   if (!configured) {
-    VT_CUDA_OK(cudaFuncSetAttribute(k_pair_tc<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, kPreload, TR, WS, ActT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    VT_CUDA_OK(cudaFuncSetAttribute(k_pair_tc<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, kPreload, TR, WS, ActT, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   if (a.mc) {
@@ -823,9 +891,9 @@ int launch_pair_ws(const ConvArgs& a, const PairArgs& p, uint32_t idesc, int gri
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    VT_CUDA_OK(cudaLaunchKernelEx(&cfg, k_pair_tc<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, kPreload, TR, WS, ActT>, a, p, idesc));
+    VT_CUDA_OK(cudaLaunchKernelEx(&cfg, k_pair_tc<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, kPreload, TR, WS, ActT, NS>, a, p, idesc));
   } else {
-    VT_CUDA_OK(launch_pdl(k_pair_tc<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, kPreload, TR, WS, ActT>, dim3((unsigned)grid), dim3(PC::WARPS * 32), smem, st, a, p, idesc));
+    VT_CUDA_OK(launch_pdl(k_pair_tc<C, NBUF, NA1, NA2, W_ST, NEPI, NPROD, NSLAB, EM, kPreload, TR, WS, ActT, NS>, dim3((unsigned)grid), dim3(PC::WARPS * 32), smem, st, a, p, idesc));
   }
   VT_LAUNCHED();
   return VT_OK;
@@ -884,6 +952,37 @@ bool pair_tc_supported(const ConvLayer& c1, const ConvLayer& c2) {
 
 int pair_tc_tile_rows(int k) { return 256 - (k - 1); }
 
+namespace {
+// debug timeline: VT_TC_TRACE=<conv1 layer name> dumps CTA 0's per-iteration role timestamps to stderr
+long long* g_trace = nullptr;
+bool trace_begin(ConvArgs& a, const std::string& name, cudaStream_t st) {
+  static const char* trace_name = getenv("VT_TC_TRACE");
+  if (!(trace_name && name == trace_name)) return false;
+  if (!g_trace && cudaMalloc(&g_trace, tc::kTraceTiles * tc::kTraceEvents * 8) != cudaSuccess) return false;
+  cudaMemsetAsync(g_trace, 0, tc::kTraceTiles * tc::kTraceEvents * 8, st);
+  a.trace = g_trace;
+  return true;
+}
+int trace_dump(const ConvArgs& a, const std::string& name, int k, int dil, int grid, cudaStream_t st) {
+  std::vector<long long> h(tc::kTraceTiles * tc::kTraceEvents);
+  VT_CUDA_OK(cudaStreamSynchronize(st));
+  VT_CUDA_OK(cudaMemcpy(h.data(), g_trace, h.size() * 8, cudaMemcpyDeviceToHost));
+  long long t0 = 0;
+  for (size_t q = 0; q < h.size(); ++q)
+    if ((int)(q % tc::kTraceEvents) < 10 && h[q] && (!t0 || h[q] < t0)) t0 = h[q];
+  fprintf(stderr, "[vt trace] pair %s k=%d dil=%d tiles=%d grid=%d (cycles; PROD start end | MID start end | FIN start end | "
+          "C1 start issued | C2 start issued)\n", name.c_str(), k, dil, a.n_tiles, grid);
+  for (int it = 0; it < tc::kTraceTiles; ++it) {
+    if (!h[it * tc::kTraceEvents + 0]) break;
+    fprintf(stderr, "[vt trace] %2d", it);
+    for (int e = 0; e < 10; ++e) fprintf(stderr, " %7lld", h[it * tc::kTraceEvents + e] ? h[it * tc::kTraceEvents + e] - t0 : -1);
+    fprintf(stderr, "  w_wait c1=%lld c2=%lld x_wait=%lld", h[it * tc::kTraceEvents + 10], h[it * tc::kTraceEvents + 11], h[it * tc::kTraceEvents + 12]);
+    fprintf(stderr, "\n");
+  }
+  return VT_OK;
+}
+}  // namespace
+
 // `a` describes the fin epilogue (bias = conv2 bias, res1 = the pair's input stream, out, tiles of
 // pair_tc_tile_rows(k) output steps); alpha1 / alpha2 are the Snake parameters before conv1 / conv2.
 int launch_pair_tc(const ConvArgs& a_in, const ConvLayer& c1, const ConvLayer& c2, const float* alpha1, const float* alpha2,
@@ -920,15 +1019,7 @@ int launch_pair_tc(const ConvArgs& a_in, const ConvLayer& c1, const ConvLayer& c
   a.mc = use_mc ? 1 : 0;
   const int n_even = (a.n_tiles + 1) & ~1;
   const int grid = a.mc ? (n_even < (sm_count & ~1) ? n_even : (sm_count & ~1)) : (a.n_tiles < sm_count ? a.n_tiles : sm_count);
-  // debug timeline: VT_TC_TRACE=<conv1 layer name> dumps CTA 0's per-tile role timestamps to stderr
-  static const char* trace_name = getenv("VT_TC_TRACE");
-  static long long* d_trace = nullptr;
-  const bool tracing = trace_name && c1.name == trace_name;
-  if (tracing) {
-    if (!d_trace) VT_CUDA_OK(cudaMalloc(&d_trace, tc::kTraceTiles * tc::kTraceEvents * 8));
-    VT_CUDA_OK(cudaMemsetAsync(d_trace, 0, tc::kTraceTiles * tc::kTraceEvents * 8, st));
-    a.trace = d_trace;
-  }
+  const bool tracing = trace_begin(a, c1.name, st);
   const uint32_t fmt = act_elem == ELEM_F16 ? 0u : 1u;
   const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(C >> 3) << 17) | ((128u >> 4) << 24);
   int rc;
@@ -945,23 +1036,69 @@ int launch_pair_tc(const ConvArgs& a_in, const ConvLayer& c1, const ConvLayer& c
   else
     rc = C == 64 ? tc::launch_pair_c<64, 2, 2, 1, 4, 8, 2, 5, __nv_bfloat16>(a, p, idesc, grid, st)
                  : tc::launch_pair_c<128, 1, 1, 1, 3, 8, 4, 3, __nv_bfloat16>(a, p, idesc, grid, st);
-  if (tracing && rc == VT_OK) {
-    std::vector<long long> h(tc::kTraceTiles * tc::kTraceEvents);
-    VT_CUDA_OK(cudaStreamSynchronize(st));
-    VT_CUDA_OK(cudaMemcpy(h.data(), d_trace, h.size() * 8, cudaMemcpyDeviceToHost));
-    long long t0 = 0;
-    for (size_t q = 0; q < h.size(); ++q)
-      if ((int)(q % tc::kTraceEvents) < 10 && h[q] && (!t0 || h[q] < t0)) t0 = h[q];
-    fprintf(stderr, "[vt trace] pair %s k=%d dil=%d tiles=%d grid=%d (cycles; PROD start end | MID start end | FIN start end | "
-            "C1 start issued | C2 start issued)\n", c1.name.c_str(), c1.k, c1.dil, a.n_tiles, grid);
-    for (int it = 0; it < tc::kTraceTiles; ++it) {
-      if (!h[it * tc::kTraceEvents + 0]) break;
-      fprintf(stderr, "[vt trace] %2d", it);
-      for (int e = 0; e < 10; ++e) fprintf(stderr, " %7lld", h[it * tc::kTraceEvents + e] ? h[it * tc::kTraceEvents + e] - t0 : -1);
-      fprintf(stderr, "  w_wait c1=%lld c2=%lld x_wait=%lld", h[it * tc::kTraceEvents + 10], h[it * tc::kTraceEvents + 11], h[it * tc::kTraceEvents + 12]);
-      fprintf(stderr, "\n");
-    }
+  if (tracing && rc == VT_OK) return trace_dump(a, c1.name, c1.k, c1.dil, grid, st);
+  return rc;
+}
+
+// Mean-fused launch of the LAST pairs of the three ResBlocks of a stage (k_pair_tc, NS = 3):
+//   out = (1/3) sum_r [ x_r + conv2_r(Snake(conv1_r(Snake(x_r)))) ]   (+ the next layer's leaky-ReLU operand copy)
+// `a` describes the fin epilogue as for launch_pair_tc (out, out_scale = 1/3, act[0] = the leaky-ReLU copy) on the tiles of
+// the LARGEST kernel size (pair_tc_tile_rows(k_max) output steps: every sub is evaluated on the same 256 conv1 rows, a
+// smaller kernel only needs less halo).
+bool pair3_tc_supported(const ConvLayer* const c1[3], const ConvLayer* const c2[3], int act_elem) {
+  // default: C = 64 only.  At C = 128 (D2 single buffered: TMEM is full) conv2 of the next tile's first sub waits for the
+  // whole fin pass, which now loads three residual streams: level 1 7.43 -> 7.89 ms (VT_PAIR3=all enables it there too,
+  // VT_PAIR3=0 disables the mean-fused launch everywhere)
+  static const char* sw = getenv("VT_PAIR3");
+  const bool off = sw && sw[0] == '0', all = sw && sw[0] == 'a';
+  if (off || act_elem != ELEM_F16 || (c1[0]->cin != 64 && !all)) return false;
+  for (int r = 0; r < 3; ++r)
+    if (!pair_tc_supported(*c1[r], *c2[r]) || c1[r]->scaled || c2[r]->scaled || c1[r]->cin != c1[0]->cin) return false;
+  return true;
+}
+
+int launch_pair3_tc(const ConvArgs& a_in, const ConvLayer* const c1[3], const ConvLayer* const c2[3], const float* const alpha1[3],
+                    const float* const alpha2[3], const float* const x_in[3], int act_elem, cudaStream_t st) {
+  VT_REQUIRE(pair3_tc_supported(c1, c2, act_elem), "pair3_tc: layers %s .. cannot be mean-fused", c1[0]->name.c_str());
+  if (a_in.n_tiles == 0) return VT_OK;
+  ConvArgs a = a_in;
+  static const int dbg = getenv("VT_TC_DBG") ? atoi(getenv("VT_TC_DBG")) : 0;
+  a.dbg = dbg;
+  VT_REQUIRE(a.out && !a.res2 && !a.out_accum && a.act[0].dst && a.act[0].kind == ACT_LRELU && a.act_from_out && !a.act[1].dst,
+             "pair3_tc: needs an fp32 output and the leaky-ReLU operand copy, nothing else");
+  a.bias = c2[0]->bias; a.res1 = x_in[0]; a.wscale = nullptr; a.mc = 0; a.trace = nullptr;
+  const bool tracing = trace_begin(a, c1[0]->name, st);
+  a.cout = c2[0]->cout; a.phase_c = c2[0]->cout; a.out_mul = 1; a.out_shift = 0; a.dup_row2 = 0;
+  PairArgs p{};
+  p.x_in = x_in[0]; p.alpha1 = alpha1[0]; p.alpha2 = alpha2[0]; p.bias1 = c1[0]->bias;
+  p.w1 = reinterpret_cast<const uint8_t*>(c1[0]->w_tc); p.w2 = reinterpret_cast<const uint8_t*>(c2[0]->w_tc);
+  p.k = c1[0]->k; p.dil = c1[0]->dil;
+  p.nsub = 3;
+  for (int r = 1; r < 3; ++r) {
+    PairArgs::Sub& m = p.more[r - 1];
+    m.x_in = x_in[r]; m.alpha1 = alpha1[r]; m.alpha2 = alpha2[r]; m.bias1 = c1[r]->bias; m.bias2 = c2[r]->bias;
+    m.w1 = reinterpret_cast<const uint8_t*>(c1[r]->w_tc); m.w2 = reinterpret_cast<const uint8_t*>(c2[r]->w_tc);
+    m.k = c1[r]->k; m.dil = c1[r]->dil;
   }
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    VT_CUDA_OK(cudaGetDevice(&dev));
+    VT_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int C = c1[0]->cin;
+  const int grid = a.n_tiles < sm_count ? a.n_tiles : sm_count;
+  constexpr int EM = tc::EM_RES1 | tc::EM_OUT | tc::EM_OACT;
+  int rc;
+  if (C == 64) {
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((128u >> 4) << 24);
+    rc = tc::launch_pair_ws<64, 2, 2, 1, 4, 8, 2, 5, EM, true, false, false, __half, 3>(a, p, idesc, grid, st);
+  } else {
+    // transposed MMA: M = 128 output channels, N = 256 time steps
+    const uint32_t idesc_t = (1u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+    rc = tc::launch_pair_ws<128, 1, 1, 1, 3, 8, 4, 3, EM, false, true, false, __half, 3>(a, p, idesc_t, grid, st);
+  }
+  if (tracing && rc == VT_OK) return trace_dump(a, c1[0]->name, c1[0]->k, c1[0]->dil, grid, st);
   return rc;
 }
 

@@ -19,6 +19,15 @@ struct PairArgs {
   const uint8_t* w1;      // conv1 / conv2 weights: pack_conv_tc images (chunk = (tap, 64-channel block)), or the
   const uint8_t* w2;      // tap-pair images of pack_pair64
   int k, dil;
+  // Mean-fused launch (nsub == 3): the LAST pairs of the three ResBlocks of a stage run as sub-iterations of one tile
+  // and accumulate in the same TMEM buffer - out = (1/3) sum_r [x_r + b2_r + conv2_r(Snake(conv1_r(Snake(x_r))))] - so the
+  // partial mean never travels through HBM.  Sub 0 is described by the fields above (and ConvArgs::bias / res1).
+  int nsub;
+  struct Sub {
+    const float* x_in; const float* alpha1; const float* alpha2; const float* bias1; const float* bias2;
+    const uint8_t* w1; const uint8_t* w2;
+    int k, dil;
+  } more[2];
 };
 
 namespace tc {
