@@ -136,7 +136,13 @@ __global__ void __launch_bounds__(kP64Warps * 32, 1) k_pair64_tc(const ConvArgs 
     static_assert(kP64SlabRows % RPP == 0, "slab rows must divide among the producer threads");
     const int pt = threadIdx.x - kP64W_AP * 32;
     const int ch = pt % QPR, r_raw = pt / QPR;
-    const int r_in = (r_raw & ~6) | ((r_raw & 2) << 1) | ((r_raw & 4) >> 1);   // spread a warp's rows over the swizzle halves
+    // bits 0 and 2 swapped: the two rows of a HALF warp (the unit an 8-byte store is served in) lie 4 rows apart, on both
+    // sides of the swizzle pattern's (row & 4) - their 16 stores then cover all 32 banks once (see vt_pair_tc.cu)
+#ifdef VT_OLD_ROWPERM
+    const int r_in = (r_raw & ~6) | ((r_raw & 2) << 1) | ((r_raw & 4) >> 1);
+#else
+    const int r_in = (r_raw & ~5) | ((r_raw & 1) << 2) | ((r_raw & 4) >> 2);
+#endif
     const int cA = 4 * ch, cB = C / 2 + 4 * ch;
     float alA[4], iaA[4], alB[4], iaB[4];
 #pragma unroll

@@ -216,9 +216,17 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
     constexpr int RPP = kProdT / QPR;              // rows per pass of all producer threads
     const int pt = threadIdx.x - W_AP * 32;
     const int ch = pt % QPR, r_raw = pt / QPR;
-    // swap bits 1 and 2 of the row index: the 4 rows of a warp (C = 64) then cover both (row & 4) halves of the
-    // swizzle pattern and the 8-byte stores spread over all 32 banks
+    // C = 64: swap bits 0 and 2 of the row index.  An 8-byte store is served per HALF warp (16 lanes x 8 B = 128 B = all
+    // 32 banks once if the lanes hit 8 distinct 16-byte chunks); a half warp holds two rows, each writing chunks
+    // (0..3) ^ (row & 7) - two rows on the same side of (row & 4) collide (ncu source view: every A1 store took twice
+    // its ideal wavefronts, 6-10 % of all shared-memory wavefronts of the C = 64 launches), rows 4 apart do not.
+    // C = 128: a half warp is one whole 128-byte row either way (bits 1 and 2 swapped as before).
+#ifdef VT_OLD_ROWPERM          // A/B build switch (tools/ab_build.sh oldperm -DVT_OLD_ROWPERM)
     const int r_in = (r_raw & ~6) | ((r_raw & 2) << 1) | ((r_raw & 4) >> 1);
+#else
+    const int r_in = C == 64 ? ((r_raw & ~5) | ((r_raw & 1) << 2) | ((r_raw & 4) >> 2))
+                             : ((r_raw & ~6) | ((r_raw & 2) << 1) | ((r_raw & 4) >> 1));
+#endif
     const int cA = 4 * ch, cB = C / 2 + 4 * ch;    // first channel of the two pieces
     float alA[4], iaA[4], alB[4], iaB[4];
     auto load_snake1 = [&](int r) {
