@@ -16,6 +16,7 @@
 #include "vt_tc.cuh"
 
 #include <cstdlib>
+#include <type_traits>
 
 namespace vt {
 namespace tc {
@@ -187,33 +188,40 @@ k_convT_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ide
         constexpr bool kLoads = (EM & (EM_RES1 | EM_RES2 | EM_ACCUM)) != 0;
         const bool accum = ((EM & EM_ACCUM) != 0) && a.out_accum;
         const float inv = 1.0f / a.out_scale;
-        // residual terms of the first block: requested before the accumulator wait
+        // residual terms of the first block: requested before the accumulator wait.
+        // kFull (every column of the tile is an output step - all tiles but a sequence's last): no index clamps, no
+        // per-element predicates, and every address is one base pointer plus a compile-time offset.  The epilogue of
+        // conv2 carries three streams per element (residual in, fp32 out, operand copy out); with clamps and 64-bit
+        // index arithmetic per access it took 225 us against 157 us for conv1's MMAs at k = 7.
         float x[32];
-        auto issue = [&](int cc) {
+        auto issue = [&](int cc, auto full_tag) {
+          constexpr bool kFull = decltype(full_tag)::value;
           const int col0 = chalf * 128 + cc * 32;
+          const float* rp = a.res1 + obase + (long long)col0 * C;
 #pragma unroll
           for (int q = 0; q < 32; ++q) {
-            const long long o = obase + (long long)(col0 + q < last ? col0 + q : last) * C;
             float r = 0.0f;
-            if constexpr ((EM & EM_RES1) != 0) r = __ldg(a.res1 + o);
+            if constexpr ((EM & EM_RES1) != 0) {
+              if constexpr (kFull) r = __ldg(rp + q * C);
+              else r = __ldg(a.res1 + obase + (long long)(col0 + q < last ? col0 + q : last) * C);
+            }
             x[q] = r;
           }
         };
-        if constexpr (kLoads) issue(0);
-        mbar_wait(&acc_full[buf], (uint32_t)(seq >> 1) & 1u);
-        tc_fence_after();
-#pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {
+        auto block = [&](int cc, auto full_tag) {
+          constexpr bool kFull = decltype(full_tag)::value;
           const int col0 = chalf * 128 + cc * 32;
-          if (a.dbg & 4) break;
+          const long long cbase = obase + (long long)col0 * C;
           if constexpr ((EM & EM_RES2) != 0) {
 #pragma unroll
-            for (int q = 0; q < 32; ++q) x[q] += __ldg(a.res2 + obase + (long long)(col0 + q < last ? col0 + q : last) * C);
+            for (int q = 0; q < 32; ++q)
+              x[q] += kFull ? __ldg(a.res2 + cbase + q * C) : __ldg(a.res2 + obase + (long long)(col0 + q < last ? col0 + q : last) * C);
           }
           if (accum) {
 #pragma unroll
             for (int q = 0; q < 32; ++q)
-              x[q] = fmaf(__ldg(a.out + obase + (long long)(col0 + q < last ? col0 + q : last) * C), inv, x[q]);
+              x[q] = fmaf(kFull ? __ldg(a.out + cbase + q * C) : __ldg(a.out + obase + (long long)(col0 + q < last ? col0 + q : last) * C),
+                          inv, x[q]);
           }
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
@@ -229,10 +237,10 @@ k_convT_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ide
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
               const int row = col0 + hh * 16 + q;
-              if (row < tile.n) {
+              if (kFull || row < tile.n) {
                 float y = fmaf(__uint_as_float(v[q]), wsc, bias);
                 if constexpr (kLoads) y += x[hh * 16 + q];
-                const long long idx = obase + (long long)row * C;
+                const long long idx = kFull ? cbase + (hh * 16 + q) * C : obase + (long long)row * C;
                 if constexpr ((EM & EM_OUT) != 0) {
                   const float o = y * a.out_scale;
                   a.out[idx] = o;
@@ -248,7 +256,23 @@ k_convT_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ide
             }
           }
           if constexpr (kLoads) {
-            if (cc < 3) issue(cc + 1);
+            if (cc < 3) issue(cc + 1, full_tag);
+          }
+        };
+        const bool full = tile.n == kTRows && !(a.dbg & 1024);   // warp-uniform (CTA-uniform); VT_TC_DBG=1024: A/B switch, results valid
+        if constexpr (kLoads) {
+          if (full) issue(0, std::true_type{});
+          else issue(0, std::false_type{});
+        }
+        mbar_wait(&acc_full[buf], (uint32_t)(seq >> 1) & 1u);
+        tc_fence_after();
+        if (!(a.dbg & 4)) {
+          if (full) {
+#pragma unroll 1
+            for (int cc = 0; cc < 4; ++cc) block(cc, std::true_type{});
+          } else {
+#pragma unroll 1
+            for (int cc = 0; cc < 4; ++cc) block(cc, std::false_type{});
           }
         }
         tc_fence_before();

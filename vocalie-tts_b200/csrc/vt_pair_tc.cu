@@ -19,6 +19,7 @@
 #include "vt_tc.cuh"
 
 #include <cstdlib>
+#include <type_traits>
 
 namespace vt {
 
@@ -472,14 +473,28 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
           uint32_t v[32];
           tmem_ld32(tmem_base + lane_sel + (uint32_t)col0, v);
           tmem_ld_wait();
+          const int p0 = tile.q0 - H2 + col0;                              // sequence position of the block's first row
+          if (p0 >= 0 && p0 + 32 <= tile.out_len && !(a.dbg & 1024)) {
+            // the whole block lies inside the sequence (all blocks but those at a sequence's ends): no per-row test,
+            // and (col0 & 7) == 0 makes the swizzle phase of row col0 + t a compile-time function of t.  The mid pass is
+            // on the conv1 -> mid -> conv2 chain that bounds the k >= 7 tiles.
+            const uint32_t base = dst0 + (uint32_t)col0 * 128u;
 #pragma unroll
-          for (int t = 0; t < 32; ++t) {
-            const int row = col0 + t;                                      // conv1 output row of the tile = A2 row
-            const int pseq = tile.q0 - H2 + row;
-            const bool valid = pseq >= 0 && pseq < tile.out_len;          // warp-uniform
-            const float y = valid ? snake_f(fmaf(__uint_as_float(v[t]), ws1, b1), al2, ia2) : 0.0f;
-            const uint32_t addr = dst0 + (uint32_t)row * 128u + ((chunk ^ (uint32_t)(row & 7)) << 4);
-            asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(to_op_bits<ActT>(y)) : "memory");
+            for (int t = 0; t < 32; ++t) {
+              const float y = snake_f(fmaf(__uint_as_float(v[t]), ws1, b1), al2, ia2);
+              asm volatile("st.shared.u16 [%0], %1;" ::"r"(base + ((chunk ^ (uint32_t)(t & 7)) << 4) + (uint32_t)(t * 128)),
+                           "h"(to_op_bits<ActT>(y)) : "memory");
+            }
+          } else {
+#pragma unroll
+            for (int t = 0; t < 32; ++t) {
+              const int row = col0 + t;                                      // conv1 output row of the tile = A2 row
+              const int pseq = tile.q0 - H2 + row;
+              const bool valid = pseq >= 0 && pseq < tile.out_len;          // warp-uniform
+              const float y = valid ? snake_f(fmaf(__uint_as_float(v[t]), ws1, b1), al2, ia2) : 0.0f;
+              const uint32_t addr = dst0 + (uint32_t)row * 128u + ((chunk ^ (uint32_t)(row & 7)) << 4);
+              asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(to_op_bits<ActT>(y)) : "memory");
+            }
           }
         }
         tc_fence_before();
@@ -507,11 +522,19 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
         n = tl.n;
         return (tl.out_row0 + tl.q0) * (long long)C + c;
       };
+      // A block whose 32 time steps are all output steps of the tile (every block but a tile's last one or two) takes
+      // the "full" paths below: no index clamps, no per-element predicates, one base pointer plus compile-time offsets.
       auto issue = [&](long long base, int n, int cc) {
-        const float* xr = a.res1 + base;
         const int col0 = half * 128 + cc * 32, last = n - 1;
+        if (col0 + 32 <= n && !(a.dbg & 1024)) {
+          const float* xr = a.res1 + base + (long long)col0 * C;
 #pragma unroll
-        for (int t = 0; t < 32; ++t) x[t] = (a.dbg & 32) ? 0.0f : __ldg(xr + (long long)(col0 + t < last ? col0 + t : last) * C);
+          for (int t = 0; t < 32; ++t) x[t] = (a.dbg & 32) ? 0.0f : __ldg(xr + t * C);
+        } else {
+          const float* xr = a.res1 + base;
+#pragma unroll
+          for (int t = 0; t < 32; ++t) x[t] = (a.dbg & 32) ? 0.0f : __ldg(xr + (long long)(col0 + t < last ? col0 + t : last) * C);
+        }
       };
       int n_cur = 1;
       long long obase = n_my > 0 ? tile_base(0, n_cur) : 0;
@@ -521,46 +544,52 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
         tc_fence_after();
         if (warp == 0 && lane == 0) trace_ev(a.trace, i * NS + NS - 1, 4);
         struct { int n; } tile{n_cur};
-#pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {
+        auto block = [&](int cc, auto full_tag) {
+          constexpr bool kFull = decltype(full_tag)::value;
           const int col0 = half * 128 + cc * 32, last = tile.n - 1;
-          if (!(a.dbg & 4)) {
-            if constexpr (kRes2) {
+          const long long cbase = obase + (long long)col0 * C;
+          auto at = [&](int t) { return kFull ? cbase + t * C : obase + (long long)(col0 + t < last ? col0 + t : last) * C; };
+          if constexpr (kRes2) {
 #pragma unroll
-              for (int t = 0; t < 32; ++t) x[t] += __ldg(a.res2 + obase + (long long)(col0 + t < last ? col0 + t : last) * C);
+            for (int t = 0; t < 32; ++t) x[t] += __ldg(a.res2 + at(t));
+          }
+          if (accum) {
+#pragma unroll
+            for (int t = 0; t < 32; ++t) x[t] = fmaf(__ldg(a.out + at(t)), inv, x[t]);
+          }
+          if constexpr (NS > 1) {                          // the other subs' residual inputs (pair inputs share the row map)
+#pragma unroll
+            for (int q = 0; q < NS - 1; ++q) {
+              const float* xq = p.more[q].x_in;
+#pragma unroll
+              for (int t = 0; t < 32; ++t) x[t] += __ldg(xq + at(t));
             }
-            if (accum) {
+          }
 #pragma unroll
-              for (int t = 0; t < 32; ++t)
-                x[t] = fmaf(__ldg(a.out + obase + (long long)(col0 + t < last ? col0 + t : last) * C), inv, x[t]);
-            }
-            if constexpr (NS > 1) {                          // the other subs' residual inputs (pair inputs share the row map)
+          for (int hh = 0; hh < 2; ++hh) {                 // 16 accumulator columns at a time: x[32] stays live
+            uint32_t v[16];
+            tmem_ld16(d2 + (uint32_t)(col0 + hh * 16), v);
+            tmem_ld_wait();
 #pragma unroll
-              for (int q = 0; q < NS - 1; ++q) {
-                const float* xq = p.more[q].x_in + obase;
-#pragma unroll
-                for (int t = 0; t < 32; ++t) x[t] += __ldg(xq + (long long)(col0 + t < last ? col0 + t : last) * C);
-              }
-            }
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {                 // 16 accumulator columns at a time: x[32] stays live
-              uint32_t v[16];
-              tmem_ld16(d2 + (uint32_t)(col0 + hh * 16), v);
-              tmem_ld_wait();
-#pragma unroll
-              for (int t = 0; t < 16; ++t) {
-                const int row = col0 + hh * 16 + t;
-                if (row < tile.n) {
-                  const float o = fmaf(__uint_as_float(v[t]), ws2, b2 + x[hh * 16 + t]) * a.out_scale;
-                  const long long idx = obase + (long long)row * C;
-                  if (!(a.dbg & 64)) a.out[idx] = o;
-                  if constexpr ((EM & EM_OACT) != 0) {
-                    const float sl = a.act[0].slope;
-                    reinterpret_cast<unsigned short*>(a.act[0].dst)[idx] = to_op_bits<ActT>(o > 0.f ? o : o * sl);
-                  }
+            for (int t = 0; t < 16; ++t) {
+              const int row = col0 + hh * 16 + t;
+              if (kFull || row < tile.n) {
+                const float o = fmaf(__uint_as_float(v[t]), ws2, b2 + x[hh * 16 + t]) * a.out_scale;
+                const long long idx = kFull ? cbase + (hh * 16 + t) * C : obase + (long long)row * C;
+                if (!(a.dbg & 64)) a.out[idx] = o;
+                if constexpr ((EM & EM_OACT) != 0) {
+                  const float sl = a.act[0].slope;
+                  reinterpret_cast<unsigned short*>(a.act[0].dst)[idx] = to_op_bits<ActT>(o > 0.f ? o : o * sl);
                 }
               }
             }
+          }
+        };
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+          if (!(a.dbg & 4)) {
+            if (half * 128 + cc * 32 + 32 <= tile.n && !(a.dbg & 1024)) block(cc, std::true_type{});
+            else block(cc, std::false_type{});
           }
           // next block of this tile, or the first block of the next one (in flight during the d2_full wait)
           if (cc < 3) issue(obase, n_cur, cc + 1);
