@@ -338,15 +338,19 @@ def test_bf16_operand_mode_runs_at_its_documented_accuracy(torch, weights):
     {"VT_WSCALE": "1", "VT_CONVT": "0", "VT_PAIR_TR": "0", "VT_PAIR64": "0"},
     {"VT_PAIR3": "0"},
     {"VT_PAIR3": "0", "VT_PAIR_TR": "0"},
+    {"VT_PAIR3": "64"},
+    {"VT_TC_DBG": "1024"},
 ], ids=["activation-major", "tap-paired-all", "tap-paired-single-a1", "weight-multicast", "row-scaled-weights",
-        "row-scaled-activation-major", "separate-last-pairs", "separate-last-pairs-activation-major"])
+        "row-scaled-activation-major", "separate-last-pairs", "separate-last-pairs-activation-major",
+        "mean-fused-c64-only", "general-epilogue-paths"])
 def test_alternative_kernels_meet_the_parity_bar(env):
     """The kernel selections that are read from the environment once per process (VT_CONVT=0: activation-resident conv
     at C = 256, VT_PAIR_TR=0: untransposed pair kernel at C = 128, VT_PAIR64=0 / all: tap-paired pair kernel at C = 64
     for no / every pair, VT_P64_NA1=1: its single-A1 configuration, VT_PAIR_MC=1: weight ring multicast across a 2-CTA
     cluster, VT_WSCALE=1: power-of-two weight-row scales on EVERY layer - by default only layers with out-of-range rows
     get them, VT_PAIR3=0: the last pairs of a stage's three ResBlocks as three launches with a running mean in HBM
-    instead of the mean-fused launch) are alternative implementations of the same arithmetic; run them in a fresh process and hold them to the
+    instead of the mean-fused launch, VT_PAIR3=64: mean-fused at C = 64 only, VT_TC_DBG=1024: the transposed epilogues
+    without their full-block fast paths) are alternative implementations of the same arithmetic; run them in a fresh process and hold them to the
     same waveform bar."""
     import os
     import subprocess

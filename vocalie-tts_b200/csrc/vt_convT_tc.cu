@@ -234,24 +234,44 @@ k_convT_tc(const ConvArgs a, const uint8_t* __restrict__ wtc, const uint32_t ide
                 : "r"(tmem_base + lane_sel + (uint32_t)(buf * kTRows + col0 + hh * 16))
                 : "memory");
             tmem_ld_wait();
-#pragma unroll
-            for (int q = 0; q < 16; ++q) {
-              const int row = col0 + hh * 16 + q;
-              if (kFull || row < tile.n) {
-                float y = fmaf(__uint_as_float(v[q]), wsc, bias);
-                if constexpr (kLoads) y += x[hh * 16 + q];
-                const long long idx = kFull ? cbase + (hh * 16 + q) * C : obase + (long long)row * C;
-                if constexpr ((EM & EM_OUT) != 0) {
-                  const float o = y * a.out_scale;
-                  a.out[idx] = o;
-                  if constexpr ((EM & EM_OACT) != 0) {
-                    const float sl = a.act[0].slope;
-                    reinterpret_cast<unsigned short*>(a.act[0].dst)[idx] = op_bits<ActT>(o > 0.f ? o : o * sl);
-                  }
+            // one output element: everything but the Snake copies (those run two at a time in the full path)
+            auto finish = [&](int q, long long idx) {
+              float y = fmaf(__uint_as_float(v[q]), wsc, bias);
+              if constexpr (kLoads) y += x[hh * 16 + q];
+              if constexpr ((EM & EM_OUT) != 0) {
+                const float o = y * a.out_scale;
+                a.out[idx] = o;
+                if constexpr ((EM & EM_OACT) != 0) {
+                  const float sl = a.act[0].slope;
+                  reinterpret_cast<unsigned short*>(a.act[0].dst)[idx] = op_bits<ActT>(o > 0.f ? o : o * sl);
                 }
+              }
+              return y;
+            };
+            if constexpr (kFull) {
 #pragma unroll
-                for (int s = 0; s < NACT; ++s)
-                  reinterpret_cast<unsigned short*>(a.act[s].dst)[idx] = op_bits<ActT>(snake_f(y, al[s], ia[s]));
+              for (int q = 0; q < 16; q += 2) {
+                const long long idx0 = cbase + (hh * 16 + q) * C, idx1 = idx0 + C;
+                const float y0 = finish(q, idx0), y1 = finish(q + 1, idx1);
+#pragma unroll
+                for (int s = 0; s < NACT; ++s) {
+                  float z0, z1;
+                  snake_f2(y0, y1, al[s], al[s], ia[s], ia[s], z0, z1);
+                  reinterpret_cast<unsigned short*>(a.act[s].dst)[idx0] = op_bits<ActT>(z0);
+                  reinterpret_cast<unsigned short*>(a.act[s].dst)[idx1] = op_bits<ActT>(z1);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 16; ++q) {
+                const int row = col0 + hh * 16 + q;
+                if (row < tile.n) {
+                  const long long idx = obase + (long long)row * C;
+                  const float y = finish(q, idx);
+#pragma unroll
+                  for (int s = 0; s < NACT; ++s)
+                    reinterpret_cast<unsigned short*>(a.act[s].dst)[idx] = op_bits<ActT>(snake_f(y, al[s], ia[s]));
+                }
               }
             }
           }

@@ -1083,12 +1083,13 @@ int launch_pair_tc(const ConvArgs& a_in, const ConvLayer& c1, const ConvLayer& c
 // the LARGEST kernel size (pair_tc_tile_rows(k_max) output steps: every sub is evaluated on the same 256 conv1 rows, a
 // smaller kernel only needs less halo).
 bool pair3_tc_supported(const ConvLayer* const c1[3], const ConvLayer* const c2[3], int act_elem) {
-  // default: C = 64 only.  At C = 128 (D2 single buffered: TMEM is full) conv2 of the next tile's first sub waits for the
-  // whole fin pass, which now loads three residual streams: level 1 7.43 -> 7.89 ms (VT_PAIR3=all enables it there too,
-  // VT_PAIR3=0 disables the mean-fused launch everywhere)
+  // VT_PAIR3=0 disables the mean-fused launch everywhere, VT_PAIR3=64 keeps it to C = 64.  At C = 128 (D2 single buffered:
+  // TMEM is full) conv2 of the next tile's first sub waits for the whole fin pass, which loads three residual streams:
+  // with the general fin pass (clamped indices, 112 bytes of spills at the 80-register cap) level 1 went 7.43 -> 7.89 ms;
+  // with the full-block fast path the instance no longer spills and the launch wins there too (7.21 -> 7.13 ms).
   static const char* sw = getenv("VT_PAIR3");
-  const bool off = sw && sw[0] == '0', all = sw && sw[0] == 'a';
-  if (off || act_elem != ELEM_F16 || (c1[0]->cin != 64 && !all)) return false;
+  const bool off = sw && sw[0] == '0', only64 = sw && sw[0] == '6';
+  if (off || act_elem != ELEM_F16 || (c1[0]->cin != 64 && only64)) return false;
   for (int r = 0; r < 3; ++r)
     if (!pair_tc_supported(*c1[r], *c2[r]) || c1[r]->scaled || c2[r]->scaled || c1[r]->cin != c1[0]->cin) return false;
   return true;

@@ -266,6 +266,57 @@ __device__ __forceinline__ float snake_f(float v, float alpha, float inv_alpha) 
   return fmaf(inv_alpha, s * s, v);
 }
 
+// Two Snakes at once on the packed fp32 pipe (sm_100 FMUL2 / FFMA2: one issue slot for two lanes of a register pair).
+// Same operations and roundings as two snake_f calls - bit-identical results - with 3.5 instead of 5 instructions per
+// element (the two range-reduction multiplies and the two MUFU.SIN stay scalar).  The pair kernels' producer and mid roles
+// are bound by the issue rate of exactly this instruction stream.
+__device__ __forceinline__ unsigned long long f2_pack(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(unsigned long long r, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r)); }
+#ifdef VT_NO_F32X2            // A/B build switch (tools/ab_build.sh scalar -DVT_NO_F32X2): the same arithmetic on the scalar pipe
+__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b) {
+  float a0, a1, b0, b1; f2_unpack(a, a0, a1); f2_unpack(b, b0, b1);
+  return f2_pack(__fmul_rn(a0, b0), __fmul_rn(a1, b1));
+}
+__device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsigned long long b) {
+  float a0, a1, b0, b1; f2_unpack(a, a0, a1); f2_unpack(b, b0, b1);
+  return f2_pack(__fadd_rn(a0, b0), __fadd_rn(a1, b1));
+}
+__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+  float a0, a1, b0, b1, c0, c1; f2_unpack(a, a0, a1); f2_unpack(b, b0, b1); f2_unpack(c, c0, c1);
+  return f2_pack(__fmaf_rn(a0, b0, c0), __fmaf_rn(a1, b1, c1));
+}
+#else
+__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+#endif
+// y = v + inv_alpha * sin^2(alpha v) on a packed pair (v, alpha, inv_alpha: packed pairs)
+__device__ __forceinline__ unsigned long long snake_f2(unsigned long long v, unsigned long long alpha, unsigned long long inv_alpha) {
+  float t0, t1;
+  f2_unpack(f2_mul(v, alpha), t0, t1);
+  const unsigned long long s = f2_pack(__sinf(t0), __sinf(t1));
+  return f2_fma(inv_alpha, f2_mul(s, s), v);
+}
+__device__ __forceinline__ void snake_f2(float v0, float v1, float a0, float a1, float i0, float i1, float& y0, float& y1) {
+  f2_unpack(snake_f2(f2_pack(v0, v1), f2_pack(a0, a1), f2_pack(i0, i1)), y0, y1);
+}
+
 // Debug timeline (VT_TC_TRACE): CTA 0 records clock64 at role events of its first kTraceTiles tiles.
 constexpr int kTraceTiles = 48, kTraceEvents = 14;   // 0-9 role timestamps, 10/11 weight-ring waits of conv1/conv2, 12 producer x-ring wait, 13 spare
 __device__ __forceinline__ void trace_ev(long long* trace, int it, int ev) {
