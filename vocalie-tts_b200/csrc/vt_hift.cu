@@ -1032,7 +1032,7 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
     if (rc) return rc;
   }
   mark(h, "conv_post", st);
-  rc = launch_istft_head(w.post, P.d_mel_off, P.d_T, P.d_off[LL], B, P.T_max, h->trim_fade, cfg.trim_fade ? 2 * cfg.trim_n : 0, cfg.spf, wav, st);
+  rc = launch_istft_head(w.post, P.d_mel_off, P.d_T, P.d_off[LL], B, P.T_max, h->trim_fade, cfg.trim_fade ? 2 * cfg.trim_n : 0, cfg.spf, h->use_tc, wav, st);
   if (rc) return rc;
   mark(h, "istft_head", st);
   if (prof) VT_CUDA_OK(cudaEventRecord(h->ev_fwd[1], st));

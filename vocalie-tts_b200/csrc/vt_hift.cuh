@@ -144,6 +144,6 @@ int launch_pack_mel(const float* mel, const int* mel_off, const int* T, const lo
                     void* mel_hi, void* mel_lo, cudaStream_t st);
 // Spectral head (vt_head.cu): conv_post output -> exp/sin -> iSTFT -> clamp -> trim_fade
 int launch_istft_head(const float* post, const int* mel_off, const int* T, const long long* off2, int B,
-                      int T_max, const float* trim_fade, int trim_len, int spf, float* wav, cudaStream_t st);
+                      int T_max, const float* trim_fade, int trim_len, int spf, bool fast, float* wav, cudaStream_t st);
 
 }  // namespace vt
