@@ -2,5 +2,5 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 N=$1
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/r01_tc_v10_bench_fp16_${N}gpu.json 2> gpurun_out/bench_${N}gpu.err; echo rc=$?
-tail -1 gpurun_out/r01_tc_v10_bench_fp16_${N}gpu.json | cut -c1-200
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/bench_${N}gpu.json 2> gpurun_out/bench_${N}gpu.err; echo rc=$?
+tail -1 gpurun_out/bench_${N}gpu.json | cut -c1-200
