@@ -959,6 +959,14 @@ int vt_hift_forward(vt_hift* h, const float* mel, const int32_t* T, int B, const
         c.act_from_out = 1;
         const float* a1[3] = {h->rb_a1[i * 3][2], h->rb_a1[i * 3 + 1][2], h->rb_a1[i * 3 + 2][2]};
         const float* a2[3] = {h->rb_a2[i * 3][2], h->rb_a2[i * 3 + 1][2], h->rb_a2[i * 3 + 2][2]};
+        // Sub order.  At C = 128 the tile's single D2 buffer is drained by the fin pass while the NEXT tile's first sub
+        // already runs conv1 and mid; its conv2 then waits for the fin pass to end.  The largest kernel first gives the fin
+        // pass (three residual streams) the longest conv1 to hide behind (VT_PAIR3_ORDER=0: kernel sizes ascending).
+        static const bool asc = getenv("VT_PAIR3_ORDER") && getenv("VT_PAIR3_ORDER")[0] == '0';
+        if ((kBase >> (i + 1)) == 128 && !asc) {
+          std::swap(l1[0], l1[2]); std::swap(l2[0], l2[2]); std::swap(a1[0], a1[2]); std::swap(a2[0], a2[2]);
+          std::swap(ylast[0], ylast[2]);
+        }
         rc = launch_pair3_tc(c, l1, l2, a1, a2, ylast, ae, st);
         if (rc) return rc;
       }
