@@ -165,6 +165,9 @@ def test_two_threads_apply_minimal_edit_files(env, tmp_path):
     names = ["balance", "pauses", "many", "single"]
     for n in names:
         wav.write_pcm16(tmp_path / f"{n}.wav", z[f"raw_{n}_250"], SR)
+    # the goldens are read BEFORE the threads start: NpzFile decompresses lazily through one zipfile handle, which two
+    # threads cannot share (a run on the GPU box failed with BadZipFile("Overlapped entries") inside the test itself)
+    want = {n: (np.asarray(z[f"ame_tn_{n}_250"]), json.loads(bytes(z[f"ame_tn_meta_{n}_250"]).decode())) for n in names}
     errors = []
 
     def worker(tid):
@@ -174,8 +177,8 @@ def test_two_threads_apply_minimal_edit_files(env, tmp_path):
                 out = tmp_path / f"{n}_{tid}_{it}.wav"
                 res = post.apply_minimal_edit(tmp_path / f"{n}.wav", out, trim_enabled=True, normalize_enabled=True, target_dbfs=-1.0)
                 q, _ = wav.read_pcm16(out)
-                meta = json.loads(bytes(z[f"ame_tn_meta_{n}_250"]).decode())
-                if not np.array_equal(q, z[f"ame_tn_{n}_250"]) or res["peak_before"] != meta["peak_before"]:
+                golden, meta = want[n]
+                if not np.array_equal(q, golden) or res["peak_before"] != meta["peak_before"]:
                     errors.append((tid, it, n))
         except Exception as exc:  # noqa: BLE001
             errors.append((tid, repr(exc)))
