@@ -340,9 +340,10 @@ def test_bf16_operand_mode_runs_at_its_documented_accuracy(torch, weights):
     {"VT_PAIR3": "0", "VT_PAIR_TR": "0"},
     {"VT_PAIR3": "64"},
     {"VT_TC_DBG": "1024"},
+    {"VT_PAIR3_ORDER": "0"},
 ], ids=["activation-major", "tap-paired-all", "tap-paired-single-a1", "weight-multicast", "row-scaled-weights",
         "row-scaled-activation-major", "separate-last-pairs", "separate-last-pairs-activation-major",
-        "mean-fused-c64-only", "general-epilogue-paths"])
+        "mean-fused-c64-only", "general-epilogue-paths", "mean-fused-ascending-kernel-sizes"])
 def test_alternative_kernels_meet_the_parity_bar(env):
     """The kernel selections that are read from the environment once per process (VT_CONVT=0: activation-resident conv
     at C = 256, VT_PAIR_TR=0: untransposed pair kernel at C = 128, VT_PAIR64=0 / all: tap-paired pair kernel at C = 64
@@ -350,7 +351,7 @@ def test_alternative_kernels_meet_the_parity_bar(env):
     cluster, VT_WSCALE=1: power-of-two weight-row scales on EVERY layer - by default only layers with out-of-range rows
     get them, VT_PAIR3=0: the last pairs of a stage's three ResBlocks as three launches with a running mean in HBM
     instead of the mean-fused launch, VT_PAIR3=64: mean-fused at C = 64 only, VT_TC_DBG=1024: the transposed epilogues
-    without their full-block fast paths) are alternative implementations of the same arithmetic; run them in a fresh process and hold them to the
+    without their full-block fast paths, VT_PAIR3_ORDER=0: the subs of the C = 128 mean-fused launch in ascending kernel size) are alternative implementations of the same arithmetic; run them in a fresh process and hold them to the
     same waveform bar."""
     import os
     import subprocess
