@@ -300,7 +300,7 @@ int launch_plain(const ConvArgs& a, const void* wtc, uint32_t idesc, int grid, c
 }  // namespace tc
 
 // Which compiled instance a layer maps to (0 = none): 1..3 ResBlock C=64/128/256, 4..6 the three
-// transposed convs, 7 conv_post, 8 conv_pre.
+// transposed convs, 7 conv_post (C = 64), 8 conv_pre, 9 conv_post at C = 128 (two-stage generators: CosyVoice-300M).
 static int tc_instance(const ConvLayer& L) {
   if (L.stride != 1 || L.pad > kGap) return 0;
   if (L.out_mul == 1 && L.cin == L.cout && (L.k - 1) * L.dil <= 50) {
@@ -315,6 +315,7 @@ static int tc_instance(const ConvLayer& L) {
   }
   if (L.out_mul == 1 && L.cin == 64 && L.cout == 32 && (L.k - 1) * L.dil <= 6) return 7;
   if (L.out_mul == 1 && L.cin == 128 && L.cout == 512 && (L.k - 1) * L.dil <= 6) return 8;
+  if (L.out_mul == 1 && L.cin == 128 && L.cout == 32 && (L.k - 1) * L.dil <= 6) return 9;   // conv_post of a two-stage generator
   return 0;
 }
 
@@ -328,6 +329,7 @@ static int tc_nt(int inst) {
     case 6: return 64;
     case 7: return 32;
     case 8: return 128;
+    case 9: return 32;
   }
   return 0;
 }
@@ -336,7 +338,7 @@ bool conv_tc_supported(const ConvLayer& L) { return tc_instance(L) != 0; }
 
 int conv_tc_tile_rows(const ConvLayer& L) {
   const int inst = tc_instance(L);
-  return (inst == 1 || inst == 2 || inst == 7) ? 256 : 128;
+  return (inst == 1 || inst == 2 || inst == 7 || inst == 9) ? 256 : 128;
 }
 
 // [k][cin][cout] fp32 -> per (column tile nt, tap j, 64-channel block cb) the shared-memory image
@@ -409,6 +411,7 @@ static int launch_conv_tc_t(const ConvArgs& a, const ConvLayer& L, int inst, uin
     case 16: return tc::launch_plain<128, 64, 1, 2, 3, 4, 2, ActT>(a, L.w_tc, idesc, grid, st);  // 110 KB: two CTAs per SM
     case 17: return tc::launch_plain<64, 32, 2, 2, 4, 4, 6, ActT>(a, L.w_tc, idesc, grid, st);   // 102 KB: two CTAs per SM
     case 8: return tc::launch_plain<128, 128, 1, 2, 4, 4, 6, ActT>(a, L.w_tc, idesc, grid, st);
+    case 9: return tc::launch_plain<128, 32, 2, 2, 4, 4, 6, ActT>(a, L.w_tc, idesc, grid, st);   // CosyVoice-300M conv_post (128 -> 18)
   }
   VT_REQUIRE(false, "conv_tc: layer %s has no tensor-core instance", L.name.c_str());
   return VT_OK;
