@@ -75,7 +75,9 @@ def cpu_model() -> str:
 
 
 class ClockSampler:
-    """nvidia-smi sampled DURING the timed region (profiling recipe's clocks line)."""
+    """SM clock, power and throttle reasons sampled DURING the timed region (profiling recipe's clocks line): through NVML
+    every 5 ms when pynvml is importable (the timed region of the default run is ~140 ms: nvidia-smi's 100 ms loop sees it
+    once or twice), else the recipe's nvidia-smi loop."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -84,8 +86,43 @@ class ClockSampler:
         self.idx = gpu_index
         self.rows = []
         self.p = None
+        self.nv = None          # (pynvml module, device handle) when NVML is usable: ~200 samples per second instead of 10
+        self._stop = threading.Event()
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:                    # CUDA ordinal -> NVML device through the PCI address (CUDA_VISIBLE_DEVICES may renumber)
+            import torch
+            pr = torch.cuda.get_device_properties(self.idx)
+            bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            return pynvml, pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:       # noqa: BLE001  (older torch without the PCI fields)
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+
+    def _poll_nvml(self):
+        nv, h = self.nv
+        R = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+             "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        while not self._stop.is_set():
+            try:
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append([str(self.idx), str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(mx),
+                                  str(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)] +
+                                 ["Active" if mask & bit else "Not Active" for bit in R.values()])
+            except Exception:   # noqa: BLE001
+                pass
+            self._stop.wait(0.005)
 
     def start(self):
+        try:
+            self.nv = self._nvml_handle()
+            self.t = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.t.start()
+            return
+        except Exception:       # noqa: BLE001  (no pynvml / NVML refused: the nvidia-smi loop of the profiling recipe)
+            self.nv = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                        "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
@@ -99,13 +136,17 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
-        if not self.p:
+        if self.nv:
+            self._stop.set()
+            self.t.join(timeout=2)
+        elif not self.p:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.p.kill()
+        else:
+            self.p.terminate()
+            try:
+                self.p.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.p.kill()
         sm, mx, pw, reasons = [], [], [], set()
         for r in self.rows:
             if len(r) < 8:
@@ -123,7 +164,7 @@ class ClockSampler:
         thr = (max(pw) + min(pw)) / 2 if pw else 0
         load = [s for s, p in zip(sm, pw) if p >= thr] or sm
         return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "power_w_max": max(pw), "samples": len(sm)}
+                "power_w_max": max(pw), "samples": len(sm), "sampler": "nvml" if self.nv else "nvidia-smi"}
 
 
 def peaks():
