@@ -191,18 +191,6 @@ __global__ void __launch_bounds__(kP64Warps * 32, 1) k_pair64_tc(const ConvArgs 
         if (pt == 0) trace_ev(a.trace, ti, 0);
       }
       if (g + 1 < total) load_slab(wa, wb, slot_nxt);
-      // The current slab has been in registers since the previous step: its ring slot is released BEFORE the conversion,
-      // not after it - the refill gets a whole conversion (~900 cycles) more to arrive (the role trace showed 3.2-4 k of
-      // the 11.4 k producer cycles of a tile waiting on the ring).  The empty asm makes every loaded register an input, so
-      // the arrive is ordered after the last load has landed.  VT_TC_DBG=4096: release after the conversion (A/B).
-      const bool early = !(a.dbg & 4096);
-      if (early) {
-#pragma unroll
-        for (int t = 0; t < TPS; ++t)
-          asm volatile("" ::"f"(va[t].x), "f"(va[t].y), "f"(va[t].z), "f"(va[t].w), "f"(vb[t].x), "f"(vb[t].y), "f"(vb[t].z), "f"(vb[t].w));
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&x_empty[slot_cur]);
-      }
 #pragma unroll
       for (int t = 0; t < TPS; ++t) {
         const int r = sl * kP64SlabRows + r_in + t * RPP;
@@ -219,7 +207,7 @@ __global__ void __launch_bounds__(kP64Warps * 32, 1) k_pair64_tc(const ConvArgs 
         }
       }
       __syncwarp();
-      if (!early && lane == 0) mbar_arrive(&x_empty[slot_cur]);
+      if (lane == 0) mbar_arrive(&x_empty[slot_cur]);   // the slab is in registers and converted: the loader may refill it
       if (++sl == n_slab) {
         fence_proxy_async();
         if (pt == 0) trace_ev(a.trace, ti, 1);

@@ -275,15 +275,6 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(vb[t].x), "=f"(vb[t].y), "=f"(vb[t].z), "=f"(vb[t].w)
                        : "r"(xsrc + (uint32_t)(rr * C * 4 + cB * 4)));
         }
-        // the slab is in registers: its ring slot is released before the conversion (see vt_pair64_tc.cu; the empty asm
-        // orders the arrive after the last load has landed).  VT_TC_DBG=4096: release after the conversion (A/B).
-        const bool early = !(a.dbg & 4096);
-        if (early) {
-#pragma unroll
-          for (int t = 0; t < TPS; ++t)
-            asm volatile("" ::"f"(va[t].x), "f"(va[t].y), "f"(va[t].z), "f"(va[t].w), "f"(vb[t].x), "f"(vb[t].y), "f"(vb[t].z), "f"(vb[t].w));
-          mbar_arrive_warp(&x_empty[xs]);
-        }
 #pragma unroll
         for (int t = 0; t < TPS; ++t) {
           const int r = sl * SLAB_ROWS + r_in + t * RPP;
@@ -299,7 +290,7 @@ k_pair_tc(const ConvArgs a, const PairArgs p, const uint32_t idesc) {
             asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(rowb + blkB + ((chkB ^ swz) << 4) + halfB), "r"(pb.x), "r"(pb.y) : "memory");
           }
         }
-        if (!early) mbar_arrive_warp(&x_empty[xs]);      // the slab has been read: the loader may refill it
+        mbar_arrive_warp(&x_empty[xs]);                  // the slab has been read: the loader may refill it
         if (++xs == (uint32_t)NSLAB) { xs = 0; xph ^= 1u; }
       }
       fence_proxy_async();
