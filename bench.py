@@ -87,6 +87,8 @@ class ClockSampler:
         self.rows = []
         self.p = None
         self.nv = None          # (pynvml module, device handle) when NVML is usable: ~200 samples per second instead of 10
+        self.extra = set()      # throttle reasons beyond the four of the profiling recipe's query (NVML sampler)
+        self.first = 0          # first sample of the timed region (mark())
         self._stop = threading.Event()
 
     def _nvml_handle(self):
@@ -104,6 +106,12 @@ class ClockSampler:
         nv, h = self.nv
         R = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
              "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        # every other reason NVML knows (GPU idle excepted) is reported under its own name: a clock below the maximum
+        # should never appear without the reason the driver gives for it
+        other = {"hw_power_brake_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0),
+                 "sync_boost": getattr(nv, "nvmlClocksThrottleReasonSyncBoost", 0),
+                 "applications_clocks_setting": getattr(nv, "nvmlClocksThrottleReasonApplicationsClocksSetting", 0),
+                 "display_clock_setting": getattr(nv, "nvmlClocksThrottleReasonDisplayClockSetting", 0)}
         mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
         while not self._stop.is_set():
             try:
@@ -111,6 +119,9 @@ class ClockSampler:
                 self.rows.append([str(self.idx), str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(mx),
                                   str(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)] +
                                  ["Active" if mask & bit else "Not Active" for bit in R.values()])
+                for name, bit in other.items():
+                    if bit and mask & bit:
+                        self.extra.add(name)
             except Exception:   # noqa: BLE001
                 pass
             self._stop.wait(0.005)
@@ -131,6 +142,10 @@ class ClockSampler:
         except OSError:
             self.p = None
 
+    def mark(self):
+        """The timed region starts here: clocks and power are reported from the samples taken after this call."""
+        self.first = len(self.rows)
+
     def _read(self):
         for line in self.p.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
@@ -148,21 +163,26 @@ class ClockSampler:
             except subprocess.TimeoutExpired:
                 self.p.kill()
         sm, mx, pw, reasons = [], [], [], set()
+        timed = self.rows[self.first:] if len(self.rows) > self.first else self.rows
         for r in self.rows:
+            if len(r) < 8:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        for r in timed:
             if len(r) < 8:
                 continue
             try:
                 sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         # "under load": samples in the upper half of the observed power range
         thr = (max(pw) + min(pw)) / 2 if pw else 0
         load = [s for s, p in zip(sm, pw) if p >= thr] or sm
+        reasons |= self.extra
         return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
                 "power_w_max": max(pw), "samples": len(sm), "sampler": "nvml" if self.nv else "nvidia-smi"}
 
@@ -487,12 +507,15 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
-        step_device(i)
-    barrier()
+    # the sampler runs from the warm-up on: throttle reasons are collected over warm-up + timed region (the power-cap flag of
+    # a ~140 ms timed region is not always set while one of its samples is taken), clocks and power over the timed region
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for i in range(args.warmup):
+        step_device(i)
+    barrier()
+    sampler.mark()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches = 0
     prof = {"total_ms": 0.0, "resblock_ms": 0.0, "resblock_flops": 0.0, "resblock_launches": 0}
