@@ -162,9 +162,17 @@ class ClockSampler:
                 self.p.wait(timeout=5)
             except subprocess.TimeoutExpired:
                 self.p.kill()
+        out = self.summarize(self.rows, self.first, self.extra)
+        out["sampler"] = "nvml" if self.nv else "nvidia-smi"
+        return out
+
+    @staticmethod
+    def summarize(rows, first, extra=()):
+        """rows: [index, sm MHz, max sm MHz, power W, hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap]
+        as strings (the nvidia-smi query order); clocks and power from rows[first:], throttle reasons from every row."""
         sm, mx, pw, reasons = [], [], [], set()
-        timed = self.rows[self.first:] if len(self.rows) > self.first else self.rows
-        for r in self.rows:
+        timed = rows[first:] if len(rows) > first else rows
+        for r in rows:
             if len(r) < 8:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
@@ -182,9 +190,9 @@ class ClockSampler:
         # "under load": samples in the upper half of the observed power range
         thr = (max(pw) + min(pw)) / 2 if pw else 0
         load = [s for s, p in zip(sm, pw) if p >= thr] or sm
-        reasons |= self.extra
+        reasons |= set(extra)
         return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "power_w_max": max(pw), "samples": len(sm), "sampler": "nvml" if self.nv else "nvidia-smi"}
+                "power_w_max": max(pw), "samples": len(sm)}
 
 
 def peaks():

@@ -113,3 +113,26 @@ def test_algorithmic_flops_per_frame_matches_survey():
         total += 2.0 * cin * cout * k * n
     total += 2 * 512   # classifier
     assert abs(total - algorithmic_flops_per_frame()) < 1.0
+
+
+def test_bench_clock_summary_uses_timed_samples_and_all_reasons():
+    """bench.py's clocks object: SM clock / power from the samples of the timed region only, throttle reasons from the
+    warm-up too (the power-cap flag is not always up while a sample of a ~140 ms region is taken)."""
+    import importlib.util
+    from pathlib import Path
+    spec = importlib.util.spec_from_file_location("vt_bench", Path(__file__).resolve().parent.parent / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    na, ac = "Not Active", "Active"
+    rows = [["0", "1965", "1965", "210.0", na, na, na, na],        # warm-up: idle clock, no reason
+            ["0", "1700", "1965", "900.0", na, na, na, ac],        # warm-up: capped
+            ["0", "1650", "1965", "950.0", na, na, na, na],        # timed region: the flag happens to be down
+            ["0", "1670", "1965", "960.0", na, na, na, na],
+            ["0", "bad", "1965", "960.0", na, na, na, na],         # unparsable sample is skipped
+            ["0", "1660", "1965", "940.0", na, na, na, na]]
+    c = bench.ClockSampler.summarize(rows, 2, {"sync_boost"})
+    assert c["sm_mhz"] == 1660.0 and c["sm_max_mhz"] == 1965.0 and c["samples"] == 3
+    assert c["reasons"] == ["sw_power_cap", "sync_boost"] and c["power_w_max"] == 960.0
+    assert bench.ClockSampler.summarize([], 0)["reasons"] == ["no samples"]
+    # no mark (or a mark past the end): every sample counts
+    assert bench.ClockSampler.summarize(rows[:2], 5)["samples"] == 2
